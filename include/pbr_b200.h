@@ -1,0 +1,148 @@
+/*
+ * pbr_b200.h -- C ABI of libpbr_b200.so, the B200 (sm_100a) replacement for the reference's
+ * OpenCL device layer.
+ *
+ * The reference reaches its device through the C++ class `CL` (source/CL.h:20-83, source/CL.cpp),
+ * a thin wrapper over the OpenCL 1.1 C API, and runs exactly one kernel, `pathTracing`
+ * (source/opencl/pathtracing.cl:207-334).  Every entry point below names the `CL` method (and the
+ * OpenCL call underneath it) that it replaces.  A header-only `CL` shim with the reference's method
+ * names (physically-based-rendering_b200/host/CL.h) forwards to these, so the reference's
+ * PathTracer code binds to this library without changes to its call sites; INTEGRATION.md shows
+ * the binding a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - plain C: opaque context pointer, 64-bit handles, raw pointers + sizes.  No torch / CUDA types.
+ *   - every function returns 0 on success, else a non-zero code (cudaError_t value, or
+ *     PBR_ERR_* below); pbr_last_error(ctx) returns the message.  The `CL` shim maps failures to
+ *     the reference's behaviour (log "[OpenCL] Error in function ..." and continue, or
+ *     exit(EXIT_FAILURE) where the reference does: CL.cpp:73-79,209-211,347-350,438-448,523-566).
+ *   - host pointers are borrowed for the duration of a call; the context owns all device memory
+ *     and every handle dies with pbr_destroy (reference: CL::~CL, CL.cpp:30-52).
+ *   - one host thread per context; device work is issued on one CUDA stream per context and is
+ *     asynchronous until pbr_finish / pbr_image_read / pbr_buffer_read.
+ *   - there is NO CPU fallback: without a CUDA device pbr_create fails.
+ */
+#ifndef PBR_B200_H
+#define PBR_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#include "pbr_types.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct pbr_ctx pbr_ctx;
+typedef uint64_t pbr_mem;      /* stands in for cl_mem    (buffer or image) */
+typedef uint64_t pbr_kernel;   /* stands in for cl_kernel */
+
+#define PBR_OK 0
+#define PBR_ERR_INVALID 10001      /* bad handle / argument          (CL_INVALID_*)            */
+#define PBR_ERR_NO_DEVICE 10002    /* no usable CUDA device          (CL_DEVICE_NOT_FOUND)     */
+#define PBR_ERR_NOT_READY 10003    /* launch before program/args set (CL_INVALID_KERNEL_ARGS)  */
+#define PBR_ERR_UNSUPPORTED 10004  /* define / kernel name not known (CL_INVALID_KERNEL_NAME)  */
+
+/* ---- context ------------------------------------------------------------------------------- */
+
+/* CL::CL() -> getDefaultPlatform / getDefaultDevice / initContext / initCommandQueue
+ * (CL.cpp:10-24, 338-473, 513-547).  device = CUDA ordinal, -1 = current device. */
+int pbr_create(int device, pbr_ctx** out);
+/* CL::~CL() (CL.cpp:30-52): releases every buffer, image, kernel and the stream. */
+int pbr_destroy(pbr_ctx* ctx);
+const char* pbr_last_error(pbr_ctx* ctx);
+/* Device name and SM count (CL::getDefaultDevice debug dump, CL.cpp:377-419). */
+int pbr_device_info(pbr_ctx* ctx, char* name, size_t name_len, int* sm_count, size_t* total_mem);
+
+/* ---- buffers and images -------------------------------------------------------------------- */
+
+/* CL::createBuffer<T>(vector<T>, bytes) = clCreateBuffer(READ_ONLY|COPY_HOST_PTR) (CL.h:26-33). */
+int pbr_buffer_create(pbr_ctx* ctx, const void* host, size_t bytes, pbr_mem* out);
+/* CL::createEmptyBuffer(size, flags) (CL.cpp:136-144). */
+int pbr_buffer_create_empty(pbr_ctx* ctx, size_t bytes, pbr_mem* out);
+/* CL::updateBuffer(buffer, size, data) = clEnqueueWriteBuffer, blocking (CL.cpp:715-728). */
+int pbr_buffer_update(pbr_ctx* ctx, pbr_mem buf, size_t bytes, const void* host);
+/* Additive: read a buffer back (tests). */
+int pbr_buffer_read(pbr_ctx* ctx, pbr_mem buf, size_t bytes, void* host);
+/* CL::createImage2DReadOnly(w,h,data) / createImage2DWriteOnly(w,h): CL_RGBA / CL_FLOAT 2-D images
+ * (CL.cpp:153-197).  host may be NULL (write-only image, zero-filled). */
+int pbr_image_create(pbr_ctx* ctx, size_t width, size_t height, const float* host, pbr_mem* out);
+/* CL::updateImageReadOnly = clEnqueueWriteImage, blocking (CL.cpp:738-753). */
+int pbr_image_write(pbr_ctx* ctx, pbr_mem image, size_t width, size_t height, const float* host);
+/* CL::readImageOutput = clEnqueueReadImage, blocking (CL.cpp:581-594). */
+int pbr_image_read(pbr_ctx* ctx, pbr_mem image, size_t width, size_t height, float* host);
+/* Additive: device-side copy src -> dst.  Replaces the per-frame host round trip
+ * readImageOutput(imageOut) ; updateImageReadOnly(imageIn) of PathTracer::generateImage
+ * (PathTracer.cpp:61-66) when the host copy has not been modified in between. */
+int pbr_image_copy(pbr_ctx* ctx, pbr_mem dst, pbr_mem src);
+/* Additive: raw device pointer of a buffer / image (zero-copy interop with a caller that already
+ * owns device memory or wants to run a collective on the accumulation buffer). */
+int pbr_mem_device_ptr(pbr_ctx* ctx, pbr_mem mem, void** dev_ptr, size_t* bytes);
+/* CL::freeBuffers (CL.cpp:322-331). */
+int pbr_free_buffers(pbr_ctx* ctx);
+/* Additive: pinned host memory so image reads/writes run at full PCIe rate. */
+int pbr_host_alloc(pbr_ctx* ctx, size_t bytes, void** out);
+int pbr_host_free(pbr_ctx* ctx, void* ptr);
+
+/* ---- program ------------------------------------------------------------------------------- */
+
+/* CL::setReplacement("#NAME#", value) (CL.cpp:615-617).  Accepted names (with or without the
+ * surrounding '#'): BVH_NUM_NODES, NUM_LIGHTS, SKY_LIGHT ("(float4)( r, g, b, 0.0f )"). */
+int pbr_set_define(pbr_ctx* ctx, const char* name, const char* value);
+/* CL::loadProgram(path) = combineParts + setValues + clCreateProgramWithSource + buildProgram
+ * (CL.cpp:554-571, 107-127, 626-705, 58-80).  There is no source to compile: the values that
+ * CL::setValues splices into pt_header.cl arrive in `defines` (bvh_num_nodes / num_lights /
+ * sky_light are overridden by earlier pbr_set_define calls) and select a precompiled sm_100a
+ * kernel specialisation. */
+int pbr_program_load(pbr_ctx* ctx, const pbr_defines* defines);
+/* CL::createKernel(name) (CL.cpp:205-217).  Only "pathTracing" exists. */
+int pbr_kernel_get(pbr_ctx* ctx, const char* name, pbr_kernel* out);
+/* CL::setKernelArg(kernel, index, size, data) = clSetKernelArg (CL.cpp:604-607), with the 14-slot
+ * signature of the reference kernel (pathtracing.cl:207-234, PathTracer.cpp:88-125):
+ *   0 float seed, 1 float pixelWeight, 2 float pxDim, 3 pbr_camera (80 B), 4 bvh, 5 facesV,
+ *   6 facesN, 7 vertices, 8 normals, 9 materials, 10 lights, 11 imageIn, 12 imageOut,
+ *   13 imageDebug -- slots 4..13 take a pbr_mem (size 8). */
+int pbr_kernel_set_arg(pbr_ctx* ctx, pbr_kernel k, uint32_t index, size_t size, const void* data);
+/* CL::execute(kernel) = clEnqueueNDRangeKernel over window.width x window.height (CL.cpp:289-306).
+ * opencl.localgroupsize has no meaning here and is ignored. */
+int pbr_kernel_launch(pbr_ctx* ctx, pbr_kernel k);
+/* CL::finish() = clFlush + clFinish (CL.cpp:312-316). */
+int pbr_finish(pbr_ctx* ctx);
+/* CL::getKernelTimes()[kernel] (CL.cpp:480-506): device time of the last launch in ms. */
+int pbr_kernel_time_ms(pbr_ctx* ctx, pbr_kernel k, double* ms);
+
+/* ---- additive entry points --------------------------------------------------- */
+
+/* Restrict launches to image rows [y0, y1) -- tile sharding across GPUs. Default: all. */
+int pbr_set_tile(pbr_ctx* ctx, int32_t y0, int32_t y1);
+/* Choose the device pipeline: 0 = wavefront (default), 1 = one-thread-per-pixel megakernel
+ * (the reference's launch structure; kept as an on-device cross-check). */
+int pbr_set_pipeline(pbr_ctx* ctx, int32_t mode);
+/* Skip the imageDebug write (the counters are still available through pbr_stats). */
+int pbr_set_debug_image(pbr_ctx* ctx, int32_t enabled);
+/* Counters accumulated since the last call with reset != 0:
+ *   [0] traverse() calls  [1] traverseShadows() calls  [2] BVH nodes visited by traverse()
+ *   [3] triangle tests    [4] shaded hits              [5] BVH nodes visited by traverseShadows()
+ * These are the inputs of the algorithmic-byte formula of SURVEY.md 8d. */
+int pbr_stats(pbr_ctx* ctx, uint64_t out[6], int32_t reset);
+
+/* Explicit rays (BASELINE config 5).  `rays`/`hits` are HOST arrays of n elements; the scene is
+ * given by buffer handles in the reference layout.  any_hit = 0: traverse() (closest hit,
+ * pt_bvh.cl:82-123); any_hit = 1: traverseShadows() (pt_bvh.cl:133-177).  lights may be 0. */
+int pbr_trace(pbr_ctx* ctx, pbr_mem bvh, pbr_mem facesV, pbr_mem vertices, pbr_mem lights, int32_t num_lights,
+              const pbr_ray* rays, int64_t n, int32_t any_hit, pbr_hit* hits);
+/* Same, rays and hits already resident: device pointers (from pbr_mem_device_ptr). */
+int pbr_trace_device(pbr_ctx* ctx, pbr_mem bvh, pbr_mem facesV, pbr_mem vertices, pbr_mem lights, int32_t num_lights,
+                     pbr_mem rays, int64_t n, int32_t any_hit, pbr_mem hits);
+
+/* Pinned-math probes: evaluate include/pbr_pinned_math.h ON THE DEVICE (op: 0 sin 1 cos 2 tan
+ * 3 acos 4 atan 5 pow(x,y) 6 cbrt 7 rand-seed-step) for n host inputs -- used to prove the
+ * device and host agree bit for bit. */
+int pbr_pinned_math_eval(pbr_ctx* ctx, int32_t op, const float* x, const float* y, int64_t n, float* out);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* PBR_B200_H */

@@ -1,0 +1,680 @@
+/*
+ * pbr_capi.cu -- implementation of the C ABI declared in include/pbr_b200.h.
+ *
+ * Stands where the reference's `CL` class (source/CL.cpp) stands: owns the device, the buffers and
+ * images, the "program" (a set of precompiled sm_100a kernel specialisations selected by the values
+ * the reference would splice into pt_header.cl) and the one kernel `pathTracing` with its 14
+ * argument slots (PathTracer.cpp:88-125).  No CPU fallback: every entry point needs a CUDA device.
+ */
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <string>
+#include <vector>
+
+#include "../../include/pbr_b200.h"
+#include "pt_kernels.cuh"
+
+using namespace ptk;
+
+namespace {
+
+struct Mem {
+	void* dptr = nullptr;
+	size_t bytes = 0;
+	bool image = false;
+	size_t width = 0, height = 0;
+	bool alive = false;
+};
+
+struct KernelArgs {
+	float seed = 0.0f, pixelWeight = 0.0f, pxDim = 0.0f;
+	pbr_camera cam;
+	pbr_mem mem[14] = {0};
+	uint32_t setMask = 0;
+};
+
+} /* namespace */
+
+struct pbr_ctx {
+	int device = 0;
+	int smCount = 0;
+	cudaStream_t stream = nullptr;
+	cudaEvent_t evStart = nullptr, evStop = nullptr;
+	bool timed = false;
+	std::string lastError;
+	std::vector<Mem> mems;
+	std::vector<void*> pinned;
+
+	/* program */
+	bool programLoaded = false;
+	pbr_defines defines;
+	bool haveNumNodes = false, haveNumLights = false, haveSky = false;
+	int defNumNodes = 0, defNumLights = 0;
+	pbr_float4 defSky;
+
+	KernelArgs args;
+	int tileY0 = -1, tileY1 = -1;
+	int pipeline = 0;
+	bool debugImage = true;
+
+	/* repacked scene cache */
+	float4* nodes = nullptr;
+	float4* tris = nullptr;
+	size_t nodesCap = 0, trisCap = 0;
+	pbr_mem cacheBvh = 0, cacheFacesV = 0, cacheVertices = 0;
+	int cacheNumNodes = -1;
+	uint64_t sceneEpoch = 0, cacheEpoch = ~0ull;
+	int numNodesDev = 0;
+
+	/* wavefront state */
+	WaveState wave = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+	QueueCtl qctl = {nullptr, {nullptr, nullptr}};
+	size_t waveCap = 0;
+
+	unsigned long long* stats = nullptr;       /* 6 counters */
+	unsigned long long* cursor64 = nullptr;    /* work cursor of traceRaysKernel */
+};
+
+namespace {
+
+int fail(pbr_ctx* ctx, int code, const std::string& msg) {
+	if (ctx) ctx->lastError = msg;
+	return code;
+}
+
+int cudaFail(pbr_ctx* ctx, cudaError_t e, const char* what) {
+	if (e == cudaSuccess) return PBR_OK;
+	std::string m = std::string(what) + ": " + cudaGetErrorString(e);
+	if (ctx) ctx->lastError = m;
+	return (int) e;
+}
+
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return cudaFail(ctx, e_, #call); } while (0)
+
+Mem* getMem(pbr_ctx* ctx, pbr_mem h) {
+	if (h == 0 || h > ctx->mems.size()) return nullptr;
+	Mem* m = &ctx->mems[h - 1];
+	return m->alive ? m : nullptr;
+}
+
+int newMem(pbr_ctx* ctx, size_t bytes, pbr_mem* out, Mem** mp) {
+	Mem m;
+	m.bytes = bytes;
+	m.alive = true;
+	cudaError_t e = cudaMalloc(&m.dptr, bytes > 0 ? bytes : 16);
+	if (e != cudaSuccess) return cudaFail(ctx, e, "cudaMalloc");
+	ctx->mems.push_back(m);
+	*out = (pbr_mem) ctx->mems.size();
+	if (mp) *mp = &ctx->mems.back();
+	ctx->sceneEpoch++;
+	return PBR_OK;
+}
+
+int gridFor(long long n, int block) { return (int) ((n + block - 1) / block); }
+
+/* Rebuild the repacked node / triangle arrays when the bound buffers or BVH_NUM_NODES changed. */
+int ensureScene(pbr_ctx* ctx, pbr_mem hBvh, pbr_mem hFacesV, pbr_mem hVertices, int numNodes) {
+	if (ctx->cacheBvh == hBvh && ctx->cacheFacesV == hFacesV && ctx->cacheVertices == hVertices &&
+	    ctx->cacheNumNodes == numNodes && ctx->cacheEpoch == ctx->sceneEpoch) {
+		return PBR_OK;
+	}
+	Mem* bvh = getMem(ctx, hBvh);
+	Mem* facesV = getMem(ctx, hFacesV);
+	Mem* vertices = getMem(ctx, hVertices);
+	if (!bvh || !facesV || !vertices) return fail(ctx, PBR_ERR_INVALID, "pathTracing: bvh / facesV / vertices argument is not a live buffer");
+
+	const int numSrcNodes = (int) (bvh->bytes / sizeof(pbr_bvh_node));
+	if (numNodes > numSrcNodes) return fail(ctx, PBR_ERR_INVALID, "BVH_NUM_NODES exceeds the size of the bvh buffer");
+	if (numNodes > (1 << 24)) return fail(ctx, PBR_ERR_INVALID, "BVH_NUM_NODES exceeds 2^24: float-encoded indices are no longer exact");
+	const int numFaces = (int) (facesV->bytes / sizeof(pbr_uint4));
+	const int numVertices = (int) (vertices->bytes / sizeof(pbr_float4));
+	const int numDst = numNodes < 2 ? 2 : numNodes;
+
+	if ((size_t) numDst > ctx->nodesCap) {
+		if (ctx->nodes) cudaFree(ctx->nodes);
+		ctx->nodes = nullptr;
+		CK(cudaMalloc(&ctx->nodes, (size_t) numDst * 32));
+		ctx->nodesCap = (size_t) numDst;
+	}
+	if ((size_t) numFaces > ctx->trisCap || !ctx->tris) {
+		if (ctx->tris) cudaFree(ctx->tris);
+		ctx->tris = nullptr;
+		CK(cudaMalloc(&ctx->tris, (size_t) (numFaces > 0 ? numFaces : 1) * 48));
+		ctx->trisCap = (size_t) numFaces;
+	}
+	repackNodesKernel<<<gridFor(numDst, 256), 256, 0, ctx->stream>>>((const float4*) bvh->dptr, numNodes, ctx->nodes, numDst);
+	if (numFaces > 0 && numVertices > 0) {
+		repackTrisKernel<<<gridFor(numFaces, 256), 256, 0, ctx->stream>>>(
+			(const uint4*) facesV->dptr, numFaces, (const float4*) vertices->dptr, numVertices, ctx->tris);
+	}
+	CK(cudaGetLastError());
+	ctx->cacheBvh = hBvh; ctx->cacheFacesV = hFacesV; ctx->cacheVertices = hVertices;
+	ctx->cacheNumNodes = numNodes;
+	ctx->cacheEpoch = ctx->sceneEpoch;
+	ctx->numNodesDev = numNodes;
+	return PBR_OK;
+}
+
+int ensureWave(pbr_ctx* ctx, size_t nPaths) {
+	if (nPaths <= ctx->waveCap) return PBR_OK;
+	WaveState& W = ctx->wave;
+	cudaFree(W.rayO); cudaFree(W.rayD); cudaFree(W.colS); cudaFree(W.finF); cudaFree(W.misc); cudaFree(W.dbg);
+	cudaFree(ctx->qctl.queue[0]); cudaFree(ctx->qctl.queue[1]);
+	W = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+	ctx->qctl.queue[0] = ctx->qctl.queue[1] = nullptr;
+	ctx->waveCap = 0;
+	CK(cudaMalloc(&W.rayO, nPaths * 16));
+	CK(cudaMalloc(&W.rayD, nPaths * 16));
+	CK(cudaMalloc(&W.colS, nPaths * 16));
+	CK(cudaMalloc(&W.finF, nPaths * 16));
+	CK(cudaMalloc(&W.misc, nPaths * 16));
+	CK(cudaMalloc(&W.dbg, nPaths * 8));
+	CK(cudaMalloc(&ctx->qctl.queue[0], nPaths * 4));
+	CK(cudaMalloc(&ctx->qctl.queue[1], nPaths * 4));
+	ctx->waveCap = nPaths;
+	return PBR_OK;
+}
+
+template <int BRDF, bool SHADOW>
+int runFrame(pbr_ctx* ctx, const FrameParams& P, int nPaths) {
+	if (ctx->pipeline == 1) {
+		megaKernel<BRDF, SHADOW><<<gridFor(nPaths, 128), 128, 0, ctx->stream>>>(P, nPaths);
+		CK(cudaGetLastError());
+		return PBR_OK;
+	}
+	int rc = ensureWave(ctx, (size_t) nPaths);
+	if (rc) return rc;
+	const WaveState& W = ctx->wave;
+	const QueueCtl& Q = ctx->qctl;
+
+	int occT = 0, occS = 0;
+	CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occT, traverseKernel, 128, 0));
+	CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occS, shadeKernel<BRDF, SHADOW>, 128, 0));
+	const int gridT = ctx->smCount * (occT > 0 ? occT : 1);
+	const int gridS = ctx->smCount * (occS > 0 ? occS : 1);
+
+	raygenKernel<<<ctx->smCount * 8, 256, 0, ctx->stream>>>(P, W, Q, nPaths);
+	const int iterations = P.samples * (P.maxDepth + P.maxAddedDepth);
+	for (int it = 0; it < iterations; it++) {
+		const int in = it & 1, out = in ^ 1;
+		const uint32_t* qIn = (it == 0) ? nullptr : Q.queue[in];
+		traverseKernel<<<gridT, 128, 0, ctx->stream>>>(P.scene, W, qIn, Q.ctrl + in, Q.ctrl + 2, Q.ctrl + out, ctx->stats);
+		shadeKernel<BRDF, SHADOW><<<gridS, 128, 0, ctx->stream>>>(P, W, qIn, Q.ctrl + in, Q.queue[out], Q.ctrl + out, Q.ctrl + 2);
+	}
+	CK(cudaGetLastError());
+	return PBR_OK;
+}
+
+bool parseSky(const char* v, pbr_float4* out) {
+	/* "(float4)( %f, %f, %f, 0.0f )" (PathTracer.cpp:470-472, 515) */
+	const char* p = strstr(v, ")(");
+	p = p ? p + 2 : v;
+	float r, g, b;
+	if (sscanf(p, " %f , %f , %f", &r, &g, &b) != 3) return false;
+	out->x = r; out->y = g; out->z = b; out->w = 0.0f;
+	return true;
+}
+
+} /* namespace */
+
+extern "C" {
+
+int pbr_create(int device, pbr_ctx** out) {
+	if (!out) return PBR_ERR_INVALID;
+	*out = nullptr;
+	int n = 0;
+	cudaError_t e = cudaGetDeviceCount(&n);
+	if (e != cudaSuccess || n == 0) return PBR_ERR_NO_DEVICE;
+	if (device < 0) {
+		if (cudaGetDevice(&device) != cudaSuccess) device = 0;
+	}
+	if (device >= n) return PBR_ERR_NO_DEVICE;
+	pbr_ctx* ctx = new pbr_ctx();
+	ctx->device = device;
+	if (cudaSetDevice(device) != cudaSuccess) { delete ctx; return PBR_ERR_NO_DEVICE; }
+	cudaDeviceProp prop;
+	if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete ctx; return PBR_ERR_NO_DEVICE; }
+	ctx->smCount = prop.multiProcessorCount;
+	if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return PBR_ERR_NO_DEVICE; }
+	cudaEventCreate(&ctx->evStart);
+	cudaEventCreate(&ctx->evStop);
+	if (cudaMalloc(&ctx->stats, 6 * sizeof(unsigned long long)) != cudaSuccess ||
+	    cudaMalloc(&ctx->cursor64, sizeof(unsigned long long)) != cudaSuccess ||
+	    cudaMalloc(&ctx->qctl.ctrl, 4 * sizeof(uint32_t)) != cudaSuccess) {
+		delete ctx;
+		return PBR_ERR_NO_DEVICE;
+	}
+	cudaMemset(ctx->stats, 0, 6 * sizeof(unsigned long long));
+	cudaMemset(ctx->qctl.ctrl, 0, 4 * sizeof(uint32_t));
+	memset(&ctx->defines, 0, sizeof(ctx->defines));
+	memset(&ctx->args.cam, 0, sizeof(ctx->args.cam));
+	*out = ctx;
+	return PBR_OK;
+}
+
+int pbr_destroy(pbr_ctx* ctx) {
+	if (!ctx) return PBR_ERR_INVALID;
+	cudaSetDevice(ctx->device);
+	cudaStreamSynchronize(ctx->stream);
+	for (Mem& m : ctx->mems) if (m.alive && m.dptr) cudaFree(m.dptr);
+	for (void* p : ctx->pinned) cudaFreeHost(p);
+	cudaFree(ctx->nodes); cudaFree(ctx->tris);
+	WaveState& W = ctx->wave;
+	cudaFree(W.rayO); cudaFree(W.rayD); cudaFree(W.colS); cudaFree(W.finF); cudaFree(W.misc); cudaFree(W.dbg);
+	cudaFree(ctx->qctl.queue[0]); cudaFree(ctx->qctl.queue[1]); cudaFree(ctx->qctl.ctrl);
+	cudaFree(ctx->stats); cudaFree(ctx->cursor64);
+	cudaEventDestroy(ctx->evStart); cudaEventDestroy(ctx->evStop);
+	cudaStreamDestroy(ctx->stream);
+	delete ctx;
+	return PBR_OK;
+}
+
+const char* pbr_last_error(pbr_ctx* ctx) { return ctx ? ctx->lastError.c_str() : "no context"; }
+
+int pbr_device_info(pbr_ctx* ctx, char* name, size_t name_len, int* sm_count, size_t* total_mem) {
+	if (!ctx) return PBR_ERR_INVALID;
+	cudaDeviceProp prop;
+	CK(cudaGetDeviceProperties(&prop, ctx->device));
+	if (name && name_len) { strncpy(name, prop.name, name_len - 1); name[name_len - 1] = 0; }
+	if (sm_count) *sm_count = prop.multiProcessorCount;
+	if (total_mem) *total_mem = prop.totalGlobalMem;
+	return PBR_OK;
+}
+
+int pbr_buffer_create(pbr_ctx* ctx, const void* host, size_t bytes, pbr_mem* out) {
+	if (!ctx || !out) return PBR_ERR_INVALID;
+	CK(cudaSetDevice(ctx->device));
+	Mem* m;
+	int rc = newMem(ctx, bytes, out, &m);
+	if (rc) return rc;
+	if (host && bytes) {
+		CK(cudaMemcpyAsync(m->dptr, host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+		CK(cudaStreamSynchronize(ctx->stream));
+	}
+	return PBR_OK;
+}
+
+int pbr_buffer_create_empty(pbr_ctx* ctx, size_t bytes, pbr_mem* out) {
+	if (!ctx || !out) return PBR_ERR_INVALID;
+	CK(cudaSetDevice(ctx->device));
+	Mem* m;
+	int rc = newMem(ctx, bytes, out, &m);
+	if (rc) return rc;
+	CK(cudaMemsetAsync(m->dptr, 0, bytes > 0 ? bytes : 16, ctx->stream));
+	return PBR_OK;
+}
+
+int pbr_buffer_update(pbr_ctx* ctx, pbr_mem buf, size_t bytes, const void* host) {
+	if (!ctx) return PBR_ERR_INVALID;
+	Mem* m = getMem(ctx, buf);
+	if (!m || bytes > m->bytes || !host) return fail(ctx, PBR_ERR_INVALID, "pbr_buffer_update: bad buffer or size");
+	CK(cudaSetDevice(ctx->device));
+	CK(cudaMemcpyAsync(m->dptr, host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+	CK(cudaStreamSynchronize(ctx->stream));
+	ctx->sceneEpoch++;
+	return PBR_OK;
+}
+
+int pbr_buffer_read(pbr_ctx* ctx, pbr_mem buf, size_t bytes, void* host) {
+	if (!ctx) return PBR_ERR_INVALID;
+	Mem* m = getMem(ctx, buf);
+	if (!m || bytes > m->bytes || !host) return fail(ctx, PBR_ERR_INVALID, "pbr_buffer_read: bad buffer or size");
+	CK(cudaSetDevice(ctx->device));
+	CK(cudaMemcpyAsync(host, m->dptr, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+	CK(cudaStreamSynchronize(ctx->stream));
+	return PBR_OK;
+}
+
+int pbr_image_create(pbr_ctx* ctx, size_t width, size_t height, const float* host, pbr_mem* out) {
+	if (!ctx || !out || width == 0 || height == 0) return PBR_ERR_INVALID;
+	CK(cudaSetDevice(ctx->device));
+	const size_t bytes = width * height * 16;
+	Mem* m;
+	int rc = newMem(ctx, bytes, out, &m);
+	if (rc) return rc;
+	m->image = true; m->width = width; m->height = height;
+	if (host) {
+		CK(cudaMemcpyAsync(m->dptr, host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+		CK(cudaStreamSynchronize(ctx->stream));
+	}
+	else {
+		CK(cudaMemsetAsync(m->dptr, 0, bytes, ctx->stream));
+	}
+	return PBR_OK;
+}
+
+int pbr_image_write(pbr_ctx* ctx, pbr_mem image, size_t width, size_t height, const float* host) {
+	if (!ctx) return PBR_ERR_INVALID;
+	Mem* m = getMem(ctx, image);
+	if (!m || !m->image || width != m->width || height != m->height || !host)
+		return fail(ctx, PBR_ERR_INVALID, "pbr_image_write: bad image or size");
+	CK(cudaSetDevice(ctx->device));
+	CK(cudaMemcpyAsync(m->dptr, host, m->bytes, cudaMemcpyHostToDevice, ctx->stream));
+	CK(cudaStreamSynchronize(ctx->stream));
+	return PBR_OK;
+}
+
+int pbr_image_read(pbr_ctx* ctx, pbr_mem image, size_t width, size_t height, float* host) {
+	if (!ctx) return PBR_ERR_INVALID;
+	Mem* m = getMem(ctx, image);
+	if (!m || !m->image || width != m->width || height != m->height || !host)
+		return fail(ctx, PBR_ERR_INVALID, "pbr_image_read: bad image or size");
+	CK(cudaSetDevice(ctx->device));
+	CK(cudaMemcpyAsync(host, m->dptr, m->bytes, cudaMemcpyDeviceToHost, ctx->stream));
+	CK(cudaStreamSynchronize(ctx->stream));
+	return PBR_OK;
+}
+
+int pbr_image_copy(pbr_ctx* ctx, pbr_mem dst, pbr_mem src) {
+	if (!ctx) return PBR_ERR_INVALID;
+	Mem* d = getMem(ctx, dst);
+	Mem* s = getMem(ctx, src);
+	if (!d || !s || d->bytes != s->bytes) return fail(ctx, PBR_ERR_INVALID, "pbr_image_copy: bad images");
+	CK(cudaSetDevice(ctx->device));
+	CK(cudaMemcpyAsync(d->dptr, s->dptr, s->bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+	return PBR_OK;
+}
+
+int pbr_mem_device_ptr(pbr_ctx* ctx, pbr_mem mem, void** dev_ptr, size_t* bytes) {
+	if (!ctx) return PBR_ERR_INVALID;
+	Mem* m = getMem(ctx, mem);
+	if (!m) return fail(ctx, PBR_ERR_INVALID, "pbr_mem_device_ptr: bad handle");
+	if (dev_ptr) *dev_ptr = m->dptr;
+	if (bytes) *bytes = m->bytes;
+	return PBR_OK;
+}
+
+int pbr_free_buffers(pbr_ctx* ctx) {
+	if (!ctx) return PBR_ERR_INVALID;
+	cudaSetDevice(ctx->device);
+	cudaStreamSynchronize(ctx->stream);
+	for (Mem& m : ctx->mems) {
+		if (m.alive && m.dptr) cudaFree(m.dptr);
+		m.alive = false;
+		m.dptr = nullptr;
+	}
+	ctx->sceneEpoch++;
+	return PBR_OK;
+}
+
+int pbr_host_alloc(pbr_ctx* ctx, size_t bytes, void** out) {
+	if (!ctx || !out) return PBR_ERR_INVALID;
+	CK(cudaSetDevice(ctx->device));
+	CK(cudaMallocHost(out, bytes));
+	ctx->pinned.push_back(*out);
+	return PBR_OK;
+}
+
+int pbr_host_free(pbr_ctx* ctx, void* ptr) {
+	if (!ctx) return PBR_ERR_INVALID;
+	for (size_t i = 0; i < ctx->pinned.size(); i++) {
+		if (ctx->pinned[i] == ptr) {
+			cudaFreeHost(ptr);
+			ctx->pinned.erase(ctx->pinned.begin() + (long) i);
+			return PBR_OK;
+		}
+	}
+	return fail(ctx, PBR_ERR_INVALID, "pbr_host_free: unknown pointer");
+}
+
+int pbr_set_define(pbr_ctx* ctx, const char* name, const char* value) {
+	if (!ctx || !name || !value) return PBR_ERR_INVALID;
+	std::string n(name);
+	if (n.size() >= 2 && n.front() == '#' && n.back() == '#') n = n.substr(1, n.size() - 2);
+	if (n == "BVH_NUM_NODES") { ctx->defNumNodes = atoi(value); ctx->haveNumNodes = true; }
+	else if (n == "NUM_LIGHTS") { ctx->defNumLights = atoi(value); ctx->haveNumLights = true; }
+	else if (n == "SKY_LIGHT") {
+		if (!parseSky(value, &ctx->defSky)) return fail(ctx, PBR_ERR_INVALID, "SKY_LIGHT: cannot parse \"" + std::string(value) + "\"");
+		ctx->haveSky = true;
+	}
+	else return fail(ctx, PBR_ERR_UNSUPPORTED, "unknown define " + n);
+	if (ctx->programLoaded) {
+		if (ctx->haveNumNodes) ctx->defines.bvh_num_nodes = ctx->defNumNodes;
+		if (ctx->haveNumLights) ctx->defines.num_lights = ctx->defNumLights;
+		if (ctx->haveSky) ctx->defines.sky_light = ctx->defSky;
+	}
+	return PBR_OK;
+}
+
+int pbr_program_load(pbr_ctx* ctx, const pbr_defines* defines) {
+	if (!ctx || !defines) return PBR_ERR_INVALID;
+	pbr_defines d = *defines;
+	if (ctx->haveNumNodes) d.bvh_num_nodes = ctx->defNumNodes;
+	if (ctx->haveNumLights) d.num_lights = ctx->defNumLights;
+	if (ctx->haveSky) d.sky_light = ctx->defSky;
+	if (d.accel_struct != 0) return fail(ctx, PBR_ERR_UNSUPPORTED, "accel_struct: only 0 (BVH) exists");
+	if (d.brdf != 0 && d.brdf != 1) return fail(ctx, PBR_ERR_UNSUPPORTED, "render.brdf must be 0 (Schlick) or 1 (Shirley-Ashikhmin)");
+	if (d.phongtess != 0) return fail(ctx, PBR_ERR_UNSUPPORTED, "render.phong_tessellation > 0 is not implemented in the CUDA path yet");
+	if (d.img_width <= 0 || d.img_height <= 0 || d.samples <= 0 || d.max_depth < 0 || d.max_added_depth < 0)
+		return fail(ctx, PBR_ERR_INVALID, "invalid image size / samples / depth");
+	if (d.max_depth + d.max_added_depth > 0xffff) return fail(ctx, PBR_ERR_INVALID, "max_depth + max_added_depth too large");
+	ctx->defines = d;
+	ctx->programLoaded = true;
+	return PBR_OK;
+}
+
+int pbr_kernel_get(pbr_ctx* ctx, const char* name, pbr_kernel* out) {
+	if (!ctx || !name || !out) return PBR_ERR_INVALID;
+	if (strcmp(name, "pathTracing") != 0) return fail(ctx, PBR_ERR_UNSUPPORTED, std::string("no kernel named ") + name);
+	if (!ctx->programLoaded) return fail(ctx, PBR_ERR_NOT_READY, "createKernel before loadProgram");
+	*out = 1;
+	return PBR_OK;
+}
+
+int pbr_kernel_set_arg(pbr_ctx* ctx, pbr_kernel k, uint32_t index, size_t size, const void* data) {
+	if (!ctx || k != 1 || !data) return PBR_ERR_INVALID;
+	KernelArgs& a = ctx->args;
+	switch (index) {
+		case 0: if (size != 4) goto badsize; memcpy(&a.seed, data, 4); break;
+		case 1: if (size != 4) goto badsize; memcpy(&a.pixelWeight, data, 4); break;
+		case 2: if (size != 4) goto badsize; memcpy(&a.pxDim, data, 4); break;
+		case 3: if (size != sizeof(pbr_camera)) goto badsize; memcpy(&a.cam, data, sizeof(pbr_camera)); break;
+		default:
+			if (index > 13) return fail(ctx, PBR_ERR_INVALID, "pathTracing has 14 arguments");
+			if (size != sizeof(pbr_mem)) goto badsize;
+			memcpy(&a.mem[index], data, sizeof(pbr_mem));
+			break;
+	}
+	a.setMask |= (1u << index);
+	return PBR_OK;
+badsize:
+	return fail(ctx, PBR_ERR_INVALID, "clSetKernelArg: wrong argument size for slot " + std::to_string(index));
+}
+
+int pbr_kernel_launch(pbr_ctx* ctx, pbr_kernel k) {
+	if (!ctx || k != 1) return PBR_ERR_INVALID;
+	if (!ctx->programLoaded) return fail(ctx, PBR_ERR_NOT_READY, "execute before loadProgram");
+	KernelArgs& a = ctx->args;
+	if ((a.setMask & 0x3fffu) != 0x3fffu) return fail(ctx, PBR_ERR_NOT_READY, "pathTracing: not all 14 arguments are set");
+	CK(cudaSetDevice(ctx->device));
+	const pbr_defines& D = ctx->defines;
+
+	int rc = ensureScene(ctx, a.mem[4], a.mem[5], a.mem[7], D.bvh_num_nodes);
+	if (rc) return rc;
+
+	Mem* materials = getMem(ctx, a.mem[9]);
+	Mem* lights = getMem(ctx, a.mem[10]);
+	Mem* imageIn = getMem(ctx, a.mem[11]);
+	Mem* imageOut = getMem(ctx, a.mem[12]);
+	Mem* imageDebug = getMem(ctx, a.mem[13]);
+	if (!materials || !lights || !imageIn || !imageOut || !imageDebug)
+		return fail(ctx, PBR_ERR_INVALID, "pathTracing: a buffer / image argument is not live");
+	const size_t imgBytes = (size_t) D.img_width * D.img_height * 16;
+	if (imageIn->bytes < imgBytes || imageOut->bytes < imgBytes || imageDebug->bytes < imgBytes)
+		return fail(ctx, PBR_ERR_INVALID, "pathTracing: image smaller than IMG_WIDTH x IMG_HEIGHT");
+	if ((size_t) D.num_lights * sizeof(pbr_light) > lights->bytes)
+		return fail(ctx, PBR_ERR_INVALID, "NUM_LIGHTS exceeds the lights buffer");
+
+	FrameParams P;
+	P.scene.nodes = ctx->nodes;
+	P.scene.tris = ctx->tris;
+	P.scene.lights = (const pbr_light*) lights->dptr;
+	P.scene.numNodes = ctx->numNodesDev;
+	P.scene.numLights = D.num_lights;
+	P.materials = materials->dptr;
+	P.numMaterials = (int) (materials->bytes / (D.brdf == 0 ? sizeof(pbr_material_schlick) : sizeof(pbr_material_sa)));
+	P.cam = a.cam;
+	P.seed = a.seed; P.pixelWeight = a.pixelWeight; P.pxDim = a.pxDim;
+	P.width = D.img_width; P.height = D.img_height;
+	P.y0 = ctx->tileY0 < 0 ? 0 : ctx->tileY0;
+	P.y1 = ctx->tileY1 < 0 ? D.img_height : ctx->tileY1;
+	if (P.y0 < 0 || P.y1 > D.img_height || P.y0 >= P.y1) return fail(ctx, PBR_ERR_INVALID, "tile rows outside the image");
+	P.maxDepth = D.max_depth; P.maxAddedDepth = D.max_added_depth; P.samples = D.samples;
+	P.antiAliasing = D.anti_aliasing;
+	P.skyLight = make_float4(D.sky_light.x, D.sky_light.y, D.sky_light.z, D.sky_light.w);
+	P.imageIn = (const float4*) imageIn->dptr;
+	P.imageOut = (float4*) imageOut->dptr;
+	P.imageDebug = ctx->debugImage ? (float4*) imageDebug->dptr : nullptr;
+	P.stats = ctx->stats;
+
+	const int nPaths = D.img_width * (P.y1 - P.y0);
+	const bool shadow = (D.shadow_rays == 1);
+
+	CK(cudaEventRecord(ctx->evStart, ctx->stream));
+	if (D.brdf == 0) rc = shadow ? runFrame<0, true>(ctx, P, nPaths) : runFrame<0, false>(ctx, P, nPaths);
+	else rc = shadow ? runFrame<1, true>(ctx, P, nPaths) : runFrame<1, false>(ctx, P, nPaths);
+	if (rc) return rc;
+	CK(cudaEventRecord(ctx->evStop, ctx->stream));
+	ctx->timed = true;
+	return PBR_OK;
+}
+
+int pbr_finish(pbr_ctx* ctx) {
+	if (!ctx) return PBR_ERR_INVALID;
+	CK(cudaSetDevice(ctx->device));
+	CK(cudaStreamSynchronize(ctx->stream));
+	return PBR_OK;
+}
+
+int pbr_kernel_time_ms(pbr_ctx* ctx, pbr_kernel k, double* ms) {
+	if (!ctx || k != 1 || !ms) return PBR_ERR_INVALID;
+	*ms = 0.0;
+	if (!ctx->timed) return PBR_OK;
+	CK(cudaEventSynchronize(ctx->evStop));
+	float f = 0.0f;
+	CK(cudaEventElapsedTime(&f, ctx->evStart, ctx->evStop));
+	*ms = (double) f;
+	return PBR_OK;
+}
+
+int pbr_set_tile(pbr_ctx* ctx, int32_t y0, int32_t y1) {
+	if (!ctx) return PBR_ERR_INVALID;
+	ctx->tileY0 = y0;
+	ctx->tileY1 = y1;
+	return PBR_OK;
+}
+
+int pbr_set_pipeline(pbr_ctx* ctx, int32_t mode) {
+	if (!ctx || (mode != 0 && mode != 1)) return PBR_ERR_INVALID;
+	ctx->pipeline = mode;
+	return PBR_OK;
+}
+
+int pbr_set_debug_image(pbr_ctx* ctx, int32_t enabled) {
+	if (!ctx) return PBR_ERR_INVALID;
+	ctx->debugImage = enabled != 0;
+	return PBR_OK;
+}
+
+int pbr_stats(pbr_ctx* ctx, uint64_t out[6], int32_t reset) {
+	if (!ctx || !out) return PBR_ERR_INVALID;
+	CK(cudaSetDevice(ctx->device));
+	CK(cudaMemcpyAsync(out, ctx->stats, 6 * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+	if (reset) CK(cudaMemsetAsync(ctx->stats, 0, 6 * sizeof(uint64_t), ctx->stream));
+	CK(cudaStreamSynchronize(ctx->stream));
+	return PBR_OK;
+}
+
+static int traceImpl(pbr_ctx* ctx, pbr_mem bvh, pbr_mem facesV, pbr_mem vertices, pbr_mem lights, int32_t num_lights,
+                     const pbr_ray* dRays, int64_t n, int32_t any_hit, pbr_hit* dHits) {
+	Mem* b = getMem(ctx, bvh);
+	if (!b) return fail(ctx, PBR_ERR_INVALID, "pbr_trace: bad bvh buffer");
+	const int numNodes = ctx->haveNumNodes ? ctx->defNumNodes : (int) (b->bytes / sizeof(pbr_bvh_node));
+	int rc = ensureScene(ctx, bvh, facesV, vertices, numNodes);
+	if (rc) return rc;
+	SceneDev S;
+	S.nodes = ctx->nodes;
+	S.tris = ctx->tris;
+	S.numNodes = ctx->numNodesDev;
+	S.numLights = 0;
+	S.lights = nullptr;
+	if (num_lights > 0) {
+		Mem* l = getMem(ctx, lights);
+		if (!l || (size_t) num_lights * sizeof(pbr_light) > l->bytes) return fail(ctx, PBR_ERR_INVALID, "pbr_trace: bad lights buffer");
+		S.lights = (const pbr_light*) l->dptr;
+		S.numLights = num_lights;
+	}
+	if (n <= 0) return PBR_OK;
+	CK(cudaMemsetAsync(ctx->cursor64, 0, sizeof(unsigned long long), ctx->stream));
+	int occ = 0;
+	if (any_hit) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, traceRaysKernel<true>, 128, 0));
+	else CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, traceRaysKernel<false>, 128, 0));
+	const int grid = ctx->smCount * (occ > 0 ? occ : 1);
+	CK(cudaEventRecord(ctx->evStart, ctx->stream));
+	if (any_hit) traceRaysKernel<true><<<grid, 128, 0, ctx->stream>>>(S, dRays, (long long) n, dHits, ctx->cursor64, ctx->stats);
+	else traceRaysKernel<false><<<grid, 128, 0, ctx->stream>>>(S, dRays, (long long) n, dHits, ctx->cursor64, ctx->stats);
+	CK(cudaGetLastError());
+	CK(cudaEventRecord(ctx->evStop, ctx->stream));
+	ctx->timed = true;
+	return PBR_OK;
+}
+
+int pbr_trace_device(pbr_ctx* ctx, pbr_mem bvh, pbr_mem facesV, pbr_mem vertices, pbr_mem lights, int32_t num_lights,
+                     pbr_mem rays, int64_t n, int32_t any_hit, pbr_mem hits) {
+	if (!ctx) return PBR_ERR_INVALID;
+	CK(cudaSetDevice(ctx->device));
+	Mem* r = getMem(ctx, rays);
+	Mem* h = getMem(ctx, hits);
+	if (!r || !h || n < 0 || (size_t) n * sizeof(pbr_ray) > r->bytes || (size_t) n * sizeof(pbr_hit) > h->bytes)
+		return fail(ctx, PBR_ERR_INVALID, "pbr_trace_device: bad rays / hits buffer");
+	return traceImpl(ctx, bvh, facesV, vertices, lights, num_lights, (const pbr_ray*) r->dptr, n, any_hit, (pbr_hit*) h->dptr);
+}
+
+int pbr_trace(pbr_ctx* ctx, pbr_mem bvh, pbr_mem facesV, pbr_mem vertices, pbr_mem lights, int32_t num_lights,
+              const pbr_ray* rays, int64_t n, int32_t any_hit, pbr_hit* hits) {
+	if (!ctx || n < 0 || (n > 0 && (!rays || !hits))) return PBR_ERR_INVALID;
+	if (n == 0) return PBR_OK;
+	CK(cudaSetDevice(ctx->device));
+	pbr_ray* dRays = nullptr;
+	pbr_hit* dHits = nullptr;
+	CK(cudaMalloc(&dRays, (size_t) n * sizeof(pbr_ray)));
+	cudaError_t e = cudaMalloc(&dHits, (size_t) n * sizeof(pbr_hit));
+	if (e != cudaSuccess) { cudaFree(dRays); return cudaFail(ctx, e, "cudaMalloc"); }
+	int rc = PBR_OK;
+	e = cudaMemcpyAsync(dRays, rays, (size_t) n * sizeof(pbr_ray), cudaMemcpyHostToDevice, ctx->stream);
+	if (e != cudaSuccess) rc = cudaFail(ctx, e, "cudaMemcpyAsync");
+	if (!rc) rc = traceImpl(ctx, bvh, facesV, vertices, lights, num_lights, dRays, n, any_hit, dHits);
+	if (!rc) {
+		e = cudaMemcpyAsync(hits, dHits, (size_t) n * sizeof(pbr_hit), cudaMemcpyDeviceToHost, ctx->stream);
+		if (e != cudaSuccess) rc = cudaFail(ctx, e, "cudaMemcpyAsync");
+	}
+	e = cudaStreamSynchronize(ctx->stream);
+	if (!rc && e != cudaSuccess) rc = cudaFail(ctx, e, "cudaStreamSynchronize");
+	cudaFree(dRays);
+	cudaFree(dHits);
+	return rc;
+}
+
+int pbr_pinned_math_eval(pbr_ctx* ctx, int32_t op, const float* x, const float* y, int64_t n, float* out) {
+	if (!ctx || !x || !out || n < 0 || op < 0 || op > 7) return PBR_ERR_INVALID;
+	if (n == 0) return PBR_OK;
+	CK(cudaSetDevice(ctx->device));
+	float *dx = nullptr, *dy = nullptr, *dout = nullptr;
+	CK(cudaMalloc(&dx, (size_t) n * 4));
+	CK(cudaMalloc(&dy, (size_t) n * 4));
+	CK(cudaMalloc(&dout, (size_t) n * 4));
+	CK(cudaMemcpyAsync(dx, x, (size_t) n * 4, cudaMemcpyHostToDevice, ctx->stream));
+	if (y) CK(cudaMemcpyAsync(dy, y, (size_t) n * 4, cudaMemcpyHostToDevice, ctx->stream));
+	else CK(cudaMemsetAsync(dy, 0, (size_t) n * 4, ctx->stream));
+	pinnedMathKernel<<<gridFor(n, 256), 256, 0, ctx->stream>>>(op, dx, dy, (long long) n, dout);
+	CK(cudaGetLastError());
+	CK(cudaMemcpyAsync(out, dout, (size_t) n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+	CK(cudaStreamSynchronize(ctx->stream));
+	cudaFree(dx); cudaFree(dy); cudaFree(dout);
+	return PBR_OK;
+}
+
+} /* extern "C" */

@@ -1,0 +1,452 @@
+#!/usr/bin/env python
+"""bench.py -- the headline benchmark of the B200 path-tracing core.
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+Workload (BASELINE.json configs[1], "C2"): synthetic 1 000 000-triangle random soup, 1920 x 1080,
+16 spp rendered as 16 frames x render.samples = 1 (config.json semantics), max_depth 3 (+<= 5 added),
+BRDF 1 (Shirley-Ashikhmin), no shadow rays, anti-aliasing 0.7, camera (0, 0, 3.5) looking down -z.
+One STEP = one 16-spp job on every rank.
+
+Metric: Mrays/s = (calls of traverse() + traverseShadows()) / time, whole job over all ranks.
+  value : device-resident -- scene, path state and accumulation buffer stay in HBM; timed with CUDA
+          events on the stream the kernels run on, barrier + synchronize on both sides, max over ranks.
+  e2e   : the same job through the host API a user of the reference calls (PathTracer::generateImage
+          via libpbr_host.so): every frame the accumulated image is read back into pinned host memory,
+          kernel arguments (seed, weight, camera) go host -> device.
+  N > 1 : samples are sharded -- every rank renders whole frames with its own seeds (weak scaling, N x
+          the samples per second) and ONE NCCL all-reduce per frame forms the displayed frame
+          (--shard tiles: rows are sharded instead, one all-gather per frame, strong scaling).
+Extra objects: roofline (dominant kernel = traverse: algorithmic bytes / its summed CUDA-event time,
+against the measured HBM peak), cpu_baseline (the CPU oracle on the host cores, bounded sample),
+clocks (sampled during the timed region).
+
+--impl reference times the reference's own algorithm on the host CPU (the oracle port -- the
+reference itself cannot be built here: no OpenCL ICD, Boost, GLM, Qt) on the same workload.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (triangles, width, height, frames per step, description)
+    "c2": dict(tris=1_000_000, width=1920, height=1080, spp=16, eye=(0.0, 0.0, 3.5),
+               name="C2 soup-1M-tris 1920x1080 16spp"),
+}
+ALGO_BYTES_PER_NODE = 32      # one bvhNode: 2 x float4              (pt_bvh.cl:90)
+ALGO_BYTES_PER_TRI = 64       # facesV entry + 3 vertices            (pt_intersect.cl:146-149)
+FALLBACK_HBM_GBS = 6650.0     # B200_PROFILING.md fallback
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--shard", default="spp", choices=["spp", "tiles"])
+    # overrides for quick checks; any override is recorded in `config` and makes the run non-headline
+    ap.add_argument("--tris", type=int)
+    ap.add_argument("--width", type=int)
+    ap.add_argument("--height", type=int)
+    ap.add_argument("--spp", type=int)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def workload(args):
+    w = dict(WORKLOADS[args.workload])
+    reduced = False
+    for k in ("tris", "width", "height", "spp"):
+        v = getattr(args, k)
+        if v is not None and v != w[k]:
+            w[k] = v
+            reduced = True
+    if reduced:
+        w["name"] = "REDUCED soup-%d-tris %dx%d %dspp" % (w["tris"], w["width"], w["height"], w["spp"])
+    w["reduced"] = reduced
+    return w
+
+
+def measured_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic():
+    """dram bytes per traverse launch from the committed ncu --set full summary, if there is one."""
+    path = os.path.join(ROOT, "profiles", "traverse_ncu_summary.json")
+    try:
+        with open(path) as fh:
+            return json.load(fh).get("dram_bytes_per_launch")
+    except Exception:
+        return None
+
+
+class ClockSampler(threading.Thread):
+    """SM clock and throttle reasons of one GPU while the timed region runs (NVML, 100 ms period)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples, self.reasons = [], set()
+        self.max_mhz = None
+        self.stop_flag = threading.Event()
+        self.error = None
+
+    def run(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = self.index
+            if visible:
+                try:
+                    idx = int(visible.split(",")[self.index])
+                except Exception:
+                    idx = self.index
+            h = nv.nvmlDeviceGetHandleByIndex(idx)
+            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            names = {
+                getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
+                getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+                getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+                getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+                getattr(nv, "nvmlClocksEventReasonHwPowerBrakeSlowdown", 0x80): "hw_power_brake_slowdown",
+            }
+            get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+                getattr(nv, "nvmlDeviceGetCurrentClocksThrottleReasons")
+            while not self.stop_flag.is_set():
+                self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                mask = get_reasons(h)
+                for bit, name in names.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+                time.sleep(0.1)
+        except Exception as e:  # NVML missing: report it, do not fail the run
+            self.error = repr(e)
+
+    def result(self):
+        self.stop_flag.set()
+        self.join(timeout=2.0)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "error": self.error or "no samples"}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def host_config(cfg, w):
+    cfg.reset()
+    cfg.update({
+        "window.width": w["width"], "window.height": w["height"],
+        "camera.eye.x": w["eye"][0], "camera.eye.y": w["eye"][1], "camera.eye.z": w["eye"][2],
+        "camera.center.x": 0.0, "camera.center.y": 0.0, "camera.center.z": 1.0,
+        "render.samples": 1, "render.max_depth": 3, "render.max_added_depth": 5, "render.brdf": 1,
+        "render.shadow_rays": 0, "render.antialiasing": 0.7, "render.phong_tessellation": 0.0,
+        "bvh.max_faces": 2, "bvh.sah_faces_limit": 100000, "bvh.skip_ahead": True, "bvh.skip_ahead_compare": 0.7,
+        "logging.level": 1,
+    })
+
+
+# ------------------------------------------------------------------------------------------------ ours
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import pbr_b200
+    from pbr_b200 import host, multigpu, scenes
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the path tracer has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev_t = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29511")
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev_t)
+    w = workload(args)
+    W, H, SPP = w["width"], w["height"], w["spp"]
+
+    cfg = host.Config()
+    host_config(cfg, w)
+    scene = scenes.soup(w["tris"], seed=12345)
+    r = host.Renderer(local_rank)
+    t0 = time.perf_counter()
+    r.load_scene(scene)
+    load_s = time.perf_counter() - t0
+    info = r.info()
+    r.set_deterministic(True)
+    dev = r.device()
+    dev.setStream(torch.cuda.current_stream().cuda_stream)
+    dev.profileEnable(True)
+
+    tiles = args.shard == "tiles" and world > 1
+    if world > 1 and not tiles:
+        r.set_seed_schedule(world, rank)
+    if tiles:
+        y0, y1 = multigpu.tile_rows(H, rank, world)
+        r.set_tile(y0, y1)
+
+    views = {}
+
+    def image_tensor():
+        _, hd = r.handles()
+        ptr, _ = dev.devicePtr(hd["image"])
+        if ptr not in views:
+            views[ptr] = multigpu.DeviceImage(ptr, H, W, dev_t).tensor
+        return views[ptr]
+
+    display = torch.empty((H, W, 4), dtype=torch.float32, device=dev_t) if world > 1 else None
+
+    def frame():
+        r.render_frames(1)
+        if world > 1:
+            img = image_tensor()
+            if tiles:
+                multigpu.combine_tiles(img, rank, world)
+            else:
+                multigpu.combine_spp(img, world, out=display)
+
+    def step_resident():
+        r.reset_sample_count()
+        for _ in range(SPP):
+            frame()
+
+    pinned = torch.empty((H, W, 4), dtype=torch.float32).pin_memory()
+    pinned_np = pinned.numpy()
+
+    def step_e2e():
+        r.reset_sample_count()
+        for _ in range(SPP):
+            if world == 1:
+                r.generate_image(out=pinned_np)              # launch + read-back into pinned memory
+            else:
+                frame()
+                pinned.copy_(display if not tiles else image_tensor(), non_blocking=False)
+
+    def sync_all():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev_t)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(a):
+        if world == 1:
+            return a
+        t = torch.tensor(np.asarray(a, np.float64), device=dev_t)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return t.cpu().numpy()
+
+    # ---- device-resident timing ----------------------------------------------------------------
+    for _ in range(args.warmup):
+        step_resident()
+    sync_all()
+    dev.stats(reset=True)
+    dev.profileRead(reset=True)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sync_all()
+    start.record()
+    for _ in range(args.steps):
+        step_resident()
+    end.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ms_local = start.elapsed_time(end)
+    clocks = sampler.result()
+    ms_total = max_over_ranks(ms_local)
+    stats_local = dev.stats(reset=True).astype(np.float64)
+    prof = dev.profileRead(reset=True)
+    stats_all = sum_over_ranks(stats_local)
+    launches_all = float(sum_over_ranks(np.array([prof["launches"]], np.float64))[0])
+    rays_all = stats_all[0] + stats_all[1]
+    value = rays_all / (ms_total * 1e-3) / 1e6
+    frames_all = args.steps * SPP * (1 if tiles else world)
+    samples_per_s = frames_all * W * H / (ms_total * 1e-3)
+
+    # roofline of the dominant kernel (this rank's traverse launches)
+    peak, peak_src = measured_peak()
+    algo_bytes = ALGO_BYTES_PER_NODE * stats_local[2] + ALGO_BYTES_PER_TRI * stats_local[3]
+    trav_ms = prof["traverse_ms"]
+    achieved = algo_bytes / (trav_ms * 1e-3) / 1e9 if trav_ms > 0 else 0.0
+    roofline = {
+        "bound": "hbm", "kernel": "traverseKernel", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
+        "frac": round(achieved / peak, 4), "traffic": ncu_traffic(), "peak_source": peak_src,
+        "launches": int(prof["traverse_launches"]),
+        "avg_launch_ms": round(trav_ms / max(1, prof["traverse_launches"]), 4),
+        "algorithmic_bytes_per_launch": round(algo_bytes / max(1, prof["traverse_launches"])),
+        "kernel_share_of_step": round(trav_ms / ms_local, 4),
+        "shade_share_of_step": round(prof["shade_ms"] / ms_local, 4),
+        "nodes_per_ray": round(stats_local[2] / max(1.0, stats_local[0]), 2),
+        "tri_tests_per_ray": round(stats_local[3] / max(1.0, stats_local[0]), 2),
+    }
+
+    # ---- end to end through the host API ---------------------------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        for _ in range(max(1, args.warmup // 2)):
+            step_e2e()
+        sync_all()
+        dev.stats(reset=True)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            step_e2e()
+        torch.cuda.synchronize()
+        e2e_s = max_over_ranks(time.perf_counter() - t0)
+        e_stats = sum_over_ranks(dev.stats(reset=True).astype(np.float64))
+        e2e = {
+            "value": round((e_stats[0] + e_stats[1]) / e2e_s / 1e6, 2), "unit": "Mrays/s",
+            "h2d_bytes_per_step": SPP * (4 + 4 + 80),          # seed, pixelWeight, camera per frame
+            "d2h_bytes_per_step": SPP * W * H * 16,            # accumulated frame per frame
+            "ms_per_step": round(e2e_s * 1e3 / args.steps, 3),
+            "api": "PathTracer::generateImage (libpbr_host.so), pinned host image",
+        }
+
+    # ---- CPU baseline (rank 0, N = 1 only) ---------------------------------------------------------
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu_baseline = cpu_baseline_sample(w, r.flat(), scene)
+
+    if rank == 0:
+        line = {
+            "metric": "Mrays/s", "value": round(value, 2), "unit": "Mrays/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": round(ms_total / args.steps, 3), "higher_is_better": True,
+            "scaling": "strong" if tiles else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {
+                "workload": w["name"], "triangles": w["tris"], "width": W, "height": H, "spp_per_step": SPP,
+                "frames_per_step_per_rank": SPP, "max_depth": 3, "max_added_depth": 5, "brdf": 1,
+                "sharding": ("tiles+allgather" if tiles else "spp+allreduce") if world > 1 else "none",
+                "bvh_nodes": info["emitted_nodes"], "bvh_build_s": round(info["bvh_build_seconds"], 2),
+                "scene_load_s": round(load_s, 2),
+                "l2_policy": "working set > L2: nodes+tris %.0f MB, path state %.0f MB, images %.0f MB" % (
+                    (info["emitted_nodes"] * 32 + info["faces"] * 48) / 1e6, W * H * 104 / 1e6, W * H * 48 / 1e6),
+            },
+            "samples_per_s": round(samples_per_s), "rays_per_step": round(rays_all / args.steps),
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches_all),
+            "roofline": roofline, "cpu_baseline": cpu_baseline,
+        }
+        print(json.dumps(line), flush=True)
+    r.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def cpu_baseline_sample(w, flat, scene, frames=1):
+    """The CPU oracle (a port of the reference kernels, oracle/pt_oracle.cpp) on all host cores for a
+    bounded sample of the same workload: `frames` frames of the full image at 1 spp."""
+    from oracle import oracle as O
+    from oracle import scene as S
+    threads = os.cpu_count() or 1
+    W, H = w["width"], w["height"]
+    v4 = S.pack_float4(scene["vertices"])
+    mats, sky = S.pack_materials(scene["materials"], scene["materialNames"], 1)
+    D = S.defines(W, H, flat["nodes"].shape[0], 0, sky, brdf=1, samples=1, max_depth=3, max_added_depth=5,
+                  shadow_rays=0, antialiasing=0.7)
+    cam = S.camera(eye=w["eye"])
+    px = S.px_dim(W, H)
+    img = np.zeros((H, W, 4), np.float32)
+    rays = 0
+    t0 = time.perf_counter()
+    for k in range(frames):
+        img, _, st = O.path_tracing(D, S.frame_seed(k), S.pixel_weight(k), px, cam, flat["nodes"], flat["facesV"],
+                                    flat["facesN"], v4, None, mats, None, img, nthreads=threads, debug=False)
+        rays += int(st[0]) + int(st[1])
+    sec = time.perf_counter() - t0
+    return {"value": round(rays / sec / 1e6, 3), "unit": "Mrays/s", "cores": threads, "kind": "port",
+            "sample": "%d frame(s) of the full %dx%d image at 1 spp (%d rays) in %.1f s" % (frames, W, H, rays, sec)}
+
+
+# ------------------------------------------------------------------------------------------- reference
+
+def run_reference(args):
+    """The reference's algorithm on the host CPU: oracle port, all host threads, rank 0 only."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import oracle as O
+    from oracle import scene as S
+    import pbr_b200
+    w = workload(args)
+    W, H = w["width"], w["height"]
+    threads = os.cpu_count() or 1
+    scene = pbr_b200.scenes.soup(w["tris"], seed=12345)         # input data only
+    bvh = O.build_bvh(scene)                                    # the oracle's own (literal) BVH builder
+    v4 = S.pack_float4(scene["vertices"])
+    mats, sky = S.pack_materials(scene["materials"], scene["materialNames"], 1)
+    D = S.defines(W, H, bvh["nodes"].shape[0], 0, sky, brdf=1, samples=1, max_depth=3, max_added_depth=5,
+                  shadow_rays=0, antialiasing=0.7)
+    cam = S.camera(eye=w["eye"])
+    px = S.px_dim(W, H)
+    img = np.zeros((H, W, 4), np.float32)
+
+    def step(k):
+        nonlocal img
+        img, _, st = O.path_tracing(D, S.frame_seed(k), S.pixel_weight(k), px, cam, bvh["nodes"], bvh["facesV"],
+                                    bvh["facesN"], v4, None, mats, None, img, nthreads=threads, debug=False)
+        return int(st[0]) + int(st[1])
+
+    k = 0
+    for _ in range(args.warmup):
+        step(k)
+        k += 1
+    rays = 0
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        rays += step(k)
+        k += 1
+    sec = time.perf_counter() - t0
+    value = round(rays / sec / 1e6, 3)
+    sample = "each step = 1 frame of the full %dx%d image at 1 spp (1/%d of the GPU arm's step)" % (W, H, w["spp"])
+    line = {
+        "impl": "reference", "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(sec * 1e3 / args.steps, 3),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": w["name"], "triangles": w["tris"], "width": W, "height": H,
+                   "spp_per_step": 1, "max_depth": 3, "max_added_depth": 5, "brdf": 1,
+                   "note": "CPU restatement of the reference kernels (oracle port); the reference itself "
+                           "cannot be built here (no OpenCL ICD / pocl, Boost, GLM, Qt)"},
+        "cpu_baseline": {"value": value, "unit": "Mrays/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

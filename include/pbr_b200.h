@@ -127,6 +127,20 @@ int pbr_set_debug_image(pbr_ctx* ctx, int32_t enabled);
  * These are the inputs of the algorithmic-byte formula of SURVEY.md 8d. */
 int pbr_stats(pbr_ctx* ctx, uint64_t out[6], int32_t reset);
 
+/* Issue all device work of this context on a caller-owned CUDA stream (a cudaStream_t passed as
+ * void*, e.g. torch.cuda.current_stream().cuda_stream) so that the caller's own copies, collectives
+ * and CUDA events are ordered with the kernels.  NULL restores the context's own stream. */
+int pbr_set_stream(pbr_ctx* ctx, void* cuda_stream);
+/* Per-kernel device timing with CUDA events recorded on the launching stream around every launch
+ * (the OpenCL queue of the reference is created with CL_QUEUE_PROFILING_ENABLE, CL.cpp:538). */
+typedef struct {
+	uint64_t launches;            /* every kernel launched by this library since the last reset */
+	uint64_t raygen_launches, traverse_launches, shade_launches, other_launches;
+	double raygen_ms, traverse_ms, shade_ms, other_ms;   /* summed event times, 0 unless enabled */
+} pbr_profile;
+int pbr_profile_enable(pbr_ctx* ctx, int32_t enabled);
+int pbr_profile_read(pbr_ctx* ctx, pbr_profile* out, int32_t reset);
+
 /* Explicit rays (BASELINE config 5).  `rays`/`hits` are HOST arrays of n elements; the scene is
  * given by buffer handles in the reference layout.  any_hit = 0: traverse() (closest hit,
  * pt_bvh.cl:82-123); any_hit = 1: traverseShadows() (pt_bvh.cl:133-177).  lights may be 0. */

@@ -11,5 +11,5 @@ The directory name contains a hyphen, so import it through the alias module `pbr
 repository root (`import pbr_b200`).  Nothing here falls back to the CPU: without the built shared
 library or without a CUDA device, constructing a Device raises.
 """
-from . import capi, scenes          # noqa: F401
+from . import capi, host, multigpu, scenes    # noqa: F401
 from .capi import Device, PbrError  # noqa: F401

@@ -23,6 +23,7 @@ SYMBOLS = [
     "pbr_finish", "pbr_kernel_time_ms",
     "pbr_set_tile", "pbr_set_pipeline", "pbr_set_debug_image", "pbr_stats",
     "pbr_trace", "pbr_trace_device", "pbr_pinned_math_eval",
+    "pbr_set_stream", "pbr_profile_enable", "pbr_profile_read",
 ]
 
 DEFINES_DTYPE = np.dtype([
@@ -37,6 +38,9 @@ CAMERA_DTYPE = np.dtype([
     ("focusPoint", "<i4", (2,)), ("lense", "<f4", (2,)),
 ])
 HIT_DTYPE = np.dtype([("t", "<f4"), ("hitFace", "<i4"), ("leaf", "<i4"), ("visits", "<u4")])
+PROFILE_DTYPE = np.dtype([("launches", "<u8"), ("raygen_launches", "<u8"), ("traverse_launches", "<u8"),
+                          ("shade_launches", "<u8"), ("other_launches", "<u8"), ("raygen_ms", "<f8"),
+                          ("traverse_ms", "<f8"), ("shade_ms", "<f8"), ("other_ms", "<f8")])
 
 _lib = None
 
@@ -86,6 +90,9 @@ def load_library():
         "pbr_trace": [vp, u64, u64, u64, u64, i32, vp, i64, i32, vp],
         "pbr_trace_device": [vp, u64, u64, u64, u64, i32, u64, i64, i32, u64],
         "pbr_pinned_math_eval": [vp, i32, vp, vp, i64, vp],
+        "pbr_set_stream": [vp, vp],
+        "pbr_profile_enable": [vp, i32],
+        "pbr_profile_read": [vp, vp, i32],
     }
     for name, args in sig.items():
         f = getattr(lib, name)
@@ -104,17 +111,26 @@ def _p(a):
 class Device:
     """One pbr_ctx.  Method names follow the reference's `CL` class where one exists."""
 
-    def __init__(self, device=-1):
+    def __init__(self, device=-1, _borrowed_ctx=None):
         self.lib = load_library()
+        self.owned = _borrowed_ctx is None
+        if not self.owned:
+            self.ctx = _borrowed_ctx
+            return
         self.ctx = C.c_void_p()
         rc = self.lib.pbr_create(device, C.byref(self.ctx))
         if rc != 0:
             raise PbrError("pbr_create failed with code %d: no usable CUDA device (there is no CPU fallback)" % rc)
 
+    @classmethod
+    def from_ctx(cls, ctx_pointer):
+        """Non-owning view of a pbr_ctx created elsewhere (e.g. by the C++ CL shim)."""
+        return cls(_borrowed_ctx=ctx_pointer)
+
     def close(self):
-        if self.ctx:
+        if self.ctx and self.owned:
             self.lib.pbr_destroy(self.ctx)
-            self.ctx = C.c_void_p()
+        self.ctx = C.c_void_p()
 
     def __del__(self):
         try:
@@ -247,6 +263,17 @@ class Device:
     def traceDevice(self, bvh, facesV, vertices, rays_mem, n, hits_mem, any_hit=False, lights=0, num_lights=0):
         self._ck(self.lib.pbr_trace_device(self.ctx, bvh, facesV, vertices, lights, num_lights, rays_mem, n,
                                            int(any_hit), hits_mem), "pbr_trace_device")
+
+    def setStream(self, cuda_stream):
+        self._ck(self.lib.pbr_set_stream(self.ctx, cuda_stream), "pbr_set_stream")
+
+    def profileEnable(self, enabled=True):
+        self._ck(self.lib.pbr_profile_enable(self.ctx, int(enabled)), "pbr_profile_enable")
+
+    def profileRead(self, reset=False):
+        out = np.zeros(1, PROFILE_DTYPE)
+        self._ck(self.lib.pbr_profile_read(self.ctx, _p(out), int(reset)), "pbr_profile_read")
+        return {k: out[k][0].item() for k in PROFILE_DTYPE.names}
 
     def pinnedMath(self, op, x, y=None):
         x = np.ascontiguousarray(x, np.float32)

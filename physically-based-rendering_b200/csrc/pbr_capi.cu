@@ -42,7 +42,15 @@ struct pbr_ctx {
 	int device = 0;
 	int smCount = 0;
 	cudaStream_t stream = nullptr;
+	cudaStream_t ownStream = nullptr;
 	cudaEvent_t evStart = nullptr, evStop = nullptr;
+
+	/* per-kernel profiling */
+	bool profiling = false;
+	struct Timed { cudaEvent_t a, b; int kind; };
+	std::vector<Timed> timedInFlight;
+	std::vector<cudaEvent_t> eventPool;
+	pbr_profile prof = {};
 	bool timed = false;
 	std::string lastError;
 	std::vector<Mem> mems;
@@ -115,6 +123,65 @@ int newMem(pbr_ctx* ctx, size_t bytes, pbr_mem* out, Mem** mp) {
 
 int gridFor(long long n, int block) { return (int) ((n + block - 1) / block); }
 
+enum KernelKind { K_RAYGEN = 0, K_TRAVERSE = 1, K_SHADE = 2, K_OTHER = 3 };
+
+cudaEvent_t takeEvent(pbr_ctx* ctx) {
+	if (!ctx->eventPool.empty()) {
+		cudaEvent_t e = ctx->eventPool.back();
+		ctx->eventPool.pop_back();
+		return e;
+	}
+	cudaEvent_t e = nullptr;
+	cudaEventCreate(&e);
+	return e;
+}
+
+/* Brackets one kernel launch: counts it and, when profiling is on, times it with two events. */
+struct LaunchScope {
+	pbr_ctx* ctx;
+	cudaEvent_t a = nullptr, b = nullptr;
+	int kind;
+	LaunchScope(pbr_ctx* c, int k) : ctx(c), kind(k) {
+		ctx->prof.launches++;
+		switch (kind) {
+			case K_RAYGEN: ctx->prof.raygen_launches++; break;
+			case K_TRAVERSE: ctx->prof.traverse_launches++; break;
+			case K_SHADE: ctx->prof.shade_launches++; break;
+			default: ctx->prof.other_launches++; break;
+		}
+		if (ctx->profiling) {
+			a = takeEvent(ctx);
+			b = takeEvent(ctx);
+			cudaEventRecord(a, ctx->stream);
+		}
+	}
+	~LaunchScope() {
+		if (a) {
+			cudaEventRecord(b, ctx->stream);
+			pbr_ctx::Timed t = {a, b, kind};
+			ctx->timedInFlight.push_back(t);
+		}
+	}
+};
+
+/* Fold finished event pairs into the profile (the stream must be idle). */
+void drainTimed(pbr_ctx* ctx) {
+	for (const pbr_ctx::Timed& t : ctx->timedInFlight) {
+		float ms = 0.0f;
+		if (cudaEventElapsedTime(&ms, t.a, t.b) == cudaSuccess) {
+			switch (t.kind) {
+				case K_RAYGEN: ctx->prof.raygen_ms += ms; break;
+				case K_TRAVERSE: ctx->prof.traverse_ms += ms; break;
+				case K_SHADE: ctx->prof.shade_ms += ms; break;
+				default: ctx->prof.other_ms += ms; break;
+			}
+		}
+		ctx->eventPool.push_back(t.a);
+		ctx->eventPool.push_back(t.b);
+	}
+	ctx->timedInFlight.clear();
+}
+
 /* Rebuild the repacked node / triangle arrays when the bound buffers or BVH_NUM_NODES changed. */
 int ensureScene(pbr_ctx* ctx, pbr_mem hBvh, pbr_mem hFacesV, pbr_mem hVertices, int numNodes) {
 	if (ctx->cacheBvh == hBvh && ctx->cacheFacesV == hFacesV && ctx->cacheVertices == hVertices &&
@@ -145,8 +212,12 @@ int ensureScene(pbr_ctx* ctx, pbr_mem hBvh, pbr_mem hFacesV, pbr_mem hVertices, 
 		CK(cudaMalloc(&ctx->tris, (size_t) (numFaces > 0 ? numFaces : 1) * 48));
 		ctx->trisCap = (size_t) numFaces;
 	}
-	repackNodesKernel<<<gridFor(numDst, 256), 256, 0, ctx->stream>>>((const float4*) bvh->dptr, numNodes, ctx->nodes, numDst);
+	{
+		LaunchScope ls(ctx, K_OTHER);
+		repackNodesKernel<<<gridFor(numDst, 256), 256, 0, ctx->stream>>>((const float4*) bvh->dptr, numNodes, ctx->nodes, numDst);
+	}
 	if (numFaces > 0 && numVertices > 0) {
+		LaunchScope ls(ctx, K_OTHER);
 		repackTrisKernel<<<gridFor(numFaces, 256), 256, 0, ctx->stream>>>(
 			(const uint4*) facesV->dptr, numFaces, (const float4*) vertices->dptr, numVertices, ctx->tris);
 	}
@@ -181,7 +252,10 @@ int ensureWave(pbr_ctx* ctx, size_t nPaths) {
 template <int BRDF, bool SHADOW>
 int runFrame(pbr_ctx* ctx, const FrameParams& P, int nPaths) {
 	if (ctx->pipeline == 1) {
-		megaKernel<BRDF, SHADOW><<<gridFor(nPaths, 128), 128, 0, ctx->stream>>>(P, nPaths);
+		{
+			LaunchScope ls(ctx, K_OTHER);
+			megaKernel<BRDF, SHADOW><<<gridFor(nPaths, 128), 128, 0, ctx->stream>>>(P, nPaths);
+		}
 		CK(cudaGetLastError());
 		return PBR_OK;
 	}
@@ -196,13 +270,22 @@ int runFrame(pbr_ctx* ctx, const FrameParams& P, int nPaths) {
 	const int gridT = ctx->smCount * (occT > 0 ? occT : 1);
 	const int gridS = ctx->smCount * (occS > 0 ? occS : 1);
 
-	raygenKernel<<<ctx->smCount * 8, 256, 0, ctx->stream>>>(P, W, Q, nPaths);
+	{
+		LaunchScope ls(ctx, K_RAYGEN);
+		raygenKernel<<<ctx->smCount * 8, 256, 0, ctx->stream>>>(P, W, Q, nPaths);
+	}
 	const int iterations = P.samples * (P.maxDepth + P.maxAddedDepth);
 	for (int it = 0; it < iterations; it++) {
 		const int in = it & 1, out = in ^ 1;
 		const uint32_t* qIn = (it == 0) ? nullptr : Q.queue[in];
-		traverseKernel<<<gridT, 128, 0, ctx->stream>>>(P.scene, W, qIn, Q.ctrl + in, Q.ctrl + 2, Q.ctrl + out, ctx->stats);
-		shadeKernel<BRDF, SHADOW><<<gridS, 128, 0, ctx->stream>>>(P, W, qIn, Q.ctrl + in, Q.queue[out], Q.ctrl + out, Q.ctrl + 2);
+		{
+			LaunchScope ls(ctx, K_TRAVERSE);
+			traverseKernel<<<gridT, 128, 0, ctx->stream>>>(P.scene, W, qIn, Q.ctrl + in, Q.ctrl + 2, Q.ctrl + out, ctx->stats);
+		}
+		{
+			LaunchScope ls(ctx, K_SHADE);
+			shadeKernel<BRDF, SHADOW><<<gridS, 128, 0, ctx->stream>>>(P, W, qIn, Q.ctrl + in, Q.queue[out], Q.ctrl + out, Q.ctrl + 2);
+		}
 	}
 	CK(cudaGetLastError());
 	return PBR_OK;
@@ -238,7 +321,8 @@ int pbr_create(int device, pbr_ctx** out) {
 	cudaDeviceProp prop;
 	if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete ctx; return PBR_ERR_NO_DEVICE; }
 	ctx->smCount = prop.multiProcessorCount;
-	if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return PBR_ERR_NO_DEVICE; }
+	if (cudaStreamCreateWithFlags(&ctx->ownStream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return PBR_ERR_NO_DEVICE; }
+	ctx->stream = ctx->ownStream;
 	cudaEventCreate(&ctx->evStart);
 	cudaEventCreate(&ctx->evStop);
 	if (cudaMalloc(&ctx->stats, 6 * sizeof(unsigned long long)) != cudaSuccess ||
@@ -267,7 +351,9 @@ int pbr_destroy(pbr_ctx* ctx) {
 	cudaFree(ctx->qctl.queue[0]); cudaFree(ctx->qctl.queue[1]); cudaFree(ctx->qctl.ctrl);
 	cudaFree(ctx->stats); cudaFree(ctx->cursor64);
 	cudaEventDestroy(ctx->evStart); cudaEventDestroy(ctx->evStop);
-	cudaStreamDestroy(ctx->stream);
+	for (const pbr_ctx::Timed& t : ctx->timedInFlight) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
+	for (cudaEvent_t e : ctx->eventPool) cudaEventDestroy(e);
+	cudaStreamDestroy(ctx->ownStream);
 	delete ctx;
 	return PBR_OK;
 }
@@ -588,6 +674,30 @@ int pbr_stats(pbr_ctx* ctx, uint64_t out[6], int32_t reset) {
 	return PBR_OK;
 }
 
+int pbr_set_stream(pbr_ctx* ctx, void* cuda_stream) {
+	if (!ctx) return PBR_ERR_INVALID;
+	CK(cudaSetDevice(ctx->device));
+	CK(cudaStreamSynchronize(ctx->stream));
+	ctx->stream = cuda_stream ? (cudaStream_t) cuda_stream : ctx->ownStream;
+	return PBR_OK;
+}
+
+int pbr_profile_enable(pbr_ctx* ctx, int32_t enabled) {
+	if (!ctx) return PBR_ERR_INVALID;
+	ctx->profiling = enabled != 0;
+	return PBR_OK;
+}
+
+int pbr_profile_read(pbr_ctx* ctx, pbr_profile* out, int32_t reset) {
+	if (!ctx || !out) return PBR_ERR_INVALID;
+	CK(cudaSetDevice(ctx->device));
+	CK(cudaStreamSynchronize(ctx->stream));
+	drainTimed(ctx);
+	*out = ctx->prof;
+	if (reset) memset(&ctx->prof, 0, sizeof(ctx->prof));
+	return PBR_OK;
+}
+
 static int traceImpl(pbr_ctx* ctx, pbr_mem bvh, pbr_mem facesV, pbr_mem vertices, pbr_mem lights, int32_t num_lights,
                      const pbr_ray* dRays, int64_t n, int32_t any_hit, pbr_hit* dHits) {
 	Mem* b = getMem(ctx, bvh);
@@ -614,8 +724,11 @@ static int traceImpl(pbr_ctx* ctx, pbr_mem bvh, pbr_mem facesV, pbr_mem vertices
 	else CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, traceRaysKernel<false>, 128, 0));
 	const int grid = ctx->smCount * (occ > 0 ? occ : 1);
 	CK(cudaEventRecord(ctx->evStart, ctx->stream));
-	if (any_hit) traceRaysKernel<true><<<grid, 128, 0, ctx->stream>>>(S, dRays, (long long) n, dHits, ctx->cursor64, ctx->stats);
-	else traceRaysKernel<false><<<grid, 128, 0, ctx->stream>>>(S, dRays, (long long) n, dHits, ctx->cursor64, ctx->stats);
+	{
+		LaunchScope ls(ctx, K_TRAVERSE);
+		if (any_hit) traceRaysKernel<true><<<grid, 128, 0, ctx->stream>>>(S, dRays, (long long) n, dHits, ctx->cursor64, ctx->stats);
+		else traceRaysKernel<false><<<grid, 128, 0, ctx->stream>>>(S, dRays, (long long) n, dHits, ctx->cursor64, ctx->stats);
+	}
 	CK(cudaGetLastError());
 	CK(cudaEventRecord(ctx->evStop, ctx->stream));
 	ctx->timed = true;
@@ -669,7 +782,10 @@ int pbr_pinned_math_eval(pbr_ctx* ctx, int32_t op, const float* x, const float* 
 	CK(cudaMemcpyAsync(dx, x, (size_t) n * 4, cudaMemcpyHostToDevice, ctx->stream));
 	if (y) CK(cudaMemcpyAsync(dy, y, (size_t) n * 4, cudaMemcpyHostToDevice, ctx->stream));
 	else CK(cudaMemsetAsync(dy, 0, (size_t) n * 4, ctx->stream));
-	pinnedMathKernel<<<gridFor(n, 256), 256, 0, ctx->stream>>>(op, dx, dy, (long long) n, dout);
+	{
+		LaunchScope ls(ctx, K_OTHER);
+		pinnedMathKernel<<<gridFor(n, 256), 256, 0, ctx->stream>>>(op, dx, dy, (long long) n, dout);
+	}
 	CK(cudaGetLastError());
 	CK(cudaMemcpyAsync(out, dout, (size_t) n * 4, cudaMemcpyDeviceToHost, ctx->stream));
 	CK(cudaStreamSynchronize(ctx->stream));

@@ -1,0 +1,86 @@
+/*
+ * CL -- the reference's device-runtime class (source/CL.h:20-83) re-targeted from the OpenCL 1.1 C API
+ * onto the C ABI of libpbr_b200.so (include/pbr_b200.h).  Method names, argument meaning and error
+ * behaviour are the reference's, so PathTracer drives it with the same call sequence:
+ *     createBuffer<T>, createImage2DReadOnly / WriteOnly, setReplacement, loadProgram, createKernel,
+ *     setKernelArg, execute, finish, readImageOutput, updateImageReadOnly, getKernelNames / Times.
+ * Error convention (CL.cpp:89-99): a failing call logs "[OpenCL] Error in function <name>: ..." when
+ * opencl.check_errors is set and execution continues; failures to obtain a device, a program or a
+ * kernel end the process with EXIT_FAILURE like the reference (CL.cpp:209-211, 347-350, 438-448,
+ * 523-525, 540-542, 564-566).
+ */
+#ifndef CL_H
+#define CL_H
+
+#include <map>
+#include <string>
+#include <vector>
+
+#include "cl_types.h"
+#include "Cfg.h"
+#include "Logger.h"
+#include "utils.h"
+
+using std::map;
+using std::string;
+using std::vector;
+
+
+class CL {
+
+	public:
+		CL( const bool silent = false );
+		~CL();
+
+		template<typename T> cl_mem createBuffer( vector<T> object, size_t objectSize ) {
+			return this->createBufferFromPtr( object.empty() ? NULL : &object[0], objectSize );
+		}
+		/** Additive: same as createBuffer without the by-value vector copy. */
+		cl_mem createBufferFromPtr( const void* data, size_t objectSize );
+
+		cl_mem createEmptyBuffer( size_t size, int flags = 0 );
+		cl_mem createImage2DReadOnly( size_t width, size_t height, cl_float* data );
+		cl_mem createImage2DWriteOnly( size_t width, size_t height );
+		cl_kernel createKernel( const char* functionName );
+		void execute( cl_kernel kernel );
+		void finish();
+		void freeBuffers();
+		map<cl_kernel, string> getKernelNames();
+		map<cl_kernel, double> getKernelTimes();
+		void loadProgram( string filepath );
+		void readImageOutput( cl_mem image, size_t width, size_t height, cl_float* outputTarget );
+		void setKernelArg( cl_kernel kernel, cl_uint index, size_t size, void* data );
+		void setReplacement( string before, string after );
+		cl_mem updateBuffer( cl_mem buffer, size_t size, void* data );
+		cl_mem updateImageReadOnly( cl_mem image, size_t width, size_t height, cl_float* data );
+
+		/** Additive (see include/pbr_b200.h): device-side image copy, tiles, counters, pinned memory. */
+		void copyImage( cl_mem dst, cl_mem src );
+		void setTile( int y0, int y1 );
+		void setDebugImage( bool enabled );
+		void getStats( uint64_t out[6], bool reset );
+		void* allocHost( size_t bytes );
+		void freeHost( void* ptr );
+		pbr_ctx* getContext() { return mContext; }
+		/** The device on which the next CL() is created (multi-GPU: one process per GPU). */
+		static void setDefaultDevice( int device ) { sDefaultDevice = device; }
+
+	protected:
+		bool checkError( int err, const char* functionName );
+		pbr_defines getValues();
+
+	private:
+		bool mDoCheckErrors;
+		cl_uint mWorkHeight;
+		cl_uint mWorkWidth;
+		pbr_ctx* mContext;
+
+		vector<cl_kernel> mKernels;
+		map<cl_kernel, string> mKernelNames;
+		map<cl_kernel, double> mKernelTime;
+
+		static int sDefaultDevice;
+
+};
+
+#endif

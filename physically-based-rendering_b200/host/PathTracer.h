@@ -1,0 +1,165 @@
+/*
+ * PathTracer -- the reference's render driver (source/PathTracer.{h,cpp}) on top of the CL shim.
+ *
+ * Same public API (PathTracer.h:83-95): generateImage, initOpenCLBuffers, moveSun, resetSampleCount,
+ * setCamera, setFocus, setFOV, setWidthAndHeight; same host-side structs (camera_cl, light_cl,
+ * material_*, bvhNode_cl, PathTracer.h:25-73 -- here typedefs of the C-ABI records); same buffer
+ * packing and the same flattening of the BVH into bvhNode_cl[] + leaf-ordered faces
+ * (PathTracer.cpp:238-347), which is the layout contract of the kernel.
+ *
+ * What differs, deliberately:
+ *   - generateImage keeps the accumulated frame on the device: imageIn/imageOut are swapped from
+ *     frame to frame instead of reading the frame back and uploading it again (PathTracer.cpp:61-66);
+ *     the host copy is refreshed by one read-back per frame into pinned memory.  The debug image is
+ *     only read back when the caller passes a vector for it.
+ *   - the seed is wall-clock seconds as in the reference (PathTracer.cpp:78-82) unless a deterministic
+ *     schedule seed_k = 0.0333f * (k + 1) is selected (setDeterministicSeeds), which is what makes
+ *     frames reproducible and testable.
+ *   - additive: renderFrames(n) (n frames, no read-back until asked), readImage(), tile rows for
+ *     multi-GPU sharding, counters.
+ */
+#ifndef PATH_TRACER_H
+#define PATH_TRACER_H
+
+#include <chrono>
+#include <string>
+#include <vector>
+
+#include "Camera.h"
+#include "CL.h"
+#include "Cfg.h"
+#include "MtlParser.h"
+#include "accelstructures/BVH.h"
+
+using std::vector;
+
+typedef pbr_camera camera_cl;
+typedef pbr_light light_cl;
+typedef pbr_material_schlick material_schlick_rgb;
+typedef pbr_material_sa material_shirley_ashikhmin_rgb;
+typedef pbr_bvh_node bvhNode_cl;
+
+struct face_cl {
+	cl_uint4 vertices; // w: material
+	cl_uint4 normals;
+};
+
+
+class Camera;
+class GLWidget;
+
+
+class PathTracer {
+
+	public:
+		PathTracer( GLWidget* parent );
+		~PathTracer();
+		vector<cl_float> generateImage( vector<cl_float>* textureDebug );
+		void initOpenCLBuffers(
+			const vector<cl_float>& vertices, const vector<cl_uint>& faces, const vector<cl_float>& normals,
+			ModelLoader* ml, AccelStructure* bvh
+		);
+		void moveSun( const int key );
+		void resetSampleCount();
+		void setCamera( Camera* camera );
+		void setFocus( int x, int y );
+		void setFOV( cl_float fov );
+		void setWidthAndHeight( cl_uint width, cl_uint height );
+
+		/* ---- additive ---- */
+		/** Use seed_k = 0.0333f * (k + 1) for frame k instead of wall-clock seconds. */
+		void setDeterministicSeeds( bool enabled ) { mDeterministicSeeds = enabled; }
+		/** Deterministic schedule for sample-sharded multi-GPU runs: frame k of this renderer uses the
+		 *  global index k * stride + offset, i.e. seed = 0.0333f * (k * stride + offset + 1). */
+		void setSeedSchedule( cl_uint stride, cl_uint offset ) { mSeedStride = stride; mSeedOffset = offset; }
+		/** Render `frames` frames back to back without reading anything back. */
+		void renderFrames( cl_uint frames );
+		/** One frame, result read into `target` (W*H*4 floats; pinned memory recommended). */
+		void generateImageInto( cl_float* target, cl_float* targetDebug );
+		/** Read the current accumulated frame (and optionally the debug image) from the device. */
+		void readImage( cl_float* target, cl_float* targetDebug );
+		/** Replace the accumulated frame on the device (resume from a checkpoint). */
+		void writeImage( const cl_float* source, cl_uint sampleCount );
+		void setTileRows( int y0, int y1 );
+		cl_uint getSampleCount() const { return mSampleCount; }
+		cl_uint getWidth() const { return mWidth; }
+		cl_uint getHeight() const { return mHeight; }
+		CL* getCL() { return mCL; }
+		cl_mem getImageHandle() const { return mBufTextureOut; }
+		double getLastKernelMs();
+		/** The flattening of initOpenCLBuffers_BVH without the upload (no device needed). */
+		static void flattenBVH(
+			const BVH* bvh, const ObjParser* op, const vector<cl_uint>& faces,
+			vector<bvhNode_cl>* flatNodes, vector<cl_uint4>* flatFacesV, vector<cl_uint4>* flatFacesN
+		);
+		/** The flattened scene as uploaded (for tests and the explicit-ray entry points). */
+		const vector<bvhNode_cl>& getFlatNodes() const { return mFlatNodes; }
+		const vector<cl_uint4>& getFlatFacesV() const { return mFlatFacesV; }
+		const vector<cl_uint4>& getFlatFacesN() const { return mFlatFacesN; }
+		cl_mem getBufBVH() const { return mBufBVH; }
+		cl_mem getBufFacesV() const { return mBufFacesV; }
+		cl_mem getBufVertices() const { return mBufVertices; }
+		cl_mem getBufLights() const { return mBufLights; }
+		cl_uint getNumLights() const { return (cl_uint) mLights.size(); }
+		const camera_cl& getCameraStruct() const { return mStructCam; }
+		cl_float getPxDim() const { return mPxDim; }
+
+	protected:
+		void clPathTracing( cl_float timeSinceStart );
+		cl_float getTimeSinceStart();
+		cl_float nextSeed();
+		void initKernelArgs();
+		size_t initOpenCLBuffers_BVH( BVH* bvh, ModelLoader* ml, const vector<cl_uint>& faces );
+		size_t initOpenCLBuffers_Faces(
+			ModelLoader* ml,
+			const vector<cl_float>& vertices, const vector<cl_uint>& faces, const vector<cl_float>& normals
+		);
+		size_t initOpenCLBuffers_Lights( ModelLoader* ml );
+		size_t initOpenCLBuffers_Materials( ModelLoader* ml );
+		size_t initOpenCLBuffers_MaterialsRGB( const vector<material_t>& materials );
+		size_t initOpenCLBuffers_Textures();
+		void updateEyeBuffer();
+		void launchFrame();
+
+	private:
+		cl_uint mHeight;
+		cl_uint mWidth;
+		cl_float mFOV;
+		cl_float mPxDim;
+		cl_uint mSampleCount;
+		bool mDeterministicSeeds;
+		cl_uint mSeedStride, mSeedOffset;
+		bool mHaveOutput;             // imageOut holds a frame that the next launch must read as imageIn
+
+		cl_float* mTextureOut;        // pinned host copy of the frame, W*H*4
+		cl_float* mTextureDebugHost;  // pinned, allocated on first use
+
+		cl_kernel mKernelPathTracing;
+
+		cl_mem mBufBVH;
+		cl_mem mBufFacesV;
+		cl_mem mBufFacesN;
+		cl_mem mBufVertices;
+		cl_mem mBufNormals;
+		cl_mem mBufMaterials;
+
+		camera_cl mStructCam;
+		cl_mem mBufTextureIn;
+		cl_mem mBufTextureOut;
+		cl_mem mBufTextureDebug;
+
+		vector<light_cl> mLights;
+		cl_mem mBufLights;
+
+		vector<bvhNode_cl> mFlatNodes;
+		vector<cl_uint4> mFlatFacesV;
+		vector<cl_uint4> mFlatFacesN;
+
+		GLWidget* mGLWidget;
+		Camera* mCamera;
+		CL* mCL;
+		std::chrono::steady_clock::time_point mTimeSinceStart;
+
+};
+
+#endif

@@ -1,0 +1,155 @@
+"""GPU: the host mirror end to end -- Cfg -> ObjParser -> BVH -> PathTracer -> CL shim -> C ABI -> CUDA --
+against the oracle, plus the behaviours PathTracer adds around the kernel (accumulation, reset on
+camera change, checkpoint / resume, headless driver)."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import helpers as Hh
+from conftest import MODELS
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture()
+def cfg():
+    from pbr_b200 import host
+    c = host.Config()
+    c.reset()
+    yield c
+    c.reset()
+
+
+def _oracle_for(oracle, cfg, scene_dict, frames, **kw):
+    W, H = int(cfg.get("window.width")), int(cfg.get("window.height"))
+    p = Hh.Prepared(scene_dict, W, H, brdf=int(cfg.get("render.brdf")), samples=int(cfg.get("render.samples")),
+                    max_depth=int(cfg.get("render.max_depth")), max_added_depth=int(cfg.get("render.max_added_depth")),
+                    shadow_rays=int(cfg.get("render.shadow_rays")), antialiasing=float(cfg.get("render.antialiasing")),
+                    eye=tuple(float(cfg.get("camera.eye." + a)) for a in "xyz"),
+                    center=tuple(float(cfg.get("camera.center." + a)) for a in "xyz"),
+                    fov=float(cfg.get("camera.perspective.fov")), **kw)
+    return p, p.oracle_frames(frames)
+
+
+@pytest.mark.parametrize("brdf,shadow", [(1, 0), (0, 0), (1, 1)])
+def test_pathtracer_matches_oracle_on_suzanne(oracle, cfg, brdf, shadow):
+    """BASELINE config 1 (reduced frame size): bundled Cornell box + Suzanne through the whole host path."""
+    from pbr_b200 import host
+    cfg.update({"window.width": 160, "window.height": 120, "render.brdf": brdf, "render.shadow_rays": shadow,
+                "render.max_depth": 4})
+    r = host.Renderer(0)
+    r.set_deterministic(True)
+    r.load_model(MODELS + "/", "suzanne.obj")
+    img = None
+    for _ in range(3):
+        img, dbg = r.generate_image(debug=True)
+    scene = oracle.load_obj(os.path.join(MODELS, "suzanne.obj"), shadow)
+    p, (want, wdbg, wstats) = _oracle_for(oracle, cfg, scene, 3)
+    # host-side products: flattened BVH, camera, pixel size
+    flat = r.flat()
+    assert np.array_equal(flat["nodes"].view(np.uint32), p.nodes.view(np.uint32))
+    assert np.array_equal(flat["facesV"], p.facesV)
+    cam, px = r.camera()
+    assert cam.tobytes() == p.camera.tobytes() and px == p.px_dim
+    # the frame
+    assert Hh.mean_relative_error(img, want) <= 0.02
+    assert Hh.images_equal(img, want)
+    assert Hh.images_equal(dbg, wdbg)
+    assert np.array_equal(r.stats(reset=True), wstats)
+    assert r.info()["sample_count"] == 3 and r.info()["lights"] == (1 if shadow else 0)
+    r.close()
+
+
+def test_resident_frames_equal_per_frame_readback(cfg):
+    from pbr_b200 import host
+    cfg.update({"window.width": 96, "window.height": 64})
+    r = host.Renderer(0)
+    r.set_deterministic(True)
+    r.load_model(MODELS + "/", "suzanne.obj")
+    for _ in range(6):
+        a = r.generate_image()
+    r.reset_sample_count()
+    r.render_frames(6)
+    b = r.read_image()
+    assert Hh.images_equal(a, b)
+    # resetSampleCount (what a camera change triggers, qt/GLWidget.cpp:80-84) restarts the accumulation
+    r.reset_sample_count()
+    c = r.generate_image()
+    r2 = host.Renderer(0)
+    r2.set_deterministic(True)
+    r2.load_model(MODELS + "/", "suzanne.obj")
+    assert Hh.images_equal(c, r2.generate_image())
+    # moving the camera changes the picture and resets the count
+    r2.set_eye(0.3, 1.0, 3.0)
+    assert r2.info()["sample_count"] == 0
+    moved = r2.generate_image()
+    assert not Hh.images_equal(moved, c)
+    r.close()
+    r2.close()
+
+
+def test_checkpoint_resume(cfg, tmp_path):
+    from pbr_b200 import host
+    cfg.update({"window.width": 64, "window.height": 64})
+    r = host.Renderer(0)
+    r.set_deterministic(True)
+    r.load_model(MODELS + "/", "suzanne.obj")
+    r.render_frames(4)
+    half = r.read_image()
+    host.write_checkpoint(str(tmp_path / "acc.bin"), half, r.info()["sample_count"])
+    r.render_frames(4)
+    full = r.read_image()
+    img, sc = host.read_checkpoint(str(tmp_path / "acc.bin"), 64, 64)
+    assert sc == 4 and Hh.images_equal(img, half)
+    r2 = host.Renderer(0)
+    r2.set_deterministic(True)
+    r2.load_model(MODELS + "/", "suzanne.obj")
+    r2.write_image(img, sc)
+    r2.render_frames(4)
+    assert Hh.images_equal(r2.read_image(), full)
+    r.close()
+    r2.close()
+
+
+def test_synthetic_scene_and_explicit_rays(oracle, cfg):
+    """Soup through Scene.from_arrays: product BVH builder + kernels vs oracle builder + oracle kernels."""
+    import pbr_b200
+    from pbr_b200 import host
+    cfg.update({"window.width": 128, "window.height": 72, "camera.eye.x": 0.0, "camera.eye.y": 0.0, "camera.eye.z": 3.5})
+    sc = pbr_b200.scenes.soup(30000, seed=21)
+    r = host.Renderer(0)
+    r.set_deterministic(True)
+    r.load_scene(sc)
+    img = r.generate_image()
+    p, (want, _, _) = _oracle_for(oracle, cfg, sc, 1)
+    assert Hh.images_equal(img, want)
+    rays = Hh.primary_rays(p, 300, 200)
+    got = r.trace(rays)
+    exp, _ = p.oracle_trace(rays)
+    assert np.array_equal(got["hitFace"], exp["hitFace"]) and np.array_equal(got["leaf"], exp["leaf"])
+    assert np.array_equal(got["t"].view(np.uint32), exp["t"].view(np.uint32))
+    r.close()
+
+
+def test_headless_driver(cfg, tmp_path):
+    from pbr_b200 import host
+    out = tmp_path / "img.pfm"
+    ck = tmp_path / "acc.bin"
+    cmd = [host.HEADLESS_PATH, "--model", MODELS + "/", "suzanne.obj", "--frames", "3", "--deterministic",
+           "--set", "window.width=64", "--set", "window.height=48", "--out", str(out), "--checkpoint", str(ck)]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=120)
+    assert res.returncode == 0, res.stderr
+    assert "Mrays/s" in res.stderr
+    data = open(out, "rb").read()
+    assert data.startswith(b"PF\n64 48\n-1.0\n") and len(data) == len(b"PF\n64 48\n-1.0\n") + 64 * 48 * 12
+    img, sc = host.read_checkpoint(str(ck), 64, 48)
+    assert sc == 3
+    cfg.update({"window.width": 64, "window.height": 48})
+    r = host.Renderer(0)
+    r.set_deterministic(True)
+    r.load_model(MODELS + "/", "suzanne.obj")
+    r.render_frames(3)
+    assert Hh.images_equal(r.read_image(), img)
+    r.close()

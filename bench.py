@@ -52,7 +52,7 @@ FALLBACK_HBM_GBS = 6650.0     # B200_PROFILING.md fallback
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
@@ -359,9 +359,9 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
-def cpu_baseline_sample(w, flat, scene, frames=1):
+def cpu_baseline_sample(w, flat, scene, budget_s=12.0):
     """The CPU oracle (a port of the reference kernels, oracle/pt_oracle.cpp) on all host cores for a
-    bounded sample of the same workload: `frames` frames of the full image at 1 spp."""
+    bounded sample of the same workload: whole frames of the full image at 1 spp for about budget_s."""
     from oracle import oracle as O
     from oracle import scene as S
     threads = os.cpu_count() or 1
@@ -374,11 +374,14 @@ def cpu_baseline_sample(w, flat, scene, frames=1):
     px = S.px_dim(W, H)
     img = np.zeros((H, W, 4), np.float32)
     rays = 0
+    frames = 0
     t0 = time.perf_counter()
-    for k in range(frames):
+    while frames < 1 or (time.perf_counter() - t0) * (frames + 1) / frames < budget_s:
+        k = frames
         img, _, st = O.path_tracing(D, S.frame_seed(k), S.pixel_weight(k), px, cam, flat["nodes"], flat["facesV"],
                                     flat["facesN"], v4, None, mats, None, img, nthreads=threads, debug=False)
         rays += int(st[0]) + int(st[1])
+        frames += 1
     sec = time.perf_counter() - t0
     return {"value": round(rays / sec / 1e6, 3), "unit": "Mrays/s", "cores": threads, "kind": "port",
             "sample": "%d frame(s) of the full %dx%d image at 1 spp (%d rays) in %.1f s" % (frames, W, H, rays, sec)}

@@ -128,9 +128,10 @@ int pbr_set_debug_image(pbr_ctx* ctx, int32_t enabled);
 int pbr_stats(pbr_ctx* ctx, uint64_t out[6], int32_t reset);
 
 /* Issue all device work of this context on a caller-owned CUDA stream (a cudaStream_t passed as
- * void*, e.g. torch.cuda.current_stream().cuda_stream) so that the caller's own copies, collectives
- * and CUDA events are ordered with the kernels.  NULL restores the context's own stream. */
-int pbr_set_stream(pbr_ctx* ctx, void* cuda_stream);
+ * void*, e.g. torch.cuda.current_stream().cuda_stream; 0 is the legacy default stream) so that the
+ * caller's own copies, collectives and CUDA events are ordered with the kernels.
+ * own_stream != 0 ignores the pointer and restores the context's own stream. */
+int pbr_set_stream(pbr_ctx* ctx, void* cuda_stream, int32_t own_stream);
 /* Per-kernel device timing with CUDA events recorded on the launching stream around every launch
  * (the OpenCL queue of the reference is created with CL_QUEUE_PROFILING_ENABLE, CL.cpp:538). */
 typedef struct {

@@ -90,7 +90,7 @@ def load_library():
         "pbr_trace": [vp, u64, u64, u64, u64, i32, vp, i64, i32, vp],
         "pbr_trace_device": [vp, u64, u64, u64, u64, i32, u64, i64, i32, u64],
         "pbr_pinned_math_eval": [vp, i32, vp, vp, i64, vp],
-        "pbr_set_stream": [vp, vp],
+        "pbr_set_stream": [vp, vp, i32],
         "pbr_profile_enable": [vp, i32],
         "pbr_profile_read": [vp, vp, i32],
     }
@@ -265,7 +265,9 @@ class Device:
                                            int(any_hit), hits_mem), "pbr_trace_device")
 
     def setStream(self, cuda_stream):
-        self._ck(self.lib.pbr_set_stream(self.ctx, cuda_stream), "pbr_set_stream")
+        """cuda_stream: integer cudaStream_t handle (0 = legacy default stream); None = the context's own."""
+        own = cuda_stream is None
+        self._ck(self.lib.pbr_set_stream(self.ctx, None if own else C.c_void_p(cuda_stream), int(own)), "pbr_set_stream")
 
     def profileEnable(self, enabled=True):
         self._ck(self.lib.pbr_profile_enable(self.ctx, int(enabled)), "pbr_profile_enable")

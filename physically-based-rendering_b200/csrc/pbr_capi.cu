@@ -295,9 +295,19 @@ bool parseSky(const char* v, pbr_float4* out) {
 	/* "(float4)( %f, %f, %f, 0.0f )" (PathTracer.cpp:470-472, 515) */
 	const char* p = strstr(v, ")(");
 	p = p ? p + 2 : v;
-	float r, g, b;
-	if (sscanf(p, " %f , %f , %f", &r, &g, &b) != 3) return false;
-	out->x = r; out->y = g; out->z = b; out->w = 0.0f;
+	float c[3];
+	for (int i = 0; i < 3; i++) {
+		char* end = nullptr;
+		c[i] = strtof(p, &end);
+		if (end == p) return false;
+		p = end;
+		while (*p == 'f' || *p == 'F' || *p == ' ' || *p == '\t') p++;   /* float-literal suffix */
+		if (i < 2) {
+			if (*p != ',') return false;
+			p++;
+		}
+	}
+	out->x = c[0]; out->y = c[1]; out->z = c[2]; out->w = 0.0f;
 	return true;
 }
 
@@ -674,11 +684,11 @@ int pbr_stats(pbr_ctx* ctx, uint64_t out[6], int32_t reset) {
 	return PBR_OK;
 }
 
-int pbr_set_stream(pbr_ctx* ctx, void* cuda_stream) {
+int pbr_set_stream(pbr_ctx* ctx, void* cuda_stream, int32_t own_stream) {
 	if (!ctx) return PBR_ERR_INVALID;
 	CK(cudaSetDevice(ctx->device));
 	CK(cudaStreamSynchronize(ctx->stream));
-	ctx->stream = cuda_stream ? (cudaStream_t) cuda_stream : ctx->ownStream;
+	ctx->stream = own_stream ? ctx->ownStream : (cudaStream_t) cuda_stream;
 	return PBR_OK;
 }
 

@@ -82,6 +82,7 @@ struct pbr_ctx {
 	QueueCtl qctl = {nullptr, {nullptr, nullptr}};
 	size_t waveCap = 0;
 
+	int nodePhaseMin = 20;                     /* PBR_NODE_PHASE_MIN overrides (tuning) */
 	unsigned long long* stats = nullptr;       /* 6 counters */
 	unsigned long long* cursor64 = nullptr;    /* work cursor of traceRaysKernel */
 };
@@ -343,6 +344,10 @@ int pbr_create(int device, pbr_ctx** out) {
 	}
 	cudaMemset(ctx->stats, 0, 6 * sizeof(unsigned long long));
 	cudaMemset(ctx->qctl.ctrl, 0, 4 * sizeof(uint32_t));
+	if (const char* e = getenv("PBR_NODE_PHASE_MIN")) {
+		const int v = atoi(e);
+		if (v >= 1 && v <= 32) ctx->nodePhaseMin = v;
+	}
 	memset(&ctx->defines, 0, sizeof(ctx->defines));
 	memset(&ctx->args.cam, 0, sizeof(ctx->args.cam));
 	*out = ctx;
@@ -610,6 +615,7 @@ int pbr_kernel_launch(pbr_ctx* ctx, pbr_kernel k) {
 	P.scene.lights = (const pbr_light*) lights->dptr;
 	P.scene.numNodes = ctx->numNodesDev;
 	P.scene.numLights = D.num_lights;
+	P.scene.nodePhaseMin = ctx->nodePhaseMin;
 	P.materials = materials->dptr;
 	P.numMaterials = (int) (materials->bytes / (D.brdf == 0 ? sizeof(pbr_material_schlick) : sizeof(pbr_material_sa)));
 	P.cam = a.cam;
@@ -721,6 +727,7 @@ static int traceImpl(pbr_ctx* ctx, pbr_mem bvh, pbr_mem facesV, pbr_mem vertices
 	S.numNodes = ctx->numNodesDev;
 	S.numLights = 0;
 	S.lights = nullptr;
+	S.nodePhaseMin = ctx->nodePhaseMin;
 	if (num_lights > 0) {
 		Mem* l = getMem(ctx, lights);
 		if (!l || (size_t) num_lights * sizeof(pbr_light) > l->bytes) return fail(ctx, PBR_ERR_INVALID, "pbr_trace: bad lights buffer");

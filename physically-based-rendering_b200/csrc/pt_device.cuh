@@ -45,6 +45,7 @@ struct SceneDev {
 	const pbr_light* lights;
 	int numNodes;
 	int numLights;
+	int nodePhaseMin;             /* traversal engine: leave the node phase below this many stepping lanes */
 };
 
 struct Material {                 /* both reference layouts, widened */

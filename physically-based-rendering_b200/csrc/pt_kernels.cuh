@@ -94,39 +94,181 @@ __global__ void __launch_bounds__(256) raygenKernel(const FrameParams P, const W
 
 /* ------------------------------------------------------------------ traverse */
 
-/* Persistent warps: each warp claims 32 queue slots with one atomic, every lane walks one ray.
- * qsel: which queue holds the live paths; queue pointer NULL = identity (first bounce). */
+/*
+ * Persistent-warp traversal engine shared by the wavefront kernel and the explicit-ray kernel.
+ *
+ * The reference walks the BVH with one work-item per ray and tests a leaf's triangles the moment
+ * the leaf is reached (pt_bvh.cl:82-123).  Run like that on a 32-wide warp, almost every loop trip
+ * has SOME lane in a leaf, so the whole warp pays for the (long) triangle code while only one or two
+ * lanes use it, and a warp lives as long as its slowest ray: ncu showed 5-9 active threads per warp.
+ * Each ray still visits its nodes and triangles in exactly the reference order here -- only the
+ * interleaving BETWEEN rays changes:
+ *   node phase     lanes step through nodes until they reach a leaf whose box is hit ("pending");
+ *                  the phase ends as soon as fewer than SceneDev::nodePhaseMin lanes are still stepping
+ *   triangle phase all pending lanes test their one or two faces together
+ *   retire/refill  lanes whose ray is finished store the result and immediately claim the next
+ *                  ray from the queue (one warp-aggregated atomic), so lanes do not idle while the
+ *                  slowest ray of the original batch finishes
+ */
+
+struct LaneRay {
+	vec3 o, d, invDir;
+	float rt;
+	float tLight;             /* any-hit only: the initial ray.t */
+	int hitFace, hitLeaf;
+	int index;                /* next node to visit; out of (0, numNodes) = finished */
+	uint32_t nn, nt;
+	/* pending leaf */
+	int leafCur, leafF0, leafF1;
+	float leafTNear;
+};
+
+template <bool ANY_HIT>
+__device__ __forceinline__ void startRay(const SceneDev& S, LaneRay& L, const vec3 o, const vec3 d, const float rt, const int hitFace) {
+	L.o = o;
+	L.d = d;
+	L.invDir = v3(pm::rcp(d.x), pm::rcp(d.y), pm::rcp(d.z));
+	L.rt = rt;
+	L.tLight = rt;
+	L.hitFace = hitFace;
+	L.hitLeaf = -1;
+	L.index = 1;
+	L.nn = 0;
+	L.nt = 0;
+	if (S.numLights > 0) traverseLights(S, o, d, L.rt, L.hitFace);
+}
+
+/* One node of the stackless walk (pt_bvh.cl:88-121 without the face tests). Returns true when the
+ * node is a leaf whose box was hit: the faces are tested in the triangle phase. */
+template <bool ANY_HIT>
+__device__ __forceinline__ bool nodeStep(const SceneDev& S, LaneRay& L) {
+	L.nn++;
+	float4 lo, hi;
+	loadNode(S.nodes, L.index, lo, hi);
+	const int cur = L.index;
+	const int loW = __float_as_int(lo.w), hiW = __float_as_int(hi.w);
+
+	L.index = (loW < 0) ? hiW : cur + 1;
+
+	float tNear, tFar;
+	bool isNodeHit = intersectBox(L.o, L.invDir, lo, hi, tNear, tFar) && tFar > PT_EPSILON5;
+	if (!ANY_HIT) isNodeHit = isNodeHit && (L.rt > tNear);
+	if (!isNodeHit) return false;
+
+	L.index = cur + 1;
+	if (loW < 0) return false;
+	L.leafCur = cur;
+	L.leafF0 = loW;
+	L.leafF1 = hiW;
+	L.leafTNear = tNear;
+	return true;
+}
+
+/* intersectFaces (pt_bvh.cl:35-46) for the pending leaf. */
+template <bool ANY_HIT>
+__device__ __forceinline__ void leafStep(const SceneDev& S, LaneRay& L) {
+	intersectFace(S.tris, L.leafF0, L.leafCur, L.o, L.d, L.leafTNear, L.rt, L.hitFace, L.hitLeaf);
+	L.nt++;
+	if (L.leafF1 != -1) {
+		intersectFace(S.tris, L.leafF1, L.leafCur, L.o, L.d, L.leafTNear, L.rt, L.hitFace, L.hitLeaf);
+		L.nt++;
+	}
+	if (ANY_HIT && L.rt < L.tLight) L.index = -1;     /* `break` of traverseShadows (pt_bvh.cl:170-172) */
+}
+
+/* RaySource: bool fetch(i, o, d, rt, hitFace) / void store(i, L).  count = number of rays. */
+template <bool ANY_HIT, typename RaySource, typename Counter>
+__device__ __forceinline__ void traverseEngine(
+	const SceneDev& S, RaySource& src, const Counter count, Counter* cursor,
+	uint32_t& totalNodes, uint32_t& totalTris, uint32_t& totalRays
+) {
+	const unsigned FULL = 0xffffffffu;
+	const int lane = threadIdx.x & 31;
+	const unsigned ltMask = (1u << lane) - 1u;
+
+	LaneRay L;
+	L.index = 0;
+	bool haveRay = false, pending = false, exhausted = false;
+	Counter slot = 0;
+
+	while (true) {
+		/* retire finished rays, refill idle lanes */
+		if (haveRay && !pending && !(L.index > 0 && L.index < S.numNodes)) {
+			src.store(slot, L);
+			totalNodes += L.nn; totalTris += L.nt; totalRays++;
+			haveRay = false;
+		}
+		const unsigned need = __ballot_sync(FULL, !haveRay);
+		if (need && !exhausted) {
+			const int leader = __ffs(need) - 1;
+			const int n = __popc(need);
+			Counter base = 0;
+			if (lane == leader) base = atomicAdd(cursor, (Counter) n);
+			base = __shfl_sync(FULL, base, leader);
+			if (!haveRay) {
+				const Counter i = base + (Counter) __popc(need & ltMask);
+				if (i < count) {
+					vec3 o, d;
+					float rt;
+					int hf;
+					src.fetch(i, o, d, rt, hf);
+					startRay<ANY_HIT>(S, L, o, d, rt, hf);
+					slot = i;
+					haveRay = true;
+				}
+			}
+			if (base + (Counter) n >= count) exhausted = true;
+		}
+		if (!__any_sync(FULL, haveRay)) break;
+
+		/* node phase */
+		while (true) {
+			const bool stepping = haveRay && !pending && (L.index > 0 && L.index < S.numNodes);
+			if (stepping) pending = nodeStep<ANY_HIT>(S, L);
+			const bool still = haveRay && !pending && (L.index > 0 && L.index < S.numNodes);
+			if (__popc(__ballot_sync(FULL, still)) < S.nodePhaseMin) break;
+		}
+
+		/* triangle phase */
+		if (pending) {
+			leafStep<ANY_HIT>(S, L);
+			pending = false;
+		}
+	}
+}
+
+struct WaveRaySource {
+	const WaveState& W;
+	const uint32_t* queue;
+	uint32_t p;
+	__device__ __forceinline__ void fetch(uint32_t i, vec3& o, vec3& d, float& rt, int& hf) {
+		p = queue ? queue[i] : i;
+		const float4 a = W.rayO[p], b = W.rayD[p];
+		o = v3(a.x, a.y, a.z); rt = a.w;
+		d = v3(b.x, b.y, b.z); hf = __float_as_int(b.w);
+	}
+	__device__ __forceinline__ void store(uint32_t, const LaneRay& L) {
+		W.rayO[p].w = L.rt;
+		W.rayD[p].w = __int_as_float(L.hitFace);
+		uint2 g = W.dbg[p];
+		g.x += L.nn; g.y += L.nt;
+		W.dbg[p] = g;
+	}
+};
+
+/* Closest-hit traversal of every live path.  queue pointer NULL = identity (first bounce). */
 __global__ void __launch_bounds__(128) traverseKernel(
 	const SceneDev S, const WaveState W, const uint32_t* __restrict__ queue, const uint32_t* __restrict__ countPtr,
 	uint32_t* cursor, uint32_t* countToReset, unsigned long long* stats
 ) {
 	const uint32_t count = *countPtr;
-	const int lane = threadIdx.x & 31;
 	uint32_t nodes = 0, tris = 0, rays = 0;
 	/* the other queue was consumed by the previous shade launch: empty it for the next one */
 	if (blockIdx.x == 0 && threadIdx.x == 0) *countToReset = 0u;
 
-	while (true) {
-		uint32_t base = 0;
-		if (lane == 0) base = atomicAdd(cursor, 32u);
-		base = __shfl_sync(0xffffffffu, base, 0);
-		if (base >= count) break;
-		const uint32_t i = base + lane;
-		if (i < count) {
-			const uint32_t p = queue ? queue[i] : i;
-			const float4 o = W.rayO[p], d = W.rayD[p];
-			float rt = o.w;
-			int hitFace = __float_as_int(d.w), hitLeaf = -1;
-			uint32_t nn = 0, nt = 0;
-			traverseClosest(S, v3(o.x, o.y, o.z), v3(d.x, d.y, d.z), rt, hitFace, hitLeaf, nn, nt);
-			W.rayO[p].w = rt;
-			W.rayD[p].w = __int_as_float(hitFace);
-			uint2 g = W.dbg[p];
-			g.x += nn; g.y += nt;
-			W.dbg[p] = g;
-			nodes += nn; tris += nt; rays++;
-		}
-	}
+	WaveRaySource src = {W, queue, 0u};
+	traverseEngine<false>(S, src, count, cursor, nodes, tris, rays);
+
 	warpAddStat(stats + 0, rays);
 	warpAddStat(stats + 2, nodes);
 	warpAddStat(stats + 3, tris);
@@ -233,36 +375,35 @@ __global__ void __launch_bounds__(128) megaKernel(const FrameParams P, const int
 
 /* ------------------------------------------------------------------ explicit rays (C5) */
 
+struct ExplicitRaySource {
+	const pbr_ray* __restrict__ rays;
+	pbr_hit* __restrict__ hits;
+	__device__ __forceinline__ void fetch(unsigned long long i, vec3& o, vec3& d, float& rt, int& hf) {
+		const float4 a = __ldg((const float4*) &rays[i].origin);
+		const float4 b = __ldg((const float4*) &rays[i].dir);
+		o = v3(a.x, a.y, a.z);
+		d = v3(b.x, b.y, b.z);
+		rt = b.w;
+		hf = 0;
+	}
+	__device__ __forceinline__ void store(unsigned long long i, const LaneRay& L) {
+		int4 out;
+		out.x = __float_as_int(L.rt);
+		out.y = L.hitFace;
+		out.z = L.hitLeaf;
+		out.w = (int) (min(L.nn, 0xfffffu) | (min(L.nt, 0xfffu) << 20));
+		*((int4*) &hits[i]) = out;
+	}
+};
+
 template <bool ANY_HIT>
 __global__ void __launch_bounds__(128) traceRaysKernel(
 	const SceneDev S, const pbr_ray* __restrict__ rays, const long long n, pbr_hit* __restrict__ hits,
 	unsigned long long* cursor, unsigned long long* stats
 ) {
-	const int lane = threadIdx.x & 31;
 	uint32_t nodes = 0, tris = 0, cnt = 0;
-	while (true) {
-		unsigned long long base = 0;
-		if (lane == 0) base = atomicAdd(cursor, 32ull);
-		base = __shfl_sync(0xffffffffu, base, 0);
-		if ((long long) base >= n) break;
-		const long long i = (long long) base + lane;
-		if (i < n) {
-			const float4 o = __ldg((const float4*) &rays[i].origin);
-			const float4 d = __ldg((const float4*) &rays[i].dir);
-			float rt = d.w;
-			int hitFace = 0, hitLeaf = -1;
-			uint32_t nn = 0, nt = 0;
-			if (ANY_HIT) traverseAny(S, v3(o.x, o.y, o.z), v3(d.x, d.y, d.z), rt, hitFace, hitLeaf, nn, nt);
-			else traverseClosest(S, v3(o.x, o.y, o.z), v3(d.x, d.y, d.z), rt, hitFace, hitLeaf, nn, nt);
-			nodes += nn; tris += nt; cnt++;
-			int4 out;
-			out.x = __float_as_int(rt);
-			out.y = hitFace;
-			out.z = hitLeaf;
-			out.w = (int) (min(nn, 0xfffffu) | (min(nt, 0xfffu) << 20));
-			*((int4*) &hits[i]) = out;
-		}
-	}
+	ExplicitRaySource src = {rays, hits};
+	traverseEngine<ANY_HIT>(S, src, (unsigned long long) n, cursor, nodes, tris, cnt);
 	warpAddStat(stats + (ANY_HIT ? 1 : 0), cnt);
 	warpAddStat(stats + (ANY_HIT ? 5 : 2), nodes);
 	warpAddStat(stats + 3, tris);

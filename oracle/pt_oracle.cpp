@@ -1422,6 +1422,31 @@ void oracle_trace_bruteforce(
 	}
 }
 
+/* Analysis helper: how often each BVH node is visited by traverse() for a set of rays. */
+void oracle_visit_histogram(
+	const pbr_defines* D, const pbr_bvh_node* bvh, const pbr_ray* rays, int64_t n, uint32_t* counts
+) {
+	const int N = D->bvh_num_nodes;
+	for (int64_t i = 0; i < n; i++) {
+		const vec3 o = xyz(rays[i].origin), d = xyz(rays[i].dir);
+		ray4 ray;
+		ray.origin = o; ray.dir = d; ray.t = rays[i].dir.w;
+		const vec3 invDir = v3(pm::rcp(d.x), pm::rcp(d.y), pm::rcp(d.z));
+		int index = 1;
+		int prevLine = -1;
+		do {
+			counts[index]++;
+			if ((index >> 2) != prevLine) { counts[0]++; prevLine = index >> 2; }   /* counts[0]: 128-byte line switches */
+			const pbr_bvh_node node = bvh[index];
+			const int cur = index;
+			index = (node.bbMin.w <= -1.0f) ? (int) node.bbMax.w : cur + 1;
+			float tNear = 0.0f, tFar = INF_F;
+			if (!(intersectBox(&ray, &invDir, node.bbMin, node.bbMax, &tNear, &tFar) && tFar > EPSILON5)) continue;
+			index = cur + 1;   /* no t pruning: upper bound of the visit pattern */
+		} while (index > 0 && index < N);
+	}
+}
+
 /* Scalar entry points of the pinned math, for tests/test_pinned_math.py. */
 float oracle_pm_sin(float x) { return pm::sin_(x); }
 float oracle_pm_cos(float x) { return pm::cos_(x); }

@@ -83,6 +83,7 @@ struct pbr_ctx {
 	size_t waveCap = 0;
 
 	int nodePhaseMin = 20;                     /* PBR_NODE_PHASE_MIN overrides (tuning) */
+	int refillMin = 4;                         /* PBR_REFILL_MIN overrides (tuning) */
 	unsigned long long* stats = nullptr;       /* 6 counters */
 	unsigned long long* cursor64 = nullptr;    /* work cursor of traceRaysKernel */
 };
@@ -210,7 +211,7 @@ int ensureScene(pbr_ctx* ctx, pbr_mem hBvh, pbr_mem hFacesV, pbr_mem hVertices, 
 	if ((size_t) numFaces > ctx->trisCap || !ctx->tris) {
 		if (ctx->tris) cudaFree(ctx->tris);
 		ctx->tris = nullptr;
-		CK(cudaMalloc(&ctx->tris, (size_t) (numFaces > 0 ? numFaces : 1) * 48));
+		CK(cudaMalloc(&ctx->tris, (size_t) (numFaces > 0 ? numFaces : 1) * 16 * PT_TRI_STRIDE));
 		ctx->trisCap = (size_t) numFaces;
 	}
 	{
@@ -347,6 +348,10 @@ int pbr_create(int device, pbr_ctx** out) {
 	if (const char* e = getenv("PBR_NODE_PHASE_MIN")) {
 		const int v = atoi(e);
 		if (v >= 1 && v <= 32) ctx->nodePhaseMin = v;
+	}
+	if (const char* e = getenv("PBR_REFILL_MIN")) {
+		const int v = atoi(e);
+		if (v >= 1 && v <= 32) ctx->refillMin = v;
 	}
 	memset(&ctx->defines, 0, sizeof(ctx->defines));
 	memset(&ctx->args.cam, 0, sizeof(ctx->args.cam));
@@ -616,6 +621,7 @@ int pbr_kernel_launch(pbr_ctx* ctx, pbr_kernel k) {
 	P.scene.numNodes = ctx->numNodesDev;
 	P.scene.numLights = D.num_lights;
 	P.scene.nodePhaseMin = ctx->nodePhaseMin;
+	P.scene.refillMin = ctx->refillMin;
 	P.materials = materials->dptr;
 	P.numMaterials = (int) (materials->bytes / (D.brdf == 0 ? sizeof(pbr_material_schlick) : sizeof(pbr_material_sa)));
 	P.cam = a.cam;
@@ -728,6 +734,7 @@ static int traceImpl(pbr_ctx* ctx, pbr_mem bvh, pbr_mem facesV, pbr_mem vertices
 	S.numLights = 0;
 	S.lights = nullptr;
 	S.nodePhaseMin = ctx->nodePhaseMin;
+	S.refillMin = ctx->refillMin;
 	if (num_lights > 0) {
 		Mem* l = getMem(ctx, lights);
 		if (!l || (size_t) num_lights * sizeof(pbr_light) > l->bytes) return fail(ctx, PBR_ERR_INVALID, "pbr_trace: bad lights buffer");

@@ -15,9 +15,11 @@
  *            INTEGER bit patterns instead of float-encoded indices:
  *              lo.w  >= 0: leaf, index of its first face;   < 0: inner node
  *              hi.w  leaf: index of its second face or -1;  inner: miss link or -1 (stop)
- *   tris   : 48 B per face in leaf order (3 x float4):  (a.xyz, material index bits),
- *            (edge1.xyz, 0), (edge2.xyz, 0) with edge1 = b - a, edge2 = c - a  -- the reference
- *            fetches facesV[f] and then three dependent vertices (pt_intersect.cl:146-149).
+ *   tris   : 64 B per face in leaf order: one 256-bit load (a.xyz, material index bits, edge1.xyz, 0)
+ *            and one 128-bit load (edge2.xyz, 0), with edge1 = b - a, edge2 = c - a -- the reference
+ *            fetches facesV[f] and then three dependent vertices (pt_intersect.cl:146-149).  The L1
+ *            data stage serves one 128-byte line per cycle and per load instruction of a divergent
+ *            warp, so the number of load instructions per triangle (2 instead of 4) is what counts.
  */
 #pragma once
 
@@ -41,11 +43,12 @@ using pm::v3;
 
 struct SceneDev {
 	const float4* nodes;          /* 2 x float4 per node */
-	const float4* tris;           /* 3 x float4 per face */
+	const float4* tris;           /* 4 x float4 (64 B) per face */
 	const pbr_light* lights;
 	int numNodes;
 	int numLights;
 	int nodePhaseMin;             /* traversal engine: leave the node phase below this many stepping lanes */
+	int refillMin;                /* traversal engine: claim new rays once this many lanes are idle */
 };
 
 struct Material {                 /* both reference layouts, widened */
@@ -78,6 +81,17 @@ __device__ __forceinline__ void loadNode(const float4* nodes, int index, float4&
 		: "l"(nodes + 2 * (size_t) index));
 }
 
+#define PT_TRI_STRIDE 4           /* float4s per triangle record */
+
+/* (a.xyz, material bits) + edge1 with one 256-bit load, edge2 with one 128-bit load. */
+__device__ __forceinline__ void loadTri(const float4* tris, int face, float4& A, float4& E1, float4& E2) {
+	const float4* p = tris + PT_TRI_STRIDE * (size_t) face;
+	asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+		: "=f"(A.x), "=f"(A.y), "=f"(A.z), "=f"(A.w), "=f"(E1.x), "=f"(E1.y), "=f"(E1.z), "=f"(E1.w)
+		: "l"(p));
+	E2 = __ldg(p + 2);
+}
+
 __device__ __forceinline__ vec3 f4xyz(const float4& f) { return v3(f.x, f.y, f.z); }
 /* OpenCL `vector + scalar` */
 __device__ __forceinline__ vec3 adds(const vec3 a, const float s) { return v3(a.x + s, a.y + s, a.z + s); }
@@ -92,9 +106,8 @@ __device__ __forceinline__ void intersectFace(
 	const vec3 o, const vec3 d, const float tNear,
 	float& rt, int& hitFace, int& hitLeaf
 ) {
-	const float4 A = __ldg(tris + 3 * (size_t) face);
-	const float4 E1 = __ldg(tris + 3 * (size_t) face + 1);
-	const float4 E2 = __ldg(tris + 3 * (size_t) face + 2);
+	float4 A, E1, E2;
+	loadTri(tris, face, A, E1, E2);
 
 	const float f = fmaxf(0.0f, tNear - 0.001f);
 	const vec3 closeOrigin = pm::fma3(d, f, o);
@@ -644,9 +657,8 @@ __device__ __forceinline__ BounceResult bounce(const FrameParams& P, PathState& 
 		return PATH_SAMPLE_DONE;
 	}
 
-	const float4 A = __ldg(S.tris + 3 * (size_t) s.hitFace);
-	const float4 E1 = __ldg(S.tris + 3 * (size_t) s.hitFace + 1);
-	const float4 E2 = __ldg(S.tris + 3 * (size_t) s.hitFace + 2);
+	float4 A, E1, E2;
+	loadTri(S.tris, s.hitFace, A, E1, E2);
 	const Material mtl = fetchMaterial<BRDF>(P.materials, P.numMaterials, (uint32_t) __float_as_int(A.w));
 	vec3 normal = pm::normalize(pm::cross(f4xyz(E1), f4xyz(E2)));
 

@@ -106,9 +106,9 @@ __global__ void __launch_bounds__(256) raygenKernel(const FrameParams P, const W
  *   node phase     lanes step through nodes until they reach a leaf whose box is hit ("pending");
  *                  the phase ends as soon as fewer than SceneDev::nodePhaseMin lanes are still stepping
  *   triangle phase all pending lanes test their one or two faces together
- *   retire/refill  lanes whose ray is finished store the result and immediately claim the next
- *                  ray from the queue (one warp-aggregated atomic), so lanes do not idle while the
- *                  slowest ray of the original batch finishes
+ *   retire/refill  lanes whose ray is finished store the result; once SceneDev::refillMin lanes are
+ *                  idle they claim the next rays from the queue together (one warp-aggregated
+ *                  atomic), so lanes do not idle while the slowest ray of a batch finishes
  */
 
 struct LaneRay {
@@ -199,7 +199,7 @@ __device__ __forceinline__ void traverseEngine(
 			haveRay = false;
 		}
 		const unsigned need = __ballot_sync(FULL, !haveRay);
-		if (need && !exhausted) {
+		if (!exhausted && (__popc(need) >= S.refillMin || need == FULL)) {
 			const int leader = __ffs(need) - 1;
 			const int n = __popc(need);
 			Counter base = 0;
@@ -444,9 +444,10 @@ __global__ void repackTrisKernel(
 	const uint4 fv = facesV[f];
 	const uint32_t last = (uint32_t) (numVertices - 1);
 	const float4 a = vertices[min(fv.x, last)], b = vertices[min(fv.y, last)], c = vertices[min(fv.z, last)];
-	tris[3 * (size_t) f] = make_float4(a.x, a.y, a.z, __int_as_float((int) fv.w));
-	tris[3 * (size_t) f + 1] = make_float4(b.x - a.x, b.y - a.y, b.z - a.z, 0.0f);
-	tris[3 * (size_t) f + 2] = make_float4(c.x - a.x, c.y - a.y, c.z - a.z, 0.0f);
+	tris[PT_TRI_STRIDE * (size_t) f] = make_float4(a.x, a.y, a.z, __int_as_float((int) fv.w));
+	tris[PT_TRI_STRIDE * (size_t) f + 1] = make_float4(b.x - a.x, b.y - a.y, b.z - a.z, 0.0f);
+	tris[PT_TRI_STRIDE * (size_t) f + 2] = make_float4(c.x - a.x, c.y - a.y, c.z - a.z, 0.0f);
+	tris[PT_TRI_STRIDE * (size_t) f + 3] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
 }
 
 /* ------------------------------------------------------------------ pinned-math probe */

@@ -147,6 +147,134 @@ def displaced_grid(cells_x=2237, cells_z=2236, patches=8, seed=777, size=2.0, he
                    object_names=["patch%02d" % i for i in range(patches * patches)])
 
 
+class _Mesh:
+    """Accumulates indexed triangles with per-vertex normals, object by object."""
+
+    def __init__(self):
+        self.v, self.n, self.f, self.m, self.counts, self.names = [], [], [], [], [], []
+        self.nv = 0
+
+    def add(self, name, verts, normals, faces, mtl):
+        verts = np.asarray(verts, f32).reshape(-1, 3)
+        normals = np.asarray(normals, f32).reshape(-1, 3)
+        faces = np.asarray(faces, np.uint32).reshape(-1, 3)
+        assert len(verts) == len(normals)
+        self.v.append(verts)
+        self.n.append(normals)
+        self.f.append(faces + np.uint32(self.nv))
+        mtl = np.asarray(mtl, np.int32)
+        self.m.append(np.broadcast_to(mtl, (len(faces),)).astype(np.int32))
+        self.counts.append(len(faces))
+        self.names.append(name)
+        self.nv += len(verts)
+
+    def grid(self, name, origin, du, dv, nu, nv, normal, mtl):
+        """nu x nv quads spanning origin + s*du + t*dv; mtl may be a function (i, j) -> index."""
+        s, t = np.meshgrid(np.arange(nu + 1, dtype=f32) / f32(nu), np.arange(nv + 1, dtype=f32) / f32(nv), indexing="xy")
+        P = (np.asarray(origin, f32)[None, None] + s[..., None] * np.asarray(du, f32)[None, None] +
+             t[..., None] * np.asarray(dv, f32)[None, None]).astype(f32)
+        i, j = np.meshgrid(np.arange(nu), np.arange(nv), indexing="xy")
+        a = (j * (nu + 1) + i).reshape(-1)
+        faces = np.stack([np.stack([a, a + 1, a + nu + 2], -1), np.stack([a, a + nu + 2, a + nu + 1], -1)], 1).reshape(-1, 3)
+        m = mtl if not callable(mtl) else np.repeat(mtl(i.reshape(-1), j.reshape(-1)), 2)
+        self.add(name, P.reshape(-1, 3), np.broadcast_to(np.asarray(normal, f32), (P.size // 3, 3)), faces, m)
+
+    def revolve(self, name, centre, radius_fn, y0, y1, segments, rings, mtl):
+        """Surface of revolution around the y axis through `centre`: radius_fn(t in [0,1]) -> radius."""
+        t = np.arange(rings + 1, dtype=f32) / f32(rings)
+        ang = np.arange(segments + 1, dtype=f32) * f32(2.0 * np.pi / segments)
+        r = radius_fn(t).astype(f32)
+        y = (f32(y0) + t * f32(y1 - y0)).astype(f32)
+        ca, sa = np.cos(ang).astype(f32), np.sin(ang).astype(f32)
+        P = np.stack([centre[0] + r[:, None] * ca[None], np.broadcast_to(y[:, None], (rings + 1, segments + 1)),
+                      centre[2] + r[:, None] * sa[None]], -1).astype(f32)
+        dr = np.gradient(r.astype(np.float64), y.astype(np.float64))
+        N = np.stack([ca[None] * np.ones_like(dr)[:, None], np.broadcast_to(-dr[:, None], (rings + 1, segments + 1)),
+                      sa[None] * np.ones_like(dr)[:, None]], -1)
+        N = (N / np.linalg.norm(N, axis=-1, keepdims=True)).astype(f32)
+        i, j = np.meshgrid(np.arange(segments), np.arange(rings), indexing="xy")
+        a = (j * (segments + 1) + i).reshape(-1)
+        faces = np.stack([np.stack([a, a + segments + 2, a + 1], -1), np.stack([a, a + segments + 1, a + segments + 2], -1)], 1)
+        self.add(name, P.reshape(-1, 3), N.reshape(-1, 3), faces.reshape(-1, 3), mtl)
+
+    def arch(self, name, a, b, height, tube, segments, rings, mtl):
+        """Half torus from point a to point b (same y), rising by `height`."""
+        a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+        mid, half = (a + b) / 2, (b - a) / 2
+        R = np.linalg.norm(half)
+        ex = half / R
+        up = np.array([0.0, 1.0, 0.0])
+        ez = np.cross(ex, up)
+        th = np.arange(segments + 1) * (np.pi / segments)
+        ph = np.arange(rings + 1) * (2 * np.pi / rings)
+        cth, sth = np.cos(th), np.sin(th) * (height / R)
+        centre = mid[None] - cth[:, None] * R * ex[None] + sth[:, None] * R * up[None]
+        radial = -cth[:, None] * ex[None] + (np.sin(th))[:, None] * up[None]
+        P = centre[:, None] + tube * (np.cos(ph)[None, :, None] * radial[:, None] + np.sin(ph)[None, :, None] * ez[None, None])
+        N = np.cos(ph)[None, :, None] * radial[:, None] + np.sin(ph)[None, :, None] * ez[None, None]
+        N = N / np.linalg.norm(N, axis=-1, keepdims=True)
+        i, j = np.meshgrid(np.arange(rings), np.arange(segments), indexing="xy")
+        q = (j * (rings + 1) + i).reshape(-1)
+        faces = np.stack([np.stack([q, q + 1, q + rings + 2], -1), np.stack([q, q + rings + 2, q + rings + 1], -1)], 1)
+        self.add(name, P.reshape(-1, 3).astype(f32), N.reshape(-1, 3).astype(f32), faces.reshape(-1, 3), mtl)
+
+    def finish(self, materials, lights=None):
+        v = np.concatenate(self.v)
+        n = np.concatenate(self.n)
+        f = np.concatenate(self.f)
+        return _finish(v.reshape(-1), f.reshape(-1), np.concatenate(self.m), self.counts, materials,
+                       normals=n.reshape(-1), facesVN=f.reshape(-1), lights=lights, object_names=self.names)
+
+
+def interior(detail=1.0, with_light=True):
+    """BASELINE config 3: procedural interior (~260 k triangles at detail = 1): a room with an open
+    ceiling, a tiled floor, two rows of fluted columns joined by arches, two spheres; 8 materials, diffuse
+    (nu = nv = 0, Rs = 0, Rd = 1 / rough = 1) and glossy-to-specular (nu = nv in {100, 1000}, Rs 0.8 /
+    rough in {0, 0.3}).  Vertex normals are written, faces are `v//vn`."""
+    d = float(detail)
+
+    def k(x):
+        return max(2, int(round(x * d)))
+    mats = [
+        default_material("floor_light", Kd=(0.75, 0.72, 0.68), rough=1.0),
+        default_material("floor_dark", Kd=(0.25, 0.24, 0.22), nu=100.0, nv=100.0, Rs=0.8, Rd=0.6, rough=0.3),
+        default_material("wall", Kd=(0.8, 0.78, 0.7), rough=1.0),
+        default_material("wall_accent", Kd=(0.55, 0.2, 0.15), rough=1.0),
+        default_material("column", Kd=(0.85, 0.85, 0.8), nu=100.0, nv=100.0, Rs=0.3, Rd=0.9, rough=0.3),
+        default_material("arch", Kd=(0.7, 0.6, 0.4), nu=1000.0, nv=1000.0, Rs=0.8, Rd=0.5, rough=0.0),
+        default_material("mirror", Kd=(0.95, 0.95, 0.95), Ks=(1.0, 1.0, 1.0), nu=1000.0, nv=1000.0, Rs=0.8, Rd=0.1, rough=0.0),
+        default_material("glass", Kd=(0.9, 0.95, 1.0), d=0.3, Ni=1.5, nu=1000.0, nv=1000.0, Rs=0.8, Rd=0.2, rough=0.0),
+    ]
+    M = _Mesh()
+    X, Z, Hh = 4.0, 6.0, 3.2
+    nt = k(100)
+    M.grid("floor", (-X, 0, -Z), (2 * X, 0, 0), (0, 0, 2 * Z), nt, nt, (0, 1, 0), lambda i, j: ((i + j) & 1).astype(np.int32))
+    wq = (k(60), k(30))
+    M.grid("wall_back", (-X, 0, -Z), (2 * X, 0, 0), (0, Hh, 0), wq[0], wq[1], (0, 0, 1), 2)
+    M.grid("wall_front", (X, 0, Z), (-2 * X, 0, 0), (0, Hh, 0), wq[0], wq[1], (0, 0, -1), 2)
+    M.grid("wall_left", (-X, 0, Z), (0, 0, -2 * Z), (0, Hh, 0), wq[0], wq[1], (1, 0, 0), lambda i, j: np.where(j < wq[1] // 4, 3, 2).astype(np.int32))
+    M.grid("wall_right", (X, 0, -Z), (0, 0, 2 * Z), (0, Hh, 0), wq[0], wq[1], (-1, 0, 0), lambda i, j: np.where(j < wq[1] // 4, 3, 2).astype(np.int32))
+    seg, rings = k(96), k(80)
+
+    def flute(t):
+        # base, entasis, capital
+        r = 0.22 - 0.04 * t + 0.06 * np.exp(-((t - 0.02) / 0.03) ** 2) + 0.07 * np.exp(-((t - 0.98) / 0.03) ** 2)
+        return r
+    zs = np.linspace(-Z + 1.0, Z - 1.0, 6)
+    for side, x in enumerate((-2.2, 2.2)):
+        for ci, z in enumerate(zs):
+            M.revolve("column_%d_%d" % (side, ci), (x, 0.0, z), flute, 0.0, 2.4, seg, rings, 4)
+        for ci in range(len(zs) - 1):
+            M.arch("arch_%d_%d" % (side, ci), (x, 2.4, zs[ci]), (x, 2.4, zs[ci + 1]), 0.6, 0.09, k(48), k(24), 5)
+
+    def ball(t):
+        return 0.55 * np.sqrt(np.maximum(1e-6, 1.0 - (2 * t - 1) ** 2))
+    M.revolve("sphere_mirror", (-0.8, 0.0, -1.5), ball, 0.0, 1.1, k(64), k(48), 6)
+    M.revolve("sphere_glass", (0.9, 0.0, 0.6), ball, 0.0, 1.1, k(64), k(48), 7)
+    lights = np.array([[1, 0.0, 3.0, 0.0, 0.0, 1.0, 0.95, 0.9, 0.0, 0.0]], f32) if with_light else None
+    return M.finish(mats, lights)
+
+
 def write_obj(scene, path):
     """Write <path>.obj / .mtl (/.lights) in the dialect the reference's parsers read: one `o` per
     object, `usemtl` on material change, `f v v v` or `f v//vn v//vn v//vn`, single blanks."""

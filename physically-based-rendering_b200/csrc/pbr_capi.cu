@@ -82,7 +82,7 @@ struct pbr_ctx {
 	QueueCtl qctl = {nullptr, {nullptr, nullptr}};
 	size_t waveCap = 0;
 
-	int nodePhaseMin = 20;                     /* PBR_NODE_PHASE_MIN overrides (tuning) */
+	int nodePhaseMin = 16;                     /* PBR_NODE_PHASE_MIN overrides (tuning) */
 	int refillMin = 4;                         /* PBR_REFILL_MIN overrides (tuning) */
 	unsigned long long* stats = nullptr;       /* 6 counters */
 	unsigned long long* cursor64 = nullptr;    /* work cursor of traceRaysKernel */

@@ -138,13 +138,11 @@ __device__ __forceinline__ void startRay(const SceneDev& S, LaneRay& L, const ve
 	if (S.numLights > 0) traverseLights(S, o, d, L.rt, L.hitFace);
 }
 
-/* One node of the stackless walk (pt_bvh.cl:88-121 without the face tests). Returns true when the
- * node is a leaf whose box was hit: the faces are tested in the triangle phase. */
+/* One node of the stackless walk (pt_bvh.cl:88-121 without the face tests), node already loaded.
+ * Returns true when the node is a leaf whose box was hit: the faces are tested in the triangle phase. */
 template <bool ANY_HIT>
-__device__ __forceinline__ bool nodeStep(const SceneDev& S, LaneRay& L) {
+__device__ __forceinline__ bool nodeVisit(LaneRay& L, const float4 lo, const float4 hi) {
 	L.nn++;
-	float4 lo, hi;
-	loadNode(S.nodes, L.index, lo, hi);
 	const int cur = L.index;
 	const int loW = __float_as_int(lo.w), hiW = __float_as_int(hi.w);
 
@@ -164,6 +162,13 @@ __device__ __forceinline__ bool nodeStep(const SceneDev& S, LaneRay& L) {
 	return true;
 }
 
+template <bool ANY_HIT>
+__device__ __forceinline__ bool nodeStep(const SceneDev& S, LaneRay& L) {
+	float4 lo, hi;
+	loadNode(S.nodes, L.index, lo, hi);
+	return nodeVisit<ANY_HIT>(L, lo, hi);
+}
+
 /* intersectFaces (pt_bvh.cl:35-46) for the pending leaf. */
 template <bool ANY_HIT>
 __device__ __forceinline__ void leafStep(const SceneDev& S, LaneRay& L) {
@@ -177,6 +182,9 @@ __device__ __forceinline__ void leafStep(const SceneDev& S, LaneRay& L) {
 }
 
 /* RaySource: bool fetch(i, o, d, rt, hitFace) / void store(i, L).  count = number of rays. */
+/* Lane states of the traversal engine. */
+enum { LANE_IDLE = 0, LANE_STEPPING = 1, LANE_PENDING = 2, LANE_FINISHED = 3 };
+
 template <bool ANY_HIT, typename RaySource, typename Counter>
 __device__ __forceinline__ void traverseEngine(
 	const SceneDev& S, RaySource& src, const Counter count, Counter* cursor,
@@ -185,27 +193,29 @@ __device__ __forceinline__ void traverseEngine(
 	const unsigned FULL = 0xffffffffu;
 	const int lane = threadIdx.x & 31;
 	const unsigned ltMask = (1u << lane) - 1u;
+	const unsigned lastNode = (unsigned) (S.numNodes - 1);      /* valid indices: 1 .. numNodes-1 */
 
 	LaneRay L;
 	L.index = 0;
-	bool haveRay = false, pending = false, exhausted = false;
+	int state = LANE_IDLE;
+	bool exhausted = false;
 	Counter slot = 0;
 
 	while (true) {
 		/* retire finished rays, refill idle lanes */
-		if (haveRay && !pending && !(L.index > 0 && L.index < S.numNodes)) {
+		if (state == LANE_FINISHED) {
 			src.store(slot, L);
 			totalNodes += L.nn; totalTris += L.nt; totalRays++;
-			haveRay = false;
+			state = LANE_IDLE;
 		}
-		const unsigned need = __ballot_sync(FULL, !haveRay);
+		const unsigned need = __ballot_sync(FULL, state == LANE_IDLE);
 		if (!exhausted && (__popc(need) >= S.refillMin || need == FULL)) {
 			const int leader = __ffs(need) - 1;
 			const int n = __popc(need);
 			Counter base = 0;
 			if (lane == leader) base = atomicAdd(cursor, (Counter) n);
 			base = __shfl_sync(FULL, base, leader);
-			if (!haveRay) {
+			if (state == LANE_IDLE) {
 				const Counter i = base + (Counter) __popc(need & ltMask);
 				if (i < count) {
 					vec3 o, d;
@@ -214,25 +224,27 @@ __device__ __forceinline__ void traverseEngine(
 					src.fetch(i, o, d, rt, hf);
 					startRay<ANY_HIT>(S, L, o, d, rt, hf);
 					slot = i;
-					haveRay = true;
+					state = (lastNode >= 1u) ? LANE_STEPPING : LANE_FINISHED;
 				}
 			}
 			if (base + (Counter) n >= count) exhausted = true;
 		}
-		if (!__any_sync(FULL, haveRay)) break;
+		if (__ballot_sync(FULL, state != LANE_IDLE) == 0u) break;
 
-		/* node phase */
+		/* node phase: index stays inside [1, numNodes) while a lane is stepping */
 		while (true) {
-			const bool stepping = haveRay && !pending && (L.index > 0 && L.index < S.numNodes);
-			if (stepping) pending = nodeStep<ANY_HIT>(S, L);
-			const bool still = haveRay && !pending && (L.index > 0 && L.index < S.numNodes);
-			if (__popc(__ballot_sync(FULL, still)) < S.nodePhaseMin) break;
+			if (state == LANE_STEPPING) {
+				const bool leaf = nodeStep<ANY_HIT>(S, L);
+				const bool inside = (unsigned) (L.index - 1) < lastNode;
+				state = leaf ? LANE_PENDING : (inside ? LANE_STEPPING : LANE_FINISHED);
+			}
+			if (__popc(__ballot_sync(FULL, state == LANE_STEPPING)) < S.nodePhaseMin) break;
 		}
 
 		/* triangle phase */
-		if (pending) {
+		if (state == LANE_PENDING) {
 			leafStep<ANY_HIT>(S, L);
-			pending = false;
+			state = ((unsigned) (L.index - 1) < lastNode) ? LANE_STEPPING : LANE_FINISHED;
 		}
 	}
 }

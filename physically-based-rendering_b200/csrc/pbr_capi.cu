@@ -72,13 +72,15 @@ struct pbr_ctx {
 	float4* nodes = nullptr;
 	float4* tris = nullptr;
 	size_t nodesCap = 0, trisCap = 0;
-	pbr_mem cacheBvh = 0, cacheFacesV = 0, cacheVertices = 0;
+	pbr_mem cacheBvh = 0, cacheFacesV = 0, cacheVertices = 0, cacheFacesN = 0, cacheNormals = 0;
+	bool cachePhong = false;
 	int cacheNumNodes = -1;
 	uint64_t sceneEpoch = 0, cacheEpoch = ~0ull;
 	int numNodesDev = 0;
 
 	/* wavefront state */
-	WaveState wave = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+	WaveState wave = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+	float4* hitN = nullptr;                    /* allocated with the wave state, used when PHONGTESS */
 	QueueCtl qctl = {nullptr, {nullptr, nullptr}};
 	size_t waveCap = 0;
 
@@ -185,9 +187,11 @@ void drainTimed(pbr_ctx* ctx) {
 }
 
 /* Rebuild the repacked node / triangle arrays when the bound buffers or BVH_NUM_NODES changed. */
-int ensureScene(pbr_ctx* ctx, pbr_mem hBvh, pbr_mem hFacesV, pbr_mem hVertices, int numNodes) {
+int ensureScene(pbr_ctx* ctx, pbr_mem hBvh, pbr_mem hFacesV, pbr_mem hVertices, int numNodes,
+                bool phong = false, pbr_mem hFacesN = 0, pbr_mem hNormals = 0) {
 	if (ctx->cacheBvh == hBvh && ctx->cacheFacesV == hFacesV && ctx->cacheVertices == hVertices &&
-	    ctx->cacheNumNodes == numNodes && ctx->cacheEpoch == ctx->sceneEpoch) {
+	    ctx->cacheNumNodes == numNodes && ctx->cacheEpoch == ctx->sceneEpoch && ctx->cachePhong == phong &&
+	    (!phong || (ctx->cacheFacesN == hFacesN && ctx->cacheNormals == hNormals))) {
 		return PBR_OK;
 	}
 	Mem* bvh = getMem(ctx, hBvh);
@@ -208,11 +212,17 @@ int ensureScene(pbr_ctx* ctx, pbr_mem hBvh, pbr_mem hFacesV, pbr_mem hVertices, 
 		CK(cudaMalloc(&ctx->nodes, (size_t) numDst * 32));
 		ctx->nodesCap = (size_t) numDst;
 	}
-	if ((size_t) numFaces > ctx->trisCap || !ctx->tris) {
+	Mem* facesN = phong ? getMem(ctx, hFacesN) : nullptr;
+	Mem* normals = phong ? getMem(ctx, hNormals) : nullptr;
+	if (phong && (!facesN || !normals || facesN->bytes < facesV->bytes || normals->bytes < sizeof(pbr_float4)))
+		return fail(ctx, PBR_ERR_INVALID, "pathTracing: PHONGTESS needs facesN (one entry per face) and normals");
+	const size_t triFloat4s = phong ? PT_TRI_STRIDE_PHONG : PT_TRI_STRIDE;
+	const size_t wantTris = (size_t) (numFaces > 0 ? numFaces : 1) * triFloat4s;
+	if (wantTris > ctx->trisCap || !ctx->tris) {
 		if (ctx->tris) cudaFree(ctx->tris);
 		ctx->tris = nullptr;
-		CK(cudaMalloc(&ctx->tris, (size_t) (numFaces > 0 ? numFaces : 1) * 16 * PT_TRI_STRIDE));
-		ctx->trisCap = (size_t) numFaces;
+		CK(cudaMalloc(&ctx->tris, wantTris * 16));
+		ctx->trisCap = wantTris;
 	}
 	{
 		LaunchScope ls(ctx, K_OTHER);
@@ -220,11 +230,19 @@ int ensureScene(pbr_ctx* ctx, pbr_mem hBvh, pbr_mem hFacesV, pbr_mem hVertices, 
 	}
 	if (numFaces > 0 && numVertices > 0) {
 		LaunchScope ls(ctx, K_OTHER);
-		repackTrisKernel<<<gridFor(numFaces, 256), 256, 0, ctx->stream>>>(
-			(const uint4*) facesV->dptr, numFaces, (const float4*) vertices->dptr, numVertices, ctx->tris);
+		if (phong) {
+			repackTrisPhongKernel<<<gridFor(numFaces, 256), 256, 0, ctx->stream>>>(
+				(const uint4*) facesV->dptr, (const uint4*) facesN->dptr, numFaces, (const float4*) vertices->dptr, numVertices,
+				(const float4*) normals->dptr, (int) (normals->bytes / sizeof(pbr_float4)), ctx->tris);
+		}
+		else {
+			repackTrisKernel<<<gridFor(numFaces, 256), 256, 0, ctx->stream>>>(
+				(const uint4*) facesV->dptr, numFaces, (const float4*) vertices->dptr, numVertices, ctx->tris);
+		}
 	}
 	CK(cudaGetLastError());
 	ctx->cacheBvh = hBvh; ctx->cacheFacesV = hFacesV; ctx->cacheVertices = hVertices;
+	ctx->cacheFacesN = hFacesN; ctx->cacheNormals = hNormals; ctx->cachePhong = phong;
 	ctx->cacheNumNodes = numNodes;
 	ctx->cacheEpoch = ctx->sceneEpoch;
 	ctx->numNodesDev = numNodes;
@@ -234,9 +252,10 @@ int ensureScene(pbr_ctx* ctx, pbr_mem hBvh, pbr_mem hFacesV, pbr_mem hVertices, 
 int ensureWave(pbr_ctx* ctx, size_t nPaths) {
 	if (nPaths <= ctx->waveCap) return PBR_OK;
 	WaveState& W = ctx->wave;
-	cudaFree(W.rayO); cudaFree(W.rayD); cudaFree(W.colS); cudaFree(W.finF); cudaFree(W.misc); cudaFree(W.dbg);
+	cudaFree(W.rayO); cudaFree(W.rayD); cudaFree(W.colS); cudaFree(W.finF); cudaFree(W.misc); cudaFree(W.dbg); cudaFree(ctx->hitN);
 	cudaFree(ctx->qctl.queue[0]); cudaFree(ctx->qctl.queue[1]);
-	W = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+	W = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+	ctx->hitN = nullptr;
 	ctx->qctl.queue[0] = ctx->qctl.queue[1] = nullptr;
 	ctx->waveCap = 0;
 	CK(cudaMalloc(&W.rayO, nPaths * 16));
@@ -245,30 +264,32 @@ int ensureWave(pbr_ctx* ctx, size_t nPaths) {
 	CK(cudaMalloc(&W.finF, nPaths * 16));
 	CK(cudaMalloc(&W.misc, nPaths * 16));
 	CK(cudaMalloc(&W.dbg, nPaths * 8));
+	CK(cudaMalloc(&ctx->hitN, nPaths * 16));
 	CK(cudaMalloc(&ctx->qctl.queue[0], nPaths * 4));
 	CK(cudaMalloc(&ctx->qctl.queue[1], nPaths * 4));
 	ctx->waveCap = nPaths;
 	return PBR_OK;
 }
 
-template <int BRDF, bool SHADOW>
+template <int BRDF, bool SHADOW, bool PHONG>
 int runFrame(pbr_ctx* ctx, const FrameParams& P, int nPaths) {
 	if (ctx->pipeline == 1) {
 		{
 			LaunchScope ls(ctx, K_OTHER);
-			megaKernel<BRDF, SHADOW><<<gridFor(nPaths, 128), 128, 0, ctx->stream>>>(P, nPaths);
+			megaKernel<BRDF, SHADOW, PHONG><<<gridFor(nPaths, 128), 128, 0, ctx->stream>>>(P, nPaths);
 		}
 		CK(cudaGetLastError());
 		return PBR_OK;
 	}
 	int rc = ensureWave(ctx, (size_t) nPaths);
 	if (rc) return rc;
-	const WaveState& W = ctx->wave;
+	WaveState W = ctx->wave;
+	W.hitN = PHONG ? ctx->hitN : nullptr;
 	const QueueCtl& Q = ctx->qctl;
 
 	int occT = 0, occS = 0;
-	CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occT, traverseKernel, 128, 0));
-	CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occS, shadeKernel<BRDF, SHADOW>, 128, 0));
+	CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occT, traverseKernel<PHONG>, 128, 0));
+	CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occS, shadeKernel<BRDF, SHADOW, PHONG>, 128, 0));
 	const int gridT = ctx->smCount * (occT > 0 ? occT : 1);
 	const int gridS = ctx->smCount * (occS > 0 ? occS : 1);
 
@@ -282,11 +303,11 @@ int runFrame(pbr_ctx* ctx, const FrameParams& P, int nPaths) {
 		const uint32_t* qIn = (it == 0) ? nullptr : Q.queue[in];
 		{
 			LaunchScope ls(ctx, K_TRAVERSE);
-			traverseKernel<<<gridT, 128, 0, ctx->stream>>>(P.scene, W, qIn, Q.ctrl + in, Q.ctrl + 2, Q.ctrl + out, ctx->stats);
+			traverseKernel<PHONG><<<gridT, 128, 0, ctx->stream>>>(P.scene, W, qIn, Q.ctrl + in, Q.ctrl + 2, Q.ctrl + out, ctx->stats);
 		}
 		{
 			LaunchScope ls(ctx, K_SHADE);
-			shadeKernel<BRDF, SHADOW><<<gridS, 128, 0, ctx->stream>>>(P, W, qIn, Q.ctrl + in, Q.queue[out], Q.ctrl + out, Q.ctrl + 2);
+			shadeKernel<BRDF, SHADOW, PHONG><<<gridS, 128, 0, ctx->stream>>>(P, W, qIn, Q.ctrl + in, Q.queue[out], Q.ctrl + out, Q.ctrl + 2);
 		}
 	}
 	CK(cudaGetLastError());
@@ -367,7 +388,7 @@ int pbr_destroy(pbr_ctx* ctx) {
 	for (void* p : ctx->pinned) cudaFreeHost(p);
 	cudaFree(ctx->nodes); cudaFree(ctx->tris);
 	WaveState& W = ctx->wave;
-	cudaFree(W.rayO); cudaFree(W.rayD); cudaFree(W.colS); cudaFree(W.finF); cudaFree(W.misc); cudaFree(W.dbg);
+	cudaFree(W.rayO); cudaFree(W.rayD); cudaFree(W.colS); cudaFree(W.finF); cudaFree(W.misc); cudaFree(W.dbg); cudaFree(ctx->hitN);
 	cudaFree(ctx->qctl.queue[0]); cudaFree(ctx->qctl.queue[1]); cudaFree(ctx->qctl.ctrl);
 	cudaFree(ctx->stats); cudaFree(ctx->cursor64);
 	cudaEventDestroy(ctx->evStart); cudaEventDestroy(ctx->evStop);
@@ -553,7 +574,6 @@ int pbr_program_load(pbr_ctx* ctx, const pbr_defines* defines) {
 	if (ctx->haveSky) d.sky_light = ctx->defSky;
 	if (d.accel_struct != 0) return fail(ctx, PBR_ERR_UNSUPPORTED, "accel_struct: only 0 (BVH) exists");
 	if (d.brdf != 0 && d.brdf != 1) return fail(ctx, PBR_ERR_UNSUPPORTED, "render.brdf must be 0 (Schlick) or 1 (Shirley-Ashikhmin)");
-	if (d.phongtess != 0) return fail(ctx, PBR_ERR_UNSUPPORTED, "render.phong_tessellation > 0 is not implemented in the CUDA path yet");
 	if (d.img_width <= 0 || d.img_height <= 0 || d.samples <= 0 || d.max_depth < 0 || d.max_added_depth < 0)
 		return fail(ctx, PBR_ERR_INVALID, "invalid image size / samples / depth");
 	if (d.max_depth + d.max_added_depth > 0xffff) return fail(ctx, PBR_ERR_INVALID, "max_depth + max_added_depth too large");
@@ -598,7 +618,8 @@ int pbr_kernel_launch(pbr_ctx* ctx, pbr_kernel k) {
 	CK(cudaSetDevice(ctx->device));
 	const pbr_defines& D = ctx->defines;
 
-	int rc = ensureScene(ctx, a.mem[4], a.mem[5], a.mem[7], D.bvh_num_nodes);
+	const bool phong = (D.phongtess == 1);
+	int rc = ensureScene(ctx, a.mem[4], a.mem[5], a.mem[7], D.bvh_num_nodes, phong, a.mem[6], a.mem[8]);
 	if (rc) return rc;
 
 	Mem* materials = getMem(ctx, a.mem[9]);
@@ -620,6 +641,7 @@ int pbr_kernel_launch(pbr_ctx* ctx, pbr_kernel k) {
 	P.scene.lights = (const pbr_light*) lights->dptr;
 	P.scene.numNodes = ctx->numNodesDev;
 	P.scene.numLights = D.num_lights;
+	P.scene.phongAlpha = D.phongtess_alpha;
 	P.scene.nodePhaseMin = ctx->nodePhaseMin;
 	P.scene.refillMin = ctx->refillMin;
 	P.materials = materials->dptr;
@@ -642,8 +664,17 @@ int pbr_kernel_launch(pbr_ctx* ctx, pbr_kernel k) {
 	const bool shadow = (D.shadow_rays == 1);
 
 	CK(cudaEventRecord(ctx->evStart, ctx->stream));
-	if (D.brdf == 0) rc = shadow ? runFrame<0, true>(ctx, P, nPaths) : runFrame<0, false>(ctx, P, nPaths);
-	else rc = shadow ? runFrame<1, true>(ctx, P, nPaths) : runFrame<1, false>(ctx, P, nPaths);
+	const int variant = (D.brdf == 1 ? 4 : 0) | (shadow ? 2 : 0) | (phong ? 1 : 0);
+	switch (variant) {
+		case 0: rc = runFrame<0, false, false>(ctx, P, nPaths); break;
+		case 1: rc = runFrame<0, false, true>(ctx, P, nPaths); break;
+		case 2: rc = runFrame<0, true, false>(ctx, P, nPaths); break;
+		case 3: rc = runFrame<0, true, true>(ctx, P, nPaths); break;
+		case 4: rc = runFrame<1, false, false>(ctx, P, nPaths); break;
+		case 5: rc = runFrame<1, false, true>(ctx, P, nPaths); break;
+		case 6: rc = runFrame<1, true, false>(ctx, P, nPaths); break;
+		default: rc = runFrame<1, true, true>(ctx, P, nPaths); break;
+	}
 	if (rc) return rc;
 	CK(cudaEventRecord(ctx->evStop, ctx->stream));
 	ctx->timed = true;
@@ -733,6 +764,7 @@ static int traceImpl(pbr_ctx* ctx, pbr_mem bvh, pbr_mem facesV, pbr_mem vertices
 	S.numNodes = ctx->numNodesDev;
 	S.numLights = 0;
 	S.lights = nullptr;
+	S.phongAlpha = 0.0f;
 	S.nodePhaseMin = ctx->nodePhaseMin;
 	S.refillMin = ctx->refillMin;
 	if (num_lights > 0) {

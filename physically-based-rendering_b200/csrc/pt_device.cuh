@@ -43,8 +43,9 @@ using pm::v3;
 
 struct SceneDev {
 	const float4* nodes;          /* 2 x float4 per node */
-	const float4* tris;           /* 4 x float4 (64 B) per face */
+	const float4* tris;           /* 4 x float4 (64 B) per face; PHONGTESS: 6 x float4 (a b c an bn cn) */
 	const pbr_light* lights;
+	float phongAlpha;             /* PHONGTESS_ALPHA */
 	int numNodes;
 	int numLights;
 	int nodePhaseMin;             /* traversal engine: leave the node phase below this many stepping lanes */
@@ -140,6 +141,285 @@ __device__ __forceinline__ void intersectFace(
 	}
 }
 
+/* ------------------------------------------------------------ Phong tessellation (pt_phongtess.cl) */
+
+__device__ __forceinline__ void swapf(float& a, float& b) { const float t = a; a = b; b = t; }
+
+/* solveCubic (pt_utils.cl:108-199): a0 x^3 + a1 x^2 + a2 x + a3 = 0 */
+__device__ __noinline__ int solveCubic(const float a0, const float a1, const float a2, const float a3, float x[3]) {
+	const float THIRD = 0.3333333333f;
+	const float THIRD_HALF = 0.1666666666f;
+	float w, p, q, dis, phi;
+
+	if (fabsf(a0) > 0.0f) {
+		w = pm::divide(a1, a0) * THIRD;
+		p = pm::divide(a2, a0) * THIRD - w * w;
+		p = p * p * p;
+		q = 0.5f * pm::divide(a2 * w - a3, a0) - w * w * w;
+		dis = q * q + p;
+
+		if (dis < 0.0f) {
+			phi = pm::acos_(pm::clamp_(pm::divide(q, pm::sqrt_(-p)), -1.0f, 1.0f));
+			p = 2.0f * pm::pow_(-p, THIRD_HALF);
+
+			const float u0 = p * pm::cos_(phi * THIRD) - w;
+			const float u1 = p * pm::cos_((float) (((double) phi + 2.0f * PT_M_PI) * (double) THIRD)) - w;
+			const float u2 = p * pm::cos_((float) (((double) phi + 4.0f * PT_M_PI) * (double) THIRD)) - w;
+
+			x[0] = fminf(u0, fminf(u1, u2));
+			x[1] = fmaxf(fminf(u0, u1), fmaxf(fminf(u0, u2), fminf(u1, u2)));
+			x[2] = fmaxf(u0, fmaxf(u1, u2));
+			#pragma unroll
+			for (int i = 0; i < 3; i++) {
+				x[i] -= pm::divide(
+					a3 + x[i] * (a2 + x[i] * (a1 + x[i] * a0)),
+					a2 + x[i] * (2.0f * a1 + x[i] * 3.0f * a0));
+			}
+			return 3;
+		}
+		dis = pm::sqrt_(dis);
+		x[0] = pm::cbrt_(q + dis) + pm::cbrt_(q - dis) - w;
+		x[0] -= pm::divide(
+			a3 + x[0] * (a2 + x[0] * (a1 + x[0] * a0)),
+			a2 + x[0] * (2.0f * a1 + x[0] * 3.0f * a0));
+		return 1;
+	}
+	else if (fabsf(a1) > 0.0f) {
+		p = 0.5f * pm::divide(a2, a1);
+		dis = p * p - pm::divide(a3, a1);
+		if (dis >= 0.0f) {
+			const float dis_sqrt = pm::sqrt_(dis);
+			x[0] = -p - dis_sqrt;
+			x[1] = -p + dis_sqrt;
+			x[0] -= pm::divide(a3 + x[0] * (a2 + x[0] * a1), a2 + x[0] * 2.0f * a1);
+			x[1] -= pm::divide(a3 + x[1] * (a2 + x[1] * a1), a2 + x[1] * 2.0f * a1);
+			return 2;
+		}
+	}
+	else if (fabsf(a2) > 0.0f) {
+		x[0] = pm::divide(-a3, a2);
+		return 1;
+	}
+	return 0;
+}
+
+/* projectOnPlane (pt_utils.cl:397-399) */
+__device__ __forceinline__ vec3 projectOnPlane(const vec3 q, const vec3 p, const vec3 n) {
+	return q - pm::dot(q - p, n) * n;
+}
+
+/* phongTessellation (pt_phongtess.cl:14-27) */
+__device__ __forceinline__ vec3 phongTessellation(
+	const float alpha, const vec3 P1, const vec3 P2, const vec3 P3, const vec3 N1, const vec3 N2, const vec3 N3,
+	const float u, const float v, const float w
+) {
+	const vec3 pBary = P1 * u + P2 * v + P3 * w;
+	const vec3 pTessellated =
+		u * projectOnPlane(pBary, P1, N1) +
+		v * projectOnPlane(pBary, P2, N2) +
+		w * projectOnPlane(pBary, P3, N3);
+	return (1.0f - alpha) * pBary + alpha * pTessellated;
+}
+
+/* getPhongTessNormal with getTriangleNormalS / getTriangleNormal / getTriangleReflectionVec
+ * (pt_utils.cl:231-294) */
+__device__ __forceinline__ vec3 getPhongTessNormal(
+	const vec3 an, const vec3 bn, const vec3 cn, const vec3 rayDir,
+	const float u, const float v, const float w,
+	const vec3 C12, const vec3 C23, const vec3 C31, const vec3 E23, const vec3 E31
+) {
+	const vec3 du = (w - u) * C31 + v * (C12 - C23) + E31;
+	const vec3 dv = (w - v) * C23 + u * (C12 - C31) - E23;
+	const vec3 ns = pm::normalize(pm::cross(du, dv));
+	const vec3 np = pm::normalize(an * u + bn * v + cn * w);
+	const vec3 r = rayDir - 2.0f * np * pm::dot(rayDir, np);
+	return (pm::dot(ns, r) < 0.0f) ? ns : np;
+}
+
+/* phongTessTriAndRayIntersect (pt_phongtess.cl:56-212): direct ray tracing of Phong tessellation
+ * after Ogaki & Tokuyoshi.  rayT is the current ray.t. */
+__device__ __noinline__ vec3 phongTessTriAndRayIntersect(
+	const float ALPHA,
+	const vec3 P1, const vec3 P2, const vec3 P3, const vec3 N1, const vec3 N2, const vec3 N3,
+	const vec3 rayO, const vec3 rayD, const float rayT, float* t, const float tNear, const float tFar
+) {
+	vec3 normal = v3(0.0f, 0.0f, 0.0f);
+	*t = PM_INF_F;
+
+	const vec3 E01 = P2 - P1;
+	const vec3 E12 = P3 - P2;
+	const vec3 E20 = P1 - P3;
+
+	const vec3 C1 = ALPHA * (pm::dot(N2, E01) * N2 - pm::dot(N1, E01) * N1);
+	const vec3 C2 = ALPHA * (pm::dot(N3, E12) * N3 - pm::dot(N2, E12) * N2);
+	const vec3 C3 = ALPHA * (pm::dot(N1, E20) * N1 - pm::dot(N3, E20) * N3);
+
+	float a, b, c, d, e, f, l, m, n, o, p, q;
+	{
+		/* getPlanesFromRay (pt_utils.cl:208-218) */
+		const vec3 n1 = pm::normalize(pm::cross(rayO, rayD));
+		const vec3 n2 = pm::normalize(pm::cross(n1, rayD));
+		const float o1 = pm::dot(n1, rayO);
+		const float o2 = pm::dot(n2, rayO);
+
+		a = pm::dot(-n1, C3);
+		b = pm::dot(-n1, C2);
+		c = pm::dot(n1, P3) - o1;
+		d = pm::dot(n1, C1 - C2 - C3) * 0.5f;
+		e = pm::dot(n1, C3 + E20) * 0.5f;
+		f = pm::dot(n1, C2 - E12) * 0.5f;
+		l = pm::dot(-n2, C3);
+		m = pm::dot(-n2, C2);
+		n = pm::dot(n2, P3) - o2;
+		o = pm::dot(n2, C1 - C2 - C3) * 0.5f;
+		p = pm::dot(n2, C3 + E20) * 0.5f;
+		q = pm::dot(n2, C2 - E12) * 0.5f;
+	}
+
+	float xs[3] = { -1.0f, -1.0f, -1.0f };
+	int numCubicRoots = 0;
+	{
+		const float a3 = (l*m*n + 2.0f*o*p*q) - (l*q*q + m*p*p + n*o*o);
+		const float a2 = (a*m*n + l*b*n + l*m*c + 2.0f*(d*p*q + o*e*q + o*p*f)) -
+		                 (a*q*q + b*p*p + c*o*o + 2.0f*(l*f*q + m*e*p + n*d*o));
+		const float a1 = (a*b*n + a*m*c + l*b*c + 2.0f*(o*e*f + d*e*q + d*p*f)) -
+		                 (l*f*f + m*e*e + n*d*d + 2.0f*(a*f*q + b*e*p + c*d*o));
+		const float a0 = (a*b*c + 2.0f*d*e*f) - (a*f*f + b*e*e + c*d*d);
+		numCubicRoots = solveCubic(a0, a1, a2, a3, xs);
+	}
+
+	if (0 == numCubicRoots) return normal;
+
+	float x = 0.0f;
+	float determinant = PM_INF_F;
+	float mA, mB, mC, mD, mE, mF;
+
+	for (int i = 0; i < numCubicRoots; i++) {
+		mA = a * xs[i] + l;
+		mB = b * xs[i] + m;
+		mD = d * xs[i] + o;
+		const float tmp = mD * mD - mA * mB;
+		x = (determinant > tmp) ? xs[i] : x;
+		determinant = fminf(determinant, tmp);
+	}
+
+	if (0.0f >= determinant) return normal;
+
+	/* getBestRayDomain (pt_phongtess.cl:36-45) */
+	const float dx = fabsf(rayD.x), dy = fabsf(rayD.y), dz = fabsf(rayD.z);
+	int domain = (dy > dz) ? 1 : 2;
+	if (dx > dy) domain = (dx > dz) ? 0 : 2;
+
+	mA = a * x + l;
+	mB = b * x + m;
+	mC = c * x + n;
+	mD = d * x + o;
+	mE = e * x + p;
+	mF = f * x + q;
+
+	const bool AlessB = fabsf(mA) < fabsf(mB);
+
+	const float mBorA = AlessB ? mB : mA;
+	mA = pm::divide(mA, mBorA);
+	mB = pm::divide(mB, mBorA);
+	mC = pm::divide(mC, mBorA);
+	mD = pm::divide(mD, mBorA);
+	mE = pm::divide(mE, mBorA);
+	mF = pm::divide(mF, mBorA);
+
+	const float mAorB = AlessB ? mA : mB;
+	const float mEorF = AlessB ? 2.0f * mE : 2.0f * mF;
+	const float mForE = AlessB ? mF : mE;
+	const float ab = AlessB ? a : b;
+	const float ba = AlessB ? b : a;
+	const float ef = AlessB ? e : f;
+	const float fe = AlessB ? f : e;
+
+	const float sqrtAorB = pm::sqrt_(mD * mD - mAorB);
+	const float sqrtC = pm::sqrt_(mForE * mForE - mC);
+	const float lab1 = mD + sqrtAorB;
+	const float lab2 = mD - sqrtAorB;
+	float lc1 = mForE + sqrtC;
+	float lc2 = mForE - sqrtC;
+
+	if (fabsf(mEorF - lab1 * lc1 - lab2 * lc2) < fabsf(mEorF - lab1 * lc2 - lab2 * lc1)) swapf(lc1, lc2);
+
+	for (int loop = 0; loop < 2; loop++) {
+		const float g = (0 == loop) ? -lab1 : -lab2;
+		const float h = (0 == loop) ? -lc1 : -lc2;
+
+		const float c0 = ab + g * (2.0f * d + ba * g);
+		const float c1 = 2.0f * (h * (d + ba * g) + ef + fe * g);
+		const float c2 = h * (ba * h + 2.0f * fe) + c;
+		const int numResults = solveCubic(0.0f, c0, c1, c2, xs);
+
+		for (int i = 0; i < numResults; i++) {
+			float u = xs[i];
+			float v = g * u + h;
+			const float w = 1.0f - u - v;
+
+			if (u < 0.0f || v < 0.0f || w < 0.0f) continue;
+			if (!AlessB) swapf(u, v);
+
+			const vec3 pT = phongTessellation(ALPHA, P1, P2, P3, N1, N2, N3, u, v, w) - rayO;
+			const float num = (domain == 0) ? pT.x : ((domain == 1) ? pT.y : pT.z);
+			const float den = (domain == 0) ? rayD.x : ((domain == 1) ? rayD.y : rayD.z);
+			const float tParam = pm::divide(num, den);
+
+			if (tParam >= fabsf(tNear) && tParam <= fminf(*t, fminf(rayT, tFar))) {
+				*t = tParam;
+				normal = getPhongTessNormal(N1, N2, N3, rayD, u, v, w, C1, C2, C3, E12, E20);
+			}
+		}
+	}
+	return normal;
+}
+
+/* checkFaceIntersection + intersectFace with PHONGTESS == 1 (pt_intersect.cl:142-176, pt_bvh.cl:10-24).
+ * In this mode a face record is 6 x float4: (a, material), (b, allNormalsEqual), (c, 0), an, bn, cn.
+ * Faces whose three vertex normals are component-wise equal take the flat test, the others the Phong
+ * test; the hit normal is part of the result. */
+#define PT_TRI_STRIDE_PHONG 6
+
+__device__ __forceinline__ void intersectFacePhong(
+	const SceneDev& S, const int face, const int leaf,
+	const vec3 o, const vec3 d, const float tNear, const float tFar,
+	float& rt, int& hitFace, int& hitLeaf, vec3& hitNormal
+) {
+	const float4* p = S.tris + PT_TRI_STRIDE_PHONG * (size_t) face;
+	const float4 A = __ldg(p), B = __ldg(p + 1), C = __ldg(p + 2);
+	const vec3 a = f4xyz(A), b = f4xyz(B), c = f4xyz(C);
+	float t;
+	vec3 normal;
+	if (B.w != 0.0f) {
+		/* flatTriAndRayIntersect (pt_intersect.cl:92-129) */
+		const float f = fmaxf(0.0f, tNear - 0.001f);
+		const vec3 closeOrigin = pm::fma3(d, f, o);
+		const vec3 edge1 = b - a, edge2 = c - a;
+		const vec3 tVec = closeOrigin - a;
+		const vec3 pVec = pm::cross(d, edge2);
+		const vec3 qVec = pm::cross(tVec, edge1);
+		const float invDet = pm::rcp(pm::dot(edge1, pVec));
+		t = pm::dot(edge2, qVec) * invDet;
+		if (t >= rt || t < PT_EPSILON5) return;
+		const float u = pm::dot(tVec, pVec) * invDet;
+		const float v = pm::dot(d, qVec) * invDet;
+		if (u + v > 1.0f || fminf(u, v) < 0.0f) return;
+		t += f;
+		normal = pm::normalize(pm::cross(edge1, edge2));
+	}
+	else {
+		const float4 NA = __ldg(p + 3), NB = __ldg(p + 4), NC = __ldg(p + 5);
+		normal = phongTessTriAndRayIntersect(S.phongAlpha, a, b, c, f4xyz(NA), f4xyz(NB), f4xyz(NC), o, d, rt, &t, tNear, tFar);
+	}
+	if (rt > t) {
+		rt = t;
+		hitFace = face;
+		hitLeaf = leaf;
+		hitNormal = normal;
+	}
+}
+
 /* intersectSphere (pt_intersect.cl:37-77), radius deliberately NOT squared (reference quirk). */
 __device__ __forceinline__ bool intersectSphere(const vec3 o, const vec3 d, const vec3 pos, const float r, float* tNear) {
 	const vec3 L = pos - o;
@@ -188,9 +468,10 @@ __device__ __forceinline__ bool intersectBox(
 }
 
 /* traverse (pt_bvh.cl:82-123): stackless closest hit, one thread per ray, reference visiting order. */
+template <bool PHONG>
 __device__ __forceinline__ void traverseClosest(
 	const SceneDev& S, const vec3 o, const vec3 d,
-	float& rt, int& hitFace, int& hitLeaf, uint32_t& nNodes, uint32_t& nTris
+	float& rt, int& hitFace, int& hitLeaf, uint32_t& nNodes, uint32_t& nTris, vec3& hitNormal
 ) {
 	const vec3 invDir = v3(pm::rcp(d.x), pm::rcp(d.y), pm::rcp(d.z));
 	int index = 1;
@@ -214,10 +495,12 @@ __device__ __forceinline__ void traverseClosest(
 		index = cur + 1;
 
 		if (loW >= 0) {
-			intersectFace(S.tris, loW, cur, o, d, tNear, rt, hitFace, hitLeaf);
+			if (PHONG) intersectFacePhong(S, loW, cur, o, d, tNear, tFar, rt, hitFace, hitLeaf, hitNormal);
+			else intersectFace(S.tris, loW, cur, o, d, tNear, rt, hitFace, hitLeaf);
 			nTris++;
 			if (hiW != -1) {
-				intersectFace(S.tris, hiW, cur, o, d, tNear, rt, hitFace, hitLeaf);
+				if (PHONG) intersectFacePhong(S, hiW, cur, o, d, tNear, tFar, rt, hitFace, hitLeaf, hitNormal);
+				else intersectFace(S.tris, hiW, cur, o, d, tNear, rt, hitFace, hitLeaf);
 				nTris++;
 			}
 		}
@@ -226,10 +509,12 @@ __device__ __forceinline__ void traverseClosest(
 
 /* traverseShadows (pt_bvh.cl:133-177): any hit closer than the light ends the walk; the box test
  * has no `ray.t > tNear` prune (reference behaviour). */
+template <bool PHONG>
 __device__ __forceinline__ void traverseAny(
 	const SceneDev& S, const vec3 o, const vec3 d,
 	float& rt, int& hitFace, int& hitLeaf, uint32_t& nNodes, uint32_t& nTris
 ) {
+	vec3 hitNormal = v3(0.0f, 0.0f, 0.0f);
 	const float tLight = rt;
 	const vec3 invDir = v3(pm::rcp(d.x), pm::rcp(d.y), pm::rcp(d.z));
 	int index = 1;
@@ -253,10 +538,12 @@ __device__ __forceinline__ void traverseAny(
 		index = cur + 1;
 
 		if (loW >= 0) {
-			intersectFace(S.tris, loW, cur, o, d, tNear, rt, hitFace, hitLeaf);
+			if (PHONG) intersectFacePhong(S, loW, cur, o, d, tNear, tFar, rt, hitFace, hitLeaf, hitNormal);
+			else intersectFace(S.tris, loW, cur, o, d, tNear, rt, hitFace, hitLeaf);
 			nTris++;
 			if (hiW != -1) {
-				intersectFace(S.tris, hiW, cur, o, d, tNear, rt, hitFace, hitLeaf);
+				if (PHONG) intersectFacePhong(S, hiW, cur, o, d, tNear, tFar, rt, hitFace, hitLeaf, hitNormal);
+				else intersectFace(S.tris, hiW, cur, o, d, tNear, rt, hitFace, hitLeaf);
 				nTris++;
 			}
 			if (rt < tLight) break;
@@ -556,6 +843,7 @@ struct PathState {
 	uint32_t sample;
 	uint32_t secondaryPaths;
 	uint32_t nNodes, nTris;   /* debugColor.y / debugColor.x */
+	vec3 hitNormal;           /* PHONGTESS only: ray.normal of the hit (flat faces: recomputed from the edges) */
 };
 
 enum BounceResult { PATH_CONTINUE = 0, PATH_SAMPLE_DONE = 1 };
@@ -645,7 +933,7 @@ __device__ __forceinline__ void endSampleWithLight(PathState& s, const vec3 ligh
 /* The body of the depth loop after traverse() (pathtracing.cl:261-317).  On PATH_CONTINUE the
  * state holds the next ray (t = INFINITY, hitFace = 0) and depth has been advanced and checked
  * against MAX_DEPTH + depthAdded.  On PATH_SAMPLE_DONE the sample's light has been applied. */
-template <int BRDF, bool SHADOW>
+template <int BRDF, bool SHADOW, bool PHONG>
 __device__ __forceinline__ BounceResult bounce(const FrameParams& P, PathState& s, uint32_t& shadowNodes, uint32_t& shadowRays) {
 	const SceneDev& S = P.scene;
 
@@ -657,10 +945,19 @@ __device__ __forceinline__ BounceResult bounce(const FrameParams& P, PathState& 
 		return PATH_SAMPLE_DONE;
 	}
 
-	float4 A, E1, E2;
-	loadTri(S.tris, s.hitFace, A, E1, E2);
-	const Material mtl = fetchMaterial<BRDF>(P.materials, P.numMaterials, (uint32_t) __float_as_int(A.w));
-	vec3 normal = pm::normalize(pm::cross(f4xyz(E1), f4xyz(E2)));
+	uint32_t mtlIndex;
+	vec3 normal;
+	if (PHONG) {
+		mtlIndex = (uint32_t) __float_as_int(__ldg(S.tris + PT_TRI_STRIDE_PHONG * (size_t) s.hitFace).w);
+		normal = s.hitNormal;
+	}
+	else {
+		float4 A, E1, E2;
+		loadTri(S.tris, s.hitFace, A, E1, E2);
+		mtlIndex = (uint32_t) __float_as_int(A.w);
+		normal = pm::normalize(pm::cross(f4xyz(E1), f4xyz(E2)));
+	}
+	const Material mtl = fetchMaterial<BRDF>(P.materials, P.numMaterials, mtlIndex);
 
 	/* extendDepth (pt_utils.cl:89-96) */
 	bool addDepth;
@@ -687,7 +984,7 @@ __device__ __forceinline__ BounceResult bounce(const FrameParams& P, PathState& 
 			float lt = tLight;
 			int lf = 0, ll = -1;
 			uint32_t nn = 0;
-			traverseAny(S, hitPoint, lightDir, lt, lf, ll, nn, s.nTris);
+			traverseAny<PHONG>(S, hitPoint, lightDir, lt, lf, ll, nn, s.nTris);
 			shadowNodes += nn;
 			shadowRays++;
 			if (lt >= tLight) {

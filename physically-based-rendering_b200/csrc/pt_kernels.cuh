@@ -35,6 +35,7 @@ struct WaveState {
 	float4* finF;
 	uint4* misc;
 	uint2* dbg;
+	float4* hitN;             /* PHONGTESS only: normal of the hit found by traverse */
 };
 
 /* ctrl[0], ctrl[1]: element counts of queue 0 / 1;  ctrl[2]: work cursor of the traverse kernel */
@@ -62,6 +63,8 @@ __device__ __forceinline__ void loadPath(const WaveState& W, const uint32_t p, P
 	s.depth = m.x & 0xffffu; s.depthAdded = (int) (m.x >> 16);
 	s.sample = m.y; s.secondaryPaths = m.z;
 	s.nNodes = g.x; s.nTris = g.y;
+	if (W.hitN) { const float4 n = W.hitN[p]; s.hitNormal = v3(n.x, n.y, n.z); }
+	else s.hitNormal = v3(0.0f, 0.0f, 0.0f);
 }
 
 /* Sum a per-thread counter over the warp and add it to a global 64-bit counter once. */
@@ -120,7 +123,8 @@ struct LaneRay {
 	uint32_t nn, nt;
 	/* pending leaf */
 	int leafCur, leafF0, leafF1;
-	float leafTNear;
+	float leafTNear, leafTFar;
+	vec3 normal;              /* PHONGTESS only */
 };
 
 template <bool ANY_HIT>
@@ -135,6 +139,7 @@ __device__ __forceinline__ void startRay(const SceneDev& S, LaneRay& L, const ve
 	L.index = 1;
 	L.nn = 0;
 	L.nt = 0;
+	L.normal = v3(0.0f, 0.0f, 0.0f);
 	if (S.numLights > 0) traverseLights(S, o, d, L.rt, L.hitFace);
 }
 
@@ -159,6 +164,7 @@ __device__ __forceinline__ bool nodeVisit(LaneRay& L, const float4 lo, const flo
 	L.leafF0 = loW;
 	L.leafF1 = hiW;
 	L.leafTNear = tNear;
+	L.leafTFar = tFar;
 	return true;
 }
 
@@ -170,12 +176,14 @@ __device__ __forceinline__ bool nodeStep(const SceneDev& S, LaneRay& L) {
 }
 
 /* intersectFaces (pt_bvh.cl:35-46) for the pending leaf. */
-template <bool ANY_HIT>
+template <bool ANY_HIT, bool PHONG>
 __device__ __forceinline__ void leafStep(const SceneDev& S, LaneRay& L) {
-	intersectFace(S.tris, L.leafF0, L.leafCur, L.o, L.d, L.leafTNear, L.rt, L.hitFace, L.hitLeaf);
+	if (PHONG) intersectFacePhong(S, L.leafF0, L.leafCur, L.o, L.d, L.leafTNear, L.leafTFar, L.rt, L.hitFace, L.hitLeaf, L.normal);
+	else intersectFace(S.tris, L.leafF0, L.leafCur, L.o, L.d, L.leafTNear, L.rt, L.hitFace, L.hitLeaf);
 	L.nt++;
 	if (L.leafF1 != -1) {
-		intersectFace(S.tris, L.leafF1, L.leafCur, L.o, L.d, L.leafTNear, L.rt, L.hitFace, L.hitLeaf);
+		if (PHONG) intersectFacePhong(S, L.leafF1, L.leafCur, L.o, L.d, L.leafTNear, L.leafTFar, L.rt, L.hitFace, L.hitLeaf, L.normal);
+		else intersectFace(S.tris, L.leafF1, L.leafCur, L.o, L.d, L.leafTNear, L.rt, L.hitFace, L.hitLeaf);
 		L.nt++;
 	}
 	if (ANY_HIT && L.rt < L.tLight) L.index = -1;     /* `break` of traverseShadows (pt_bvh.cl:170-172) */
@@ -185,7 +193,7 @@ __device__ __forceinline__ void leafStep(const SceneDev& S, LaneRay& L) {
 /* Lane states of the traversal engine. */
 enum { LANE_IDLE = 0, LANE_STEPPING = 1, LANE_PENDING = 2, LANE_FINISHED = 3 };
 
-template <bool ANY_HIT, typename RaySource, typename Counter>
+template <bool ANY_HIT, bool PHONG, typename RaySource, typename Counter>
 __device__ __forceinline__ void traverseEngine(
 	const SceneDev& S, RaySource& src, const Counter count, Counter* cursor,
 	uint32_t& totalNodes, uint32_t& totalTris, uint32_t& totalRays
@@ -243,7 +251,7 @@ __device__ __forceinline__ void traverseEngine(
 
 		/* triangle phase */
 		if (state == LANE_PENDING) {
-			leafStep<ANY_HIT>(S, L);
+			leafStep<ANY_HIT, PHONG>(S, L);
 			state = ((unsigned) (L.index - 1) < lastNode) ? LANE_STEPPING : LANE_FINISHED;
 		}
 	}
@@ -265,10 +273,12 @@ struct WaveRaySource {
 		uint2 g = W.dbg[p];
 		g.x += L.nn; g.y += L.nt;
 		W.dbg[p] = g;
+		if (W.hitN) W.hitN[p] = make_float4(L.normal.x, L.normal.y, L.normal.z, 0.0f);
 	}
 };
 
 /* Closest-hit traversal of every live path.  queue pointer NULL = identity (first bounce). */
+template <bool PHONG>
 __global__ void __launch_bounds__(128) traverseKernel(
 	const SceneDev S, const WaveState W, const uint32_t* __restrict__ queue, const uint32_t* __restrict__ countPtr,
 	uint32_t* cursor, uint32_t* countToReset, unsigned long long* stats
@@ -279,7 +289,7 @@ __global__ void __launch_bounds__(128) traverseKernel(
 	if (blockIdx.x == 0 && threadIdx.x == 0) *countToReset = 0u;
 
 	WaveRaySource src = {W, queue, 0u};
-	traverseEngine<false>(S, src, count, cursor, nodes, tris, rays);
+	traverseEngine<false, PHONG>(S, src, count, cursor, nodes, tris, rays);
 
 	warpAddStat(stats + 0, rays);
 	warpAddStat(stats + 2, nodes);
@@ -288,7 +298,7 @@ __global__ void __launch_bounds__(128) traverseKernel(
 
 /* ------------------------------------------------------------------ shade */
 
-template <int BRDF, bool SHADOW>
+template <int BRDF, bool SHADOW, bool PHONG>
 __global__ void __launch_bounds__(128) shadeKernel(
 	const FrameParams P, const WaveState W, const uint32_t* __restrict__ queueIn, const uint32_t* __restrict__ countInPtr,
 	uint32_t* __restrict__ queueOut, uint32_t* countOutPtr, uint32_t* cursorToReset
@@ -312,7 +322,7 @@ __global__ void __launch_bounds__(128) shadeKernel(
 			trisBefore += s.nTris;
 
 			if (s.t != PM_INF_F) shaded++;
-			const BounceResult r = bounce<BRDF, SHADOW>(P, s, shadowNodes, shadowRays);
+			const BounceResult r = bounce<BRDF, SHADOW, PHONG>(P, s, shadowNodes, shadowRays);
 			if (r == PATH_CONTINUE) {
 				alive = true;
 			}
@@ -352,12 +362,13 @@ __global__ void __launch_bounds__(128) shadeKernel(
 
 /* ------------------------------------------------------------------ megakernel (cross-check) */
 
-template <int BRDF, bool SHADOW>
+template <int BRDF, bool SHADOW, bool PHONG>
 __global__ void __launch_bounds__(128) megaKernel(const FrameParams P, const int nPaths) {
 	const int p = blockIdx.x * blockDim.x + threadIdx.x;
 	uint32_t rays = 0, shaded = 0, shadowNodes = 0, shadowRays = 0;
 	PathState s;
 	s.nNodes = 0; s.nTris = 0;
+	s.hitNormal = v3(0.0f, 0.0f, 0.0f);
 	if (p < nPaths) {
 		int px, py;
 		pathToPixel(p, P.width, P.y0, P.y1 - P.y0, px, py);
@@ -366,10 +377,10 @@ __global__ void __launch_bounds__(128) megaKernel(const FrameParams P, const int
 			beginSample(P, s, px, py);
 			while (true) {
 				int hitLeaf = -1;
-				traverseClosest(P.scene, s.o, s.d, s.t, s.hitFace, hitLeaf, s.nNodes, s.nTris);
+				traverseClosest<PHONG>(P.scene, s.o, s.d, s.t, s.hitFace, hitLeaf, s.nNodes, s.nTris, s.hitNormal);
 				rays++;
 				if (s.t != PM_INF_F) shaded++;
-				if (bounce<BRDF, SHADOW>(P, s, shadowNodes, shadowRays) != PATH_CONTINUE) break;
+				if (bounce<BRDF, SHADOW, PHONG>(P, s, shadowNodes, shadowRays) != PATH_CONTINUE) break;
 			}
 		}
 		finishPixel(P, s, px, py);
@@ -415,7 +426,7 @@ __global__ void __launch_bounds__(128) traceRaysKernel(
 ) {
 	uint32_t nodes = 0, tris = 0, cnt = 0;
 	ExplicitRaySource src = {rays, hits};
-	traverseEngine<ANY_HIT>(S, src, (unsigned long long) n, cursor, nodes, tris, cnt);
+	traverseEngine<ANY_HIT, false>(S, src, (unsigned long long) n, cursor, nodes, tris, cnt);
 	warpAddStat(stats + (ANY_HIT ? 1 : 0), cnt);
 	warpAddStat(stats + (ANY_HIT ? 5 : 2), nodes);
 	warpAddStat(stats + 3, tris);
@@ -460,6 +471,29 @@ __global__ void repackTrisKernel(
 	tris[PT_TRI_STRIDE * (size_t) f + 1] = make_float4(b.x - a.x, b.y - a.y, b.z - a.z, 0.0f);
 	tris[PT_TRI_STRIDE * (size_t) f + 2] = make_float4(c.x - a.x, c.y - a.y, c.z - a.z, 0.0f);
 	tris[PT_TRI_STRIDE * (size_t) f + 3] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+}
+
+/* PHONGTESS: facesV[f], facesN[f] + vertices[], normals[] -> (a, material), (b, allNormalsEqual), (c, 0),
+ * an, bn, cn  (pt_intersect.cl:146-160).  `an == bn` etc. are OpenCL component-wise float compares. */
+__global__ void repackTrisPhongKernel(
+	const uint4* __restrict__ facesV, const uint4* __restrict__ facesN, const int numFaces,
+	const float4* __restrict__ vertices, const int numVertices, const float4* __restrict__ normals, const int numNormals,
+	float4* __restrict__ tris
+) {
+	const int f = blockIdx.x * blockDim.x + threadIdx.x;
+	if (f >= numFaces) return;
+	const uint4 fv = facesV[f], fn = facesN[f];
+	const uint32_t lastV = (uint32_t) (numVertices - 1), lastN = (uint32_t) (numNormals - 1);
+	const float4 a = vertices[min(fv.x, lastV)], b = vertices[min(fv.y, lastV)], c = vertices[min(fv.z, lastV)];
+	const float4 an = normals[min(fn.x, lastN)], bn = normals[min(fn.y, lastN)], cn = normals[min(fn.z, lastN)];
+	const bool allEqual = an.x == bn.x && an.y == bn.y && an.z == bn.z && bn.x == cn.x && bn.y == cn.y && bn.z == cn.z;
+	float4* o = tris + PT_TRI_STRIDE_PHONG * (size_t) f;
+	o[0] = make_float4(a.x, a.y, a.z, __int_as_float((int) fv.w));
+	o[1] = make_float4(b.x, b.y, b.z, allEqual ? 1.0f : 0.0f);
+	o[2] = make_float4(c.x, c.y, c.z, 0.0f);
+	o[3] = make_float4(an.x, an.y, an.z, 0.0f);
+	o[4] = make_float4(bn.x, bn.y, bn.z, 0.0f);
+	o[5] = make_float4(cn.x, cn.y, cn.z, 0.0f);
 }
 
 /* ------------------------------------------------------------------ pinned-math probe */

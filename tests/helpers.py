@@ -16,11 +16,14 @@ class Prepared:
 
     def __init__(self, scene, width, height, brdf=1, samples=1, max_depth=3, max_added_depth=5,
                  shadow_rays=0, antialiasing=0.7, eye=(0.0, 1.0, 3.0), center=(0.0, 0.0, 1.0), fov=45.0,
-                 focus_point=(-1, -1), bvh=None, bvh_kwargs=None):
+                 focus_point=(-1, -1), bvh=None, bvh_kwargs=None, phong_tessellation=0.0):
         self.scene = scene
         self.W, self.H = width, height
         self.brdf = brdf
-        self.bvh = bvh if bvh is not None else O.build_bvh(scene, **(bvh_kwargs or {}))
+        kw = dict(bvh_kwargs or {})
+        if phong_tessellation > 0.0:
+            kw.setdefault("phong_tess", phong_tessellation)     # MathHelp::triCalcAABB grows the face boxes
+        self.bvh = bvh if bvh is not None else O.build_bvh(scene, **kw)
         self.nodes = self.bvh["nodes"]
         self.facesV = self.bvh["facesV"]
         self.facesN = self.bvh["facesN"]
@@ -34,7 +37,8 @@ class Prepared:
             shadow_rays = 0          # LightParser.cpp:119-121
         self.defines = S.defines(width, height, self.nodes.shape[0], self.num_lights, sky, brdf=brdf,
                                  samples=samples, max_depth=max_depth, max_added_depth=max_added_depth,
-                                 shadow_rays=shadow_rays, antialiasing=antialiasing)
+                                 shadow_rays=shadow_rays, antialiasing=antialiasing,
+                                 phong_tessellation=phong_tessellation)
         self.camera = S.camera(eye=eye, center=center, focus_point=focus_point)
         self.px_dim = S.px_dim(width, height, fov)
 

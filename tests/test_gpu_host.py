@@ -62,6 +62,23 @@ def test_pathtracer_matches_oracle_on_suzanne(oracle, cfg, brdf, shadow):
     r.close()
 
 
+def test_pathtracer_phong_tessellation(oracle, cfg):
+    from pbr_b200 import host
+    cfg.update({"window.width": 96, "window.height": 72, "render.phong_tessellation": 0.6})
+    r = host.Renderer(0)
+    r.set_deterministic(True)
+    r.load_model(MODELS + "/", "suzanne.obj")
+    img = None
+    for _ in range(2):
+        img = r.generate_image()
+    scene = oracle.load_obj(os.path.join(MODELS, "suzanne.obj"), 0)
+    p, (want, _, wstats) = _oracle_for(oracle, cfg, scene, 2, phong_tessellation=0.6)
+    assert np.array_equal(r.flat()["nodes"].view(np.uint32), p.nodes.view(np.uint32))
+    assert Hh.images_equal(img, want)
+    assert np.array_equal(r.stats(reset=True), wstats)
+    r.close()
+
+
 def test_resident_frames_equal_per_frame_readback(cfg):
     from pbr_b200 import host
     cfg.update({"window.width": 96, "window.height": 64})

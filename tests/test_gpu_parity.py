@@ -148,6 +148,24 @@ def test_render_parity_multisample_and_dof(device, suzanne):
     assert np.array_equal(gstats, wstats)
 
 
+@pytest.mark.parametrize("pipeline", [0, 1])
+@pytest.mark.parametrize("brdf,shadow", [(1, 0), (0, 1)])
+def test_render_parity_phong_tessellation(device, suzanne, pipeline, brdf, shadow):
+    """render.phong_tessellation > 0: Ogaki-Tokuyoshi direct ray tracing of Phong tessellation
+    (pt_phongtess.cl) for faces with differing vertex normals, flat test for the others."""
+    p = Hh.Prepared(suzanne, 96, 80, brdf=brdf, shadow_rays=shadow, max_depth=3, phong_tessellation=0.7)
+    assert int(p.defines["phongtess"][0]) == 1
+    got, gdbg, gstats, want, wdbg, wstats = _render_both(device, p, 2, pipeline)
+    assert Hh.mean_relative_error(got, want) <= RADIANCE_MRE_TOLERANCE
+    assert Hh.images_equal(got, want)
+    assert Hh.images_equal(gdbg, wdbg)
+    assert np.array_equal(gstats, wstats)
+    # the tessellated picture differs from the flat one (Suzanne has smooth normals)
+    flat = Hh.Prepared(suzanne, 96, 80, brdf=brdf, shadow_rays=shadow, max_depth=3)
+    fimg, _, _ = flat.oracle_frames(2)
+    assert not Hh.images_equal(fimg, want)
+
+
 def test_render_parity_soup(device, oracle):
     import pbr_b200
     s = pbr_b200.scenes.soup(50000, seed=5)

@@ -84,6 +84,11 @@ struct pbr_ctx {
 	QueueCtl qctl = {nullptr, {nullptr, nullptr}};
 	size_t waveCap = 0;
 
+	/* can any material extend a path beyond MAX_DEPTH? (decides how many wavefront iterations to launch) */
+	pbr_mem extendCacheMem = 0;
+	uint64_t extendCacheEpoch = ~0ull;
+	int extendCacheBrdf = -1;
+	bool canExtendDepth = true;
 	int nodePhaseMin = 16;                     /* PBR_NODE_PHASE_MIN overrides (tuning) */
 	int refillMin = 4;                         /* PBR_REFILL_MIN overrides (tuning) */
 	unsigned long long* stats = nullptr;       /* 6 counters */
@@ -271,6 +276,33 @@ int ensureWave(pbr_ctx* ctx, size_t nPaths) {
 	return PBR_OK;
 }
 
+/* extendDepth (pt_utils.cl:89-96) and the transparency branch of getNewRay (pt_brdf.cl:352-354) are the
+ * only places that set addDepth.  If no material can trigger either, depthAdded stays 0 and a path ends
+ * after MAX_DEPTH bounces: the MAX_ADDED_DEPTH extra wavefront iterations would all be empty. */
+int updateCanExtendDepth(pbr_ctx* ctx, pbr_mem hMaterials, int brdf) {
+	if (ctx->extendCacheMem == hMaterials && ctx->extendCacheEpoch == ctx->sceneEpoch && ctx->extendCacheBrdf == brdf) return PBR_OK;
+	Mem* m = getMem(ctx, hMaterials);
+	if (!m) return fail(ctx, PBR_ERR_INVALID, "pathTracing: materials argument is not a live buffer");
+	const size_t stride = brdf == 0 ? sizeof(pbr_material_schlick) : sizeof(pbr_material_sa);
+	const size_t n = m->bytes / stride;
+	std::vector<float> host(m->bytes / 4 + 1);
+	if (n > 0) {
+		CK(cudaMemcpyAsync(host.data(), m->dptr, n * stride, cudaMemcpyDeviceToHost, ctx->stream));
+		CK(cudaStreamSynchronize(ctx->stream));
+	}
+	bool can = false;
+	for (size_t i = 0; i < n; i++) {
+		const float* d = host.data() + i * stride / 4;     /* d, Ni, (p|nu), (rough|nv) */
+		if (!(d[0] >= 1.0f)) can = true;                    /* d < 1 (or NaN): transparency coin */
+		if (brdf == 1 ? !(fmaxf(d[2], d[3]) < 50.0f) : !(d[3] >= 1.0f)) can = true;
+	}
+	ctx->canExtendDepth = can;
+	ctx->extendCacheMem = hMaterials;
+	ctx->extendCacheEpoch = ctx->sceneEpoch;
+	ctx->extendCacheBrdf = brdf;
+	return PBR_OK;
+}
+
 template <int BRDF, bool SHADOW, bool PHONG>
 int runFrame(pbr_ctx* ctx, const FrameParams& P, int nPaths) {
 	if (ctx->pipeline == 1) {
@@ -297,7 +329,7 @@ int runFrame(pbr_ctx* ctx, const FrameParams& P, int nPaths) {
 		LaunchScope ls(ctx, K_RAYGEN);
 		raygenKernel<<<ctx->smCount * 8, 256, 0, ctx->stream>>>(P, W, Q, nPaths);
 	}
-	const int iterations = P.samples * (P.maxDepth + P.maxAddedDepth);
+	const int iterations = P.samples * (P.maxDepth + (ctx->canExtendDepth ? P.maxAddedDepth : 0));
 	for (int it = 0; it < iterations; it++) {
 		const int in = it & 1, out = in ^ 1;
 		const uint32_t* qIn = (it == 0) ? nullptr : Q.queue[in];
@@ -622,6 +654,8 @@ int pbr_kernel_launch(pbr_ctx* ctx, pbr_kernel k) {
 	int rc = ensureScene(ctx, a.mem[4], a.mem[5], a.mem[7], D.bvh_num_nodes, phong, a.mem[6], a.mem[8]);
 	if (rc) return rc;
 
+	rc = updateCanExtendDepth(ctx, a.mem[9], D.brdf);
+	if (rc) return rc;
 	Mem* materials = getMem(ctx, a.mem[9]);
 	Mem* lights = getMem(ctx, a.mem[10]);
 	Mem* imageIn = getMem(ctx, a.mem[11]);

@@ -116,9 +116,16 @@ int pbr_kernel_time_ms(pbr_ctx* ctx, pbr_kernel k, double* ms);
 
 /* Restrict launches to image rows [y0, y1) -- tile sharding across GPUs. Default: all. */
 int pbr_set_tile(pbr_ctx* ctx, int32_t y0, int32_t y1);
-/* Choose the device pipeline: 0 = wavefront (default), 1 = one-thread-per-pixel megakernel
- * (the reference's launch structure; kept as an on-device cross-check). */
+/* Choose the device pipeline: 0 = wavefront, one traverse + one shade launch per bounce (default);
+ * 1 = one-thread-per-pixel megakernel (the reference's launch structure; kept as an on-device cross-check);
+ * 2 = persistent: one traversal and one shading kernel resident for the whole frame, exchanging paths
+ * through rings in device memory (no per-bounce launch boundaries).  All three write identical pixels. */
 int pbr_set_pipeline(pbr_ctx* ctx, int32_t mode);
+/* Scheduling knobs (never change a pixel): "node_phase_min", "refill_min" (traversal engine), "persist_t",
+ * "persist_s" (blocks per SM of the two persistent kernels, persist_t 0 = what fits), "persist_fill".
+ * The environment variables PBR_NODE_PHASE_MIN, PBR_REFILL_MIN, PBR_PERSIST_T/_S/_FILL, PBR_PIPELINE set
+ * the initial values.  Stands where opencl.localgroupsize stands in the reference's config.json. */
+int pbr_set_tuning(pbr_ctx* ctx, const char* key, int32_t value);
 /* Skip the imageDebug write (the counters are still available through pbr_stats). */
 int pbr_set_debug_image(pbr_ctx* ctx, int32_t enabled);
 /* Counters accumulated since the last call with reset != 0:

@@ -21,7 +21,7 @@ SYMBOLS = [
     "pbr_free_buffers", "pbr_host_alloc", "pbr_host_free",
     "pbr_set_define", "pbr_program_load", "pbr_kernel_get", "pbr_kernel_set_arg", "pbr_kernel_launch",
     "pbr_finish", "pbr_kernel_time_ms",
-    "pbr_set_tile", "pbr_set_pipeline", "pbr_set_debug_image", "pbr_stats",
+    "pbr_set_tile", "pbr_set_pipeline", "pbr_set_tuning", "pbr_set_debug_image", "pbr_stats",
     "pbr_trace", "pbr_trace_device", "pbr_pinned_math_eval",
     "pbr_set_stream", "pbr_profile_enable", "pbr_profile_read",
 ]
@@ -85,6 +85,7 @@ def load_library():
         "pbr_kernel_time_ms": [vp, u64, C.POINTER(C.c_double)],
         "pbr_set_tile": [vp, i32, i32],
         "pbr_set_pipeline": [vp, i32],
+        "pbr_set_tuning": [vp, C.c_char_p, i32],
         "pbr_set_debug_image": [vp, i32],
         "pbr_stats": [vp, vp, i32],
         "pbr_trace": [vp, u64, u64, u64, u64, i32, vp, i64, i32, vp],
@@ -237,6 +238,9 @@ class Device:
 
     def setPipeline(self, mode):
         self._ck(self.lib.pbr_set_pipeline(self.ctx, mode), "pbr_set_pipeline")
+
+    def setTuning(self, key, value):
+        self._ck(self.lib.pbr_set_tuning(self.ctx, key.encode(), int(value)), "pbr_set_tuning")
 
     def setDebugImage(self, enabled):
         self._ck(self.lib.pbr_set_debug_image(self.ctx, int(enabled)), "pbr_set_debug_image")

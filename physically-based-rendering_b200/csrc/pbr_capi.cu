@@ -16,6 +16,7 @@
 
 #include "../../include/pbr_b200.h"
 #include "pt_kernels.cuh"
+#include "pt_persistent.cuh"
 
 using namespace ptk;
 
@@ -91,6 +92,14 @@ struct pbr_ctx {
 	bool canExtendDepth = true;
 	int nodePhaseMin = 16;                     /* PBR_NODE_PHASE_MIN overrides (tuning) */
 	int refillMin = 4;                         /* PBR_REFILL_MIN overrides (tuning) */
+	/* persistent pipeline (pipeline 2): rings between the two resident kernels, second stream */
+	PersistCtl* pctl = nullptr;
+	uint32_t* ring[2] = {nullptr, nullptr};    /* rayRing, hitRing */
+	size_t ringCap = 0;                        /* entries, power of two */
+	cudaStream_t shadeStream = nullptr;
+	cudaEvent_t evFork = nullptr, evJoin = nullptr;
+	bool persistUsed = false;                  /* a pipeline-2 frame ran since the last abort check */
+	int persistTBlocks = 0, persistSBlocks = 2, persistFill = 4;   /* T: 0 = what fits;  PBR_PERSIST_T / _S / _FILL override */
 	unsigned long long* stats = nullptr;       /* 6 counters */
 	unsigned long long* cursor64 = nullptr;    /* work cursor of traceRaysKernel */
 };
@@ -150,7 +159,8 @@ struct LaunchScope {
 	pbr_ctx* ctx;
 	cudaEvent_t a = nullptr, b = nullptr;
 	int kind;
-	LaunchScope(pbr_ctx* c, int k) : ctx(c), kind(k) {
+	cudaStream_t stream;
+	LaunchScope(pbr_ctx* c, int k, cudaStream_t st = nullptr) : ctx(c), kind(k), stream(st ? st : c->stream) {
 		ctx->prof.launches++;
 		switch (kind) {
 			case K_RAYGEN: ctx->prof.raygen_launches++; break;
@@ -161,12 +171,12 @@ struct LaunchScope {
 		if (ctx->profiling) {
 			a = takeEvent(ctx);
 			b = takeEvent(ctx);
-			cudaEventRecord(a, ctx->stream);
+			cudaEventRecord(a, stream);
 		}
 	}
 	~LaunchScope() {
 		if (a) {
-			cudaEventRecord(b, ctx->stream);
+			cudaEventRecord(b, stream);
 			pbr_ctx::Timed t = {a, b, kind};
 			ctx->timedInFlight.push_back(t);
 		}
@@ -276,6 +286,49 @@ int ensureWave(pbr_ctx* ctx, size_t nPaths) {
 	return PBR_OK;
 }
 
+int ensureRings(pbr_ctx* ctx, size_t nPaths) {
+	if (nPaths <= ctx->ringCap / 2 && ctx->pctl) return PBR_OK;
+	size_t cap = 1024;
+	while (cap < 2 * nPaths) cap <<= 1;
+	cudaFree(ctx->ring[0]); cudaFree(ctx->ring[1]);
+	ctx->ring[0] = ctx->ring[1] = nullptr;
+	ctx->ringCap = 0;
+	if (!ctx->pctl) CK(cudaMalloc(&ctx->pctl, sizeof(PersistCtl)));
+	if (!ctx->shadeStream) CK(cudaStreamCreateWithFlags(&ctx->shadeStream, cudaStreamNonBlocking));
+	if (!ctx->evFork) CK(cudaEventCreateWithFlags(&ctx->evFork, cudaEventDisableTiming));
+	if (!ctx->evJoin) CK(cudaEventCreateWithFlags(&ctx->evJoin, cudaEventDisableTiming));
+	CK(cudaMalloc(&ctx->ring[0], cap * 4));
+	CK(cudaMalloc(&ctx->ring[1], cap * 4));
+	CK(cudaMemsetAsync(ctx->ring[0], 0, cap * 4, ctx->stream));
+	CK(cudaMemsetAsync(ctx->ring[1], 0, cap * 4, ctx->stream));
+	CK(cudaMemsetAsync(ctx->pctl, 0, sizeof(PersistCtl), ctx->stream));
+	ctx->ringCap = cap;
+	return PBR_OK;
+}
+
+/* After a pipeline-2 frame: did a watchdog fire?  (The stream must be idle.) */
+int checkPersistAbort(pbr_ctx* ctx) {
+	if (!ctx->persistUsed || !ctx->pctl) return PBR_OK;
+	ctx->persistUsed = false;
+	PersistCtl h;
+	CK(cudaMemcpyAsync(&h, ctx->pctl, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+	CK(cudaStreamSynchronize(ctx->stream));
+	if (getenv("PBR_PERSIST_DEBUG")) {
+		fprintf(stderr, "[persist] idle polls: traverse %llu shade %llu\n", h.idleT, h.idleS);
+		cudaMemsetAsync(&ctx->pctl->idleT, 0, 16, ctx->stream);
+	}
+	if (h.abort != 0u || h.finished != h.total) {
+		cudaMemsetAsync(ctx->ring[0], 0, ctx->ringCap * 4, ctx->stream);
+		cudaMemsetAsync(ctx->ring[1], 0, ctx->ringCap * 4, ctx->stream);
+		cudaMemsetAsync(ctx->pctl, 0, sizeof(PersistCtl), ctx->stream);
+		cudaStreamSynchronize(ctx->stream);
+		char msg[160];
+		snprintf(msg, sizeof(msg), "pathTracing: persistent pipeline gave up (abort=%u, %u of %u pixels written)", h.abort, h.finished, h.total);
+		return fail(ctx, PBR_ERR_INVALID, msg);
+	}
+	return PBR_OK;
+}
+
 /* extendDepth (pt_utils.cl:89-96) and the transparency branch of getNewRay (pt_brdf.cl:352-354) are the
  * only places that set addDepth.  If no material can trigger either, depthAdded stays 0 and a path ends
  * after MAX_DEPTH bounces: the MAX_ADDED_DEPTH extra wavefront iterations would all be empty. */
@@ -318,6 +371,50 @@ int runFrame(pbr_ctx* ctx, const FrameParams& P, int nPaths) {
 	WaveState W = ctx->wave;
 	W.hitN = PHONG ? ctx->hitN : nullptr;
 	const QueueCtl& Q = ctx->qctl;
+
+	if (ctx->pipeline == 2) {
+		/* two kernels resident together for the whole frame (pt_persistent.cuh) */
+		rc = ensureRings(ctx, (size_t) nPaths);
+		if (rc) return rc;
+		const uint32_t mask = (uint32_t) ctx->ringCap - 1u;
+		/* Both kernels must be resident at once: give the shading kernel its blocks per SM and the
+		 * traversal kernel what is left of the register file and the thread slots. */
+		static int regsT = 0, regsS = 0;
+		if (regsT == 0) {
+			cudaFuncAttributes aT, aS;
+			CK(cudaFuncGetAttributes(&aT, persistTraverseKernel<PHONG>));
+			CK(cudaFuncGetAttributes(&aS, persistShadeKernel<BRDF, SHADOW, PHONG>));
+			regsT = (aT.numRegs + 7) / 8 * 8 * 128;
+			regsS = (aS.numRegs + 7) / 8 * 8 * 128;
+		}
+		int sB = ctx->persistSBlocks, tB = ctx->persistTBlocks;
+		while (sB > 1 && sB * regsS + regsT > 65536) sB--;
+		const int room = (65536 - sB * regsS) / regsT;
+		if (tB <= 0 || tB > room) tB = room;
+		if (tB + sB > 16) tB = 16 - sB;
+		if (tB < 1) return fail(ctx, PBR_ERR_INVALID, "pathTracing: persistent pipeline does not fit on an SM");
+		{
+			LaunchScope ls(ctx, K_RAYGEN);
+			persistRaygenKernel<<<ctx->smCount * 8, 256, 0, ctx->stream>>>(P, W, ctx->pctl, ctx->ring[0], nPaths);
+		}
+		CK(cudaEventRecord(ctx->evFork, ctx->stream));
+		CK(cudaStreamWaitEvent(ctx->shadeStream, ctx->evFork, 0));
+		{
+			LaunchScope ls(ctx, K_SHADE, ctx->shadeStream);
+			persistShadeKernel<BRDF, SHADOW, PHONG><<<ctx->smCount * sB, 128, 0, ctx->shadeStream>>>(
+				P, W, ctx->pctl, ctx->ring[0], ctx->ring[1], mask, ctx->persistFill);
+		}
+		CK(cudaEventRecord(ctx->evJoin, ctx->shadeStream));
+		{
+			LaunchScope ls(ctx, K_TRAVERSE);
+			persistTraverseKernel<PHONG><<<ctx->smCount * tB, 128, 0, ctx->stream>>>(
+				P.scene, W, ctx->pctl, ctx->ring[0], ctx->ring[1], mask, ctx->stats);
+		}
+		CK(cudaStreamWaitEvent(ctx->stream, ctx->evJoin, 0));
+		CK(cudaGetLastError());
+		ctx->persistUsed = true;
+		return PBR_OK;
+	}
 
 	int occT = 0, occS = 0;
 	CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occT, traverseKernel<PHONG>, 128, 0));
@@ -406,6 +503,10 @@ int pbr_create(int device, pbr_ctx** out) {
 		const int v = atoi(e);
 		if (v >= 1 && v <= 32) ctx->refillMin = v;
 	}
+	if (const char* e = getenv("PBR_PERSIST_T")) { const int v = atoi(e); if (v >= 0 && v <= 16) ctx->persistTBlocks = v; }
+	if (const char* e = getenv("PBR_PERSIST_S")) { const int v = atoi(e); if (v >= 1 && v <= 16) ctx->persistSBlocks = v; }
+	if (const char* e = getenv("PBR_PERSIST_FILL")) { const int v = atoi(e); if (v >= 0 && v <= 100000) ctx->persistFill = v; }
+	if (const char* e = getenv("PBR_PIPELINE")) { const int v = atoi(e); if (v >= 0 && v <= 2) ctx->pipeline = v; }
 	memset(&ctx->defines, 0, sizeof(ctx->defines));
 	memset(&ctx->args.cam, 0, sizeof(ctx->args.cam));
 	*out = ctx;
@@ -423,6 +524,10 @@ int pbr_destroy(pbr_ctx* ctx) {
 	cudaFree(W.rayO); cudaFree(W.rayD); cudaFree(W.colS); cudaFree(W.finF); cudaFree(W.misc); cudaFree(W.dbg); cudaFree(ctx->hitN);
 	cudaFree(ctx->qctl.queue[0]); cudaFree(ctx->qctl.queue[1]); cudaFree(ctx->qctl.ctrl);
 	cudaFree(ctx->stats); cudaFree(ctx->cursor64);
+	cudaFree(ctx->pctl); cudaFree(ctx->ring[0]); cudaFree(ctx->ring[1]);
+	if (ctx->shadeStream) { cudaStreamSynchronize(ctx->shadeStream); cudaStreamDestroy(ctx->shadeStream); }
+	if (ctx->evFork) cudaEventDestroy(ctx->evFork);
+	if (ctx->evJoin) cudaEventDestroy(ctx->evJoin);
 	cudaEventDestroy(ctx->evStart); cudaEventDestroy(ctx->evStop);
 	for (const pbr_ctx::Timed& t : ctx->timedInFlight) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
 	for (cudaEvent_t e : ctx->eventPool) cudaEventDestroy(e);
@@ -524,7 +629,7 @@ int pbr_image_read(pbr_ctx* ctx, pbr_mem image, size_t width, size_t height, flo
 	CK(cudaSetDevice(ctx->device));
 	CK(cudaMemcpyAsync(host, m->dptr, m->bytes, cudaMemcpyDeviceToHost, ctx->stream));
 	CK(cudaStreamSynchronize(ctx->stream));
-	return PBR_OK;
+	return checkPersistAbort(ctx);
 }
 
 int pbr_image_copy(pbr_ctx* ctx, pbr_mem dst, pbr_mem src) {
@@ -719,7 +824,7 @@ int pbr_finish(pbr_ctx* ctx) {
 	if (!ctx) return PBR_ERR_INVALID;
 	CK(cudaSetDevice(ctx->device));
 	CK(cudaStreamSynchronize(ctx->stream));
-	return PBR_OK;
+	return checkPersistAbort(ctx);
 }
 
 int pbr_kernel_time_ms(pbr_ctx* ctx, pbr_kernel k, double* ms) {
@@ -741,8 +846,20 @@ int pbr_set_tile(pbr_ctx* ctx, int32_t y0, int32_t y1) {
 }
 
 int pbr_set_pipeline(pbr_ctx* ctx, int32_t mode) {
-	if (!ctx || (mode != 0 && mode != 1)) return PBR_ERR_INVALID;
+	if (!ctx || mode < 0 || mode > 2) return PBR_ERR_INVALID;
 	ctx->pipeline = mode;
+	return PBR_OK;
+}
+
+int pbr_set_tuning(pbr_ctx* ctx, const char* key, int32_t value) {
+	if (!ctx || !key) return PBR_ERR_INVALID;
+	const std::string k(key);
+	if (k == "node_phase_min" && value >= 1 && value <= 32) ctx->nodePhaseMin = value;
+	else if (k == "refill_min" && value >= 1 && value <= 32) ctx->refillMin = value;
+	else if (k == "persist_t" && value >= 0 && value <= 16) ctx->persistTBlocks = value;
+	else if (k == "persist_s" && value >= 1 && value <= 16) ctx->persistSBlocks = value;
+	else if (k == "persist_fill" && value >= 0 && value <= 100000) ctx->persistFill = value;
+	else return fail(ctx, PBR_ERR_INVALID, "pbr_set_tuning: unknown key or value out of range: " + k);
 	return PBR_OK;
 }
 

@@ -1,0 +1,59 @@
+"""Persistent pipeline (pbr_set_pipeline 2) against the wavefront on the C2 scene: same bits? how fast?
+python scripts/persist_test.py [tris]          run under `timeout`: a protocol bug would spin, not crash."""
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import bench  # noqa: E402
+import pbr_b200  # noqa: E402,F401
+from pbr_b200 import host, scenes  # noqa: E402
+import helpers as Hh  # noqa: E402
+
+tris = int(sys.argv[1]) if len(sys.argv) > 1 else 1_000_000
+w = dict(bench.WORKLOADS["c2"])
+w["tris"] = tris
+cfg = host.Config()
+bench.host_config(cfg, w)
+r = host.Renderer(0)
+r.set_deterministic(True)
+r.load_scene(scenes.soup(tris, seed=12345))
+dev = r.device()
+FR = 16
+
+
+def run(label, reps=3):
+    best = None
+    for _ in range(reps):
+        r.reset_sample_count()
+        dev.stats(reset=True)
+        t = time.perf_counter()
+        r.render_frames(FR)
+        r.finish()
+        sec = time.perf_counter() - t
+        st = dev.stats(reset=True)
+        best = sec if best is None else min(best, sec)
+    rays = int(st[0]) + int(st[1])
+    img = r.read_image()
+    print("%-34s %7.3f ms/frame  %8.1f Mrays/s  rays %d nodes %d" % (label, best * 1e3 / FR, rays / best / 1e6, rays, st[2]), flush=True)
+    return img, st
+
+
+dev.setPipeline(0)
+ref, st0 = run("wavefront")
+dev.setPipeline(2)
+first = True
+for s_blocks, t_blocks, fill in [(2, 0, 4), (1, 0, 4), (3, 0, 4), (2, 0, 0), (2, 0, 16), (2, 0, 64), (2, 4, 4), (1, 6, 4), (4, 0, 4)]:
+    dev.setTuning("persist_s", s_blocks)
+    dev.setTuning("persist_t", t_blocks)
+    dev.setTuning("persist_fill", fill)
+    img, st = run("persistent S=%d T=%d fill=%d" % (s_blocks, t_blocks, fill))
+    if first:
+        print("  identical to wavefront:", Hh.images_equal(ref, img), " stats equal:", [int(a) for a in st] == [int(a) for a in st0], flush=True)
+        first = False
+    elif not Hh.images_equal(ref, img):
+        print("  MISMATCH", flush=True)

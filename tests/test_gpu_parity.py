@@ -117,7 +117,7 @@ def _render_both(device, prep, frames, pipeline=0):
 
 
 @pytest.mark.parametrize("brdf", [1, 0])
-@pytest.mark.parametrize("pipeline", [0, 1])
+@pytest.mark.parametrize("pipeline", [0, 1, 2])
 def test_render_parity_suzanne(device, suzanne, brdf, pipeline):
     p = Hh.Prepared(suzanne, 128, 96, brdf=brdf, max_depth=4)
     got, gdbg, gstats, want, wdbg, wstats = _render_both(device, p, 4, pipeline)
@@ -148,7 +148,7 @@ def test_render_parity_multisample_and_dof(device, suzanne):
     assert np.array_equal(gstats, wstats)
 
 
-@pytest.mark.parametrize("pipeline", [0, 1])
+@pytest.mark.parametrize("pipeline", [0, 1, 2])
 @pytest.mark.parametrize("brdf,shadow", [(1, 0), (0, 1)])
 def test_render_parity_phong_tessellation(device, suzanne, pipeline, brdf, shadow):
     """render.phong_tessellation > 0: Ogaki-Tokuyoshi direct ray tracing of Phong tessellation

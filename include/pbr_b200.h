@@ -121,6 +121,14 @@ int pbr_set_tile(pbr_ctx* ctx, int32_t y0, int32_t y1);
  * 2 = persistent: one traversal and one shading kernel resident for the whole frame, exchanging paths
  * through rings in device memory (no per-bounce launch boundaries).  All three write identical pixels. */
 int pbr_set_pipeline(pbr_ctx* ctx, int32_t mode);
+/* n_frames consecutive frames in one call.  Same pixels as the reference's frame loop
+ *     for f in 0..n-1: setKernelArg(0, seeds[f]); setKernelArg(1, pixel_weights[f]); execute();
+ *                      imageIn <- imageOut                     (PathTracer::generateImage, PathTracer.cpp:59-71)
+ * with the camera and every other argument as currently set; the result is in imageOut (slot 12), imageIn
+ * (slot 11) is only read.  Without depth of field a pixel's frames depend only on that pixel, so every pixel
+ * starts its next frame the moment it has finished one and the device never drains between frames; with a
+ * focus point set (camera.focusPoint >= 0) the frames are run one after the other. */
+int pbr_kernel_launch_batch(pbr_ctx* ctx, pbr_kernel k, int32_t n_frames, const float* seeds, const float* pixel_weights);
 /* Scheduling knobs (never change a pixel): "node_phase_min", "refill_min" (traversal engine), "persist_t",
  * "persist_s" (blocks per SM of the two persistent kernels, persist_t 0 = what fits), "persist_fill".
  * The environment variables PBR_NODE_PHASE_MIN, PBR_REFILL_MIN, PBR_PERSIST_T/_S/_FILL, PBR_PIPELINE set

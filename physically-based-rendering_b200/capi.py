@@ -21,7 +21,7 @@ SYMBOLS = [
     "pbr_free_buffers", "pbr_host_alloc", "pbr_host_free",
     "pbr_set_define", "pbr_program_load", "pbr_kernel_get", "pbr_kernel_set_arg", "pbr_kernel_launch",
     "pbr_finish", "pbr_kernel_time_ms",
-    "pbr_set_tile", "pbr_set_pipeline", "pbr_set_tuning", "pbr_set_debug_image", "pbr_stats",
+    "pbr_set_tile", "pbr_set_pipeline", "pbr_set_tuning", "pbr_kernel_launch_batch", "pbr_set_debug_image", "pbr_stats",
     "pbr_trace", "pbr_trace_device", "pbr_pinned_math_eval",
     "pbr_set_stream", "pbr_profile_enable", "pbr_profile_read",
 ]
@@ -86,6 +86,7 @@ def load_library():
         "pbr_set_tile": [vp, i32, i32],
         "pbr_set_pipeline": [vp, i32],
         "pbr_set_tuning": [vp, C.c_char_p, i32],
+        "pbr_kernel_launch_batch": [vp, u64, i32, vp, vp],
         "pbr_set_debug_image": [vp, i32],
         "pbr_stats": [vp, vp, i32],
         "pbr_trace": [vp, u64, u64, u64, u64, i32, vp, i64, i32, vp],
@@ -238,6 +239,14 @@ class Device:
 
     def setPipeline(self, mode):
         self._ck(self.lib.pbr_set_pipeline(self.ctx, mode), "pbr_set_pipeline")
+
+    def executeBatch(self, kernel, seeds, pixel_weights):
+        """pbr_kernel_launch_batch: len(seeds) consecutive frames, result in imageOut."""
+        sd = np.ascontiguousarray(seeds, np.float32)
+        pw = np.ascontiguousarray(pixel_weights, np.float32)
+        assert sd.shape == pw.shape and sd.ndim == 1
+        self._ck(self.lib.pbr_kernel_launch_batch(self.ctx, kernel, len(sd), sd.ctypes.data, pw.ctypes.data),
+                 "pbr_kernel_launch_batch")
 
     def setTuning(self, key, value):
         self._ck(self.lib.pbr_set_tuning(self.ctx, key.encode(), int(value)), "pbr_set_tuning")

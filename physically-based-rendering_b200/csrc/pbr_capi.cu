@@ -66,6 +66,7 @@ struct pbr_ctx {
 
 	KernelArgs args;
 	int tileY0 = -1, tileY1 = -1;
+	pbr_mem scratchImage = 0;                  /* pbr_kernel_launch_batch with depth of field */
 	int pipeline = 0;
 	bool debugImage = true;
 
@@ -426,19 +427,35 @@ int runFrame(pbr_ctx* ctx, const FrameParams& P, int nPaths) {
 		LaunchScope ls(ctx, K_RAYGEN);
 		raygenKernel<<<ctx->smCount * 8, 256, 0, ctx->stream>>>(P, W, Q, nPaths);
 	}
-	const int iterations = P.samples * (P.maxDepth + (ctx->canExtendDepth ? P.maxAddedDepth : 0));
+	const int iterations = P.frameCount * P.samples * (P.maxDepth + (ctx->canExtendDepth ? P.maxAddedDepth : 0));
+	static const bool dump = getenv("PBR_PROFILE_DUMP") != nullptr;     /* diagnostics: one line per iteration */
+	cudaEvent_t e0 = nullptr, e1 = nullptr, e2 = nullptr;
+	if (dump) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventCreate(&e2); }
 	for (int it = 0; it < iterations; it++) {
 		const int in = it & 1, out = in ^ 1;
 		const uint32_t* qIn = (it == 0) ? nullptr : Q.queue[in];
+		if (dump) cudaEventRecord(e0, ctx->stream);
 		{
 			LaunchScope ls(ctx, K_TRAVERSE);
 			traverseKernel<PHONG><<<gridT, 128, 0, ctx->stream>>>(P.scene, W, qIn, Q.ctrl + in, Q.ctrl + 2, Q.ctrl + out, ctx->stats);
 		}
+		if (dump) cudaEventRecord(e1, ctx->stream);
 		{
 			LaunchScope ls(ctx, K_SHADE);
 			shadeKernel<BRDF, SHADOW, PHONG><<<gridS, 128, 0, ctx->stream>>>(P, W, qIn, Q.ctrl + in, Q.queue[out], Q.ctrl + out, Q.ctrl + 2);
 		}
+		if (dump) {
+			cudaEventRecord(e2, ctx->stream);
+			uint32_t c[4] = {0, 0, 0, 0};
+			cudaMemcpyAsync(c, Q.ctrl, sizeof(c), cudaMemcpyDeviceToHost, ctx->stream);
+			cudaStreamSynchronize(ctx->stream);
+			float tMs = 0.0f, sMs = 0.0f;
+			cudaEventElapsedTime(&tMs, e0, e1);
+			cudaEventElapsedTime(&sMs, e1, e2);
+			fprintf(stderr, "[wavefront] it %3d  traverse %7.3f ms  shade %7.3f ms  alive after %u\n", it, tMs, sMs, c[out]);
+		}
 	}
+	if (dump) { cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2); }
 	CK(cudaGetLastError());
 	return PBR_OK;
 }
@@ -747,12 +764,10 @@ badsize:
 	return fail(ctx, PBR_ERR_INVALID, "clSetKernelArg: wrong argument size for slot " + std::to_string(index));
 }
 
-int pbr_kernel_launch(pbr_ctx* ctx, pbr_kernel k) {
-	if (!ctx || k != 1) return PBR_ERR_INVALID;
-	if (!ctx->programLoaded) return fail(ctx, PBR_ERR_NOT_READY, "execute before loadProgram");
+/* n consecutive frames (n <= PT_MAX_BATCH) in one pass over the device: frame f uses seeds[f] / weights[f];
+ * frame 0 reads hIn, every later frame reads what the one before wrote to hOut. */
+static int launchFrames(pbr_ctx* ctx, int n, const float* seeds, const float* weights, pbr_mem hIn, pbr_mem hOut) {
 	KernelArgs& a = ctx->args;
-	if ((a.setMask & 0x3fffu) != 0x3fffu) return fail(ctx, PBR_ERR_NOT_READY, "pathTracing: not all 14 arguments are set");
-	CK(cudaSetDevice(ctx->device));
 	const pbr_defines& D = ctx->defines;
 
 	const bool phong = (D.phongtess == 1);
@@ -763,8 +778,8 @@ int pbr_kernel_launch(pbr_ctx* ctx, pbr_kernel k) {
 	if (rc) return rc;
 	Mem* materials = getMem(ctx, a.mem[9]);
 	Mem* lights = getMem(ctx, a.mem[10]);
-	Mem* imageIn = getMem(ctx, a.mem[11]);
-	Mem* imageOut = getMem(ctx, a.mem[12]);
+	Mem* imageIn = getMem(ctx, hIn);
+	Mem* imageOut = getMem(ctx, hOut);
 	Mem* imageDebug = getMem(ctx, a.mem[13]);
 	if (!materials || !lights || !imageIn || !imageOut || !imageDebug)
 		return fail(ctx, PBR_ERR_INVALID, "pathTracing: a buffer / image argument is not live");
@@ -786,7 +801,12 @@ int pbr_kernel_launch(pbr_ctx* ctx, pbr_kernel k) {
 	P.materials = materials->dptr;
 	P.numMaterials = (int) (materials->bytes / (D.brdf == 0 ? sizeof(pbr_material_schlick) : sizeof(pbr_material_sa)));
 	P.cam = a.cam;
-	P.seed = a.seed; P.pixelWeight = a.pixelWeight; P.pxDim = a.pxDim;
+	P.seed = seeds[0]; P.pixelWeight = weights[0]; P.pxDim = a.pxDim;
+	P.frameCount = n;
+	for (int i = 0; i < PT_MAX_BATCH; i++) {
+		P.frameSeed[i] = i < n ? seeds[i] : 0.0f;
+		P.frameWeight[i] = i < n ? weights[i] : 0.0f;
+	}
 	P.width = D.img_width; P.height = D.img_height;
 	P.y0 = ctx->tileY0 < 0 ? 0 : ctx->tileY0;
 	P.y1 = ctx->tileY1 < 0 ? D.img_height : ctx->tileY1;
@@ -802,7 +822,6 @@ int pbr_kernel_launch(pbr_ctx* ctx, pbr_kernel k) {
 	const int nPaths = D.img_width * (P.y1 - P.y0);
 	const bool shadow = (D.shadow_rays == 1);
 
-	CK(cudaEventRecord(ctx->evStart, ctx->stream));
 	const int variant = (D.brdf == 1 ? 4 : 0) | (shadow ? 2 : 0) | (phong ? 1 : 0);
 	switch (variant) {
 		case 0: rc = runFrame<0, false, false>(ctx, P, nPaths); break;
@@ -814,7 +833,67 @@ int pbr_kernel_launch(pbr_ctx* ctx, pbr_kernel k) {
 		case 6: rc = runFrame<1, true, false>(ctx, P, nPaths); break;
 		default: rc = runFrame<1, true, true>(ctx, P, nPaths); break;
 	}
+	return rc;
+}
+
+static int checkLaunchable(pbr_ctx* ctx, pbr_kernel k, uint32_t needed) {
+	if (!ctx || k != 1) return PBR_ERR_INVALID;
+	if (!ctx->programLoaded) return fail(ctx, PBR_ERR_NOT_READY, "execute before loadProgram");
+	if ((ctx->args.setMask & needed) != needed) return fail(ctx, PBR_ERR_NOT_READY, "pathTracing: not all 14 arguments are set");
+	return PBR_OK;
+}
+
+int pbr_kernel_launch(pbr_ctx* ctx, pbr_kernel k) {
+	int rc = checkLaunchable(ctx, k, 0x3fffu);
 	if (rc) return rc;
+	CK(cudaSetDevice(ctx->device));
+	KernelArgs& a = ctx->args;
+	CK(cudaEventRecord(ctx->evStart, ctx->stream));
+	rc = launchFrames(ctx, 1, &a.seed, &a.pixelWeight, a.mem[11], a.mem[12]);
+	if (rc) return rc;
+	CK(cudaEventRecord(ctx->evStop, ctx->stream));
+	ctx->timed = true;
+	return PBR_OK;
+}
+
+int pbr_kernel_launch_batch(pbr_ctx* ctx, pbr_kernel k, int32_t n_frames, const float* seeds, const float* pixel_weights) {
+	int rc = checkLaunchable(ctx, k, 0x3ffcu);         /* slots 0 and 1 come with the call */
+	if (rc) return rc;
+	if (n_frames < 1 || !seeds || !pixel_weights) return fail(ctx, PBR_ERR_INVALID, "pbr_kernel_launch_batch: bad arguments");
+	CK(cudaSetDevice(ctx->device));
+	KernelArgs& a = ctx->args;
+	const pbr_mem hIn = a.mem[11], hOut = a.mem[12];
+	CK(cudaEventRecord(ctx->evStart, ctx->stream));
+	const bool depthOfField = a.cam.focusPoint.x >= 0 && a.cam.focusPoint.y >= 0;
+	if (!depthOfField) {
+		/* pixels are independent of each other: chunks of PT_MAX_BATCH frames, later chunks in place */
+		for (int f = 0; f < n_frames; f += PT_MAX_BATCH) {
+			const int n = n_frames - f < PT_MAX_BATCH ? n_frames - f : PT_MAX_BATCH;
+			rc = launchFrames(ctx, n, seeds + f, pixel_weights + f, f == 0 ? hIn : hOut, hOut);
+			if (rc) return rc;
+		}
+	}
+	else {
+		/* depthOfField reads ANOTHER pixel of the previous frame (pathtracing.cl:41-43): frame by frame,
+		 * ping-pong between imageOut and a scratch image so that the last frame lands in imageOut */
+		Mem* out = getMem(ctx, hOut);
+		if (!out) return fail(ctx, PBR_ERR_INVALID, "pathTracing: imageOut is not live");
+		if (ctx->scratchImage == 0 || !getMem(ctx, ctx->scratchImage) || getMem(ctx, ctx->scratchImage)->bytes < out->bytes) {
+			const uint64_t epoch = ctx->sceneEpoch;
+			Mem* m = nullptr;
+			rc = newMem(ctx, out->bytes, &ctx->scratchImage, &m);
+			if (rc) return rc;
+			m->image = true; m->width = out->width; m->height = out->height;
+			ctx->sceneEpoch = epoch;                   /* not a scene buffer: keep the repacked scene */
+		}
+		pbr_mem prev = hIn;
+		for (int f = 0; f < n_frames; f++) {
+			const pbr_mem dst = ((n_frames - 1 - f) % 2 == 0) ? hOut : ctx->scratchImage;
+			rc = launchFrames(ctx, 1, seeds + f, pixel_weights + f, prev, dst);
+			if (rc) return rc;
+			prev = dst;
+		}
+	}
 	CK(cudaEventRecord(ctx->evStop, ctx->stream));
 	ctx->timed = true;
 	return PBR_OK;

@@ -57,6 +57,8 @@ struct Material {                 /* both reference layouts, widened */
 	vec3 rgbDiff, rgbSpec;
 };
 
+#define PT_MAX_BATCH 32           /* frames per batched launch */
+
 struct FrameParams {
 	SceneDev scene;
 	const void* materials;
@@ -72,6 +74,14 @@ struct FrameParams {
 	float4* imageOut;
 	float4* imageDebug;           /* may be NULL */
 	unsigned long long* stats;    /* 6 counters, see pbr_stats */
+	/* A launch may cover several consecutive frames (pbr_kernel_launch_batch): frame f of the batch uses
+	 * frameSeed[f] / frameWeight[f]; f = 0 reads imageIn, later frames read what the frame before wrote to
+	 * imageOut.  A pixel moves on to its next frame as soon as it has finished one (the frames of one pixel
+	 * depend on each other, different pixels do not), so the device never drains between frames.
+	 * seed / pixelWeight above are frame 0's. */
+	int frameCount;
+	float frameSeed[PT_MAX_BATCH];
+	float frameWeight[PT_MAX_BATCH];
 };
 
 /* ------------------------------------------------------------------ loads */
@@ -843,6 +853,7 @@ struct PathState {
 	uint32_t sample;
 	uint32_t secondaryPaths;
 	uint32_t nNodes, nTris;   /* debugColor.y / debugColor.x */
+	uint32_t frame;           /* frame of the batch this pixel is working on */
 	vec3 hitNormal;           /* PHONGTESS only: ray.normal of the hit (flat faces: recomputed from the edges) */
 };
 
@@ -914,7 +925,7 @@ __device__ __forceinline__ void beginSample(const FrameParams& P, PathState& s, 
 /* Everything the kernel does before the sample loop (pathtracing.cl:235-249). */
 __device__ __forceinline__ void initPath(const FrameParams& P, PathState& s) {
 	s.finalColor = v3(0.0f, 0.0f, 0.0f);
-	s.seed = P.seed;
+	s.seed = P.frameSeed[s.frame];
 	s.focus = 0.0f;
 	s.sample = 0;
 	s.secondaryPaths = 1;
@@ -1091,16 +1102,36 @@ __device__ __forceinline__ void finishPixel(const FrameParams& P, PathState& s, 
 		fc = v3(fc.x / n, fc.y / n, fc.z / n);
 	}
 	const size_t o = (size_t) py * P.width + px;
-	const float4 in = P.imageIn[o];
+	const float4 in = (s.frame == 0u) ? P.imageIn[o] : P.imageOut[o];
+	const float pixelWeight = P.frameWeight[s.frame];
 	float4 out;
-	out.x = pm::mix_(fc.x, in.x, P.pixelWeight);
-	out.y = pm::mix_(fc.y, in.y, P.pixelWeight);
-	out.z = pm::mix_(fc.z, in.z, P.pixelWeight);
+	out.x = pm::mix_(fc.x, in.x, pixelWeight);
+	out.y = pm::mix_(fc.y, in.y, pixelWeight);
+	out.z = pm::mix_(fc.z, in.z, pixelWeight);
 	out.w = s.focus;
 	P.imageOut[o] = out;
 	if (P.imageDebug) {
 		P.imageDebug[o] = make_float4((float) s.nTris / 1082.0f, (float) s.nNodes / 1265.0f, 0.0f, 0.0f);
 	}
+}
+
+/* What follows a bounce: next bounce, next sample (pathtracing.cl:251 loop), or -- pixel written -- the next
+ * frame of the batch.  Returns false when the pixel has nothing left to do in this launch. */
+__device__ __forceinline__ bool advancePath(const FrameParams& P, PathState& s, const BounceResult r, const int px, const int py) {
+	if (r == PATH_CONTINUE) return true;
+	s.sample++;
+	if (s.sample < (uint32_t) P.samples) {
+		beginSample(P, s, px, py);
+		return true;
+	}
+	finishPixel(P, s, px, py);
+	s.frame++;
+	if (s.frame < (uint32_t) P.frameCount) {
+		initPath(P, s);
+		beginSample(P, s, px, py);
+		return true;
+	}
+	return false;
 }
 
 } /* namespace ptd */

@@ -49,7 +49,7 @@ __device__ __forceinline__ void storePath(const WaveState& W, const uint32_t p, 
 	W.rayD[p] = make_float4(s.d.x, s.d.y, s.d.z, __int_as_float(s.hitFace));
 	W.colS[p] = make_float4(s.color.x, s.color.y, s.color.z, s.seed);
 	W.finF[p] = make_float4(s.finalColor.x, s.finalColor.y, s.finalColor.z, s.focus);
-	W.misc[p] = make_uint4(s.depth | ((uint32_t) s.depthAdded << 16), s.sample, s.secondaryPaths, 0u);
+	W.misc[p] = make_uint4(s.depth | ((uint32_t) s.depthAdded << 16), s.sample, s.secondaryPaths, s.frame);
 }
 
 __device__ __forceinline__ void loadPath(const WaveState& W, const uint32_t p, PathState& s) {
@@ -61,7 +61,7 @@ __device__ __forceinline__ void loadPath(const WaveState& W, const uint32_t p, P
 	s.color = v3(c.x, c.y, c.z); s.seed = c.w;
 	s.finalColor = v3(f.x, f.y, f.z); s.focus = f.w;
 	s.depth = m.x & 0xffffu; s.depthAdded = (int) (m.x >> 16);
-	s.sample = m.y; s.secondaryPaths = m.z;
+	s.sample = m.y; s.secondaryPaths = m.z; s.frame = m.w;
 	s.nNodes = g.x; s.nTris = g.y;
 	if (W.hitN) { const float4 n = W.hitN[p]; s.hitNormal = v3(n.x, n.y, n.z); }
 	else s.hitNormal = v3(0.0f, 0.0f, 0.0f);
@@ -83,6 +83,7 @@ __global__ void __launch_bounds__(256) raygenKernel(const FrameParams P, const W
 		int px, py;
 		pathToPixel(p, P.width, P.y0, P.y1 - P.y0, px, py);
 		PathState s;
+		s.frame = 0u;
 		initPath(P, s);
 		beginSample(P, s, px, py);
 		storePath(W, (uint32_t) p, s);
@@ -306,7 +307,7 @@ __global__ void __launch_bounds__(128) shadeKernel(
 	const uint32_t count = *countInPtr;
 	const uint32_t stride = gridDim.x * blockDim.x;
 	const int lane = threadIdx.x & 31;
-	uint32_t shaded = 0, shadowNodes = 0, shadowRays = 0, trisBefore = 0, trisAfter = 0;
+	uint32_t shaded = 0, shadowNodes = 0, shadowRays = 0, trisAfter = 0;
 
 	/* round the loop bound up to a warp multiple so that the ballot below is convergent */
 	const uint32_t countUp = (count + 31u) & ~31u;
@@ -319,24 +320,12 @@ __global__ void __launch_bounds__(128) shadeKernel(
 			loadPath(W, p, s);
 			int px, py;
 			pathToPixel((int) p, P.width, P.y0, P.y1 - P.y0, px, py);
-			trisBefore += s.nTris;
 
 			if (s.t != PM_INF_F) shaded++;
+			const uint32_t nTrisIn = s.nTris;
 			const BounceResult r = bounce<BRDF, SHADOW, PHONG>(P, s, shadowNodes, shadowRays);
-			if (r == PATH_CONTINUE) {
-				alive = true;
-			}
-			else {
-				s.sample++;
-				if (s.sample < (uint32_t) P.samples) {
-					beginSample(P, s, px, py);
-					alive = true;
-				}
-				else {
-					finishPixel(P, s, px, py);
-				}
-			}
-			trisAfter += s.nTris;
+			trisAfter += s.nTris - nTrisIn;                /* shadow-ray triangle tests (advancePath may reset nTris) */
+			alive = advancePath(P, s, r, px, py);
 			if (alive) {
 				storePath(W, p, s);
 				W.dbg[p] = make_uint2(s.nNodes, s.nTris);
@@ -356,7 +345,7 @@ __global__ void __launch_bounds__(128) shadeKernel(
 	if (SHADOW) {
 		warpAddStat(P.stats + 1, shadowRays);
 		warpAddStat(P.stats + 5, shadowNodes);
-		warpAddStat(P.stats + 3, trisAfter - trisBefore);
+		warpAddStat(P.stats + 3, trisAfter);
 	}
 }
 
@@ -365,33 +354,33 @@ __global__ void __launch_bounds__(128) shadeKernel(
 template <int BRDF, bool SHADOW, bool PHONG>
 __global__ void __launch_bounds__(128) megaKernel(const FrameParams P, const int nPaths) {
 	const int p = blockIdx.x * blockDim.x + threadIdx.x;
-	uint32_t rays = 0, shaded = 0, shadowNodes = 0, shadowRays = 0;
+	uint32_t rays = 0, shaded = 0, shadowNodes = 0, shadowRays = 0, nodes = 0, tris = 0;
 	PathState s;
 	s.nNodes = 0; s.nTris = 0;
 	s.hitNormal = v3(0.0f, 0.0f, 0.0f);
 	if (p < nPaths) {
 		int px, py;
 		pathToPixel(p, P.width, P.y0, P.y1 - P.y0, px, py);
-		initPath(P, s);
-		for (; s.sample < (uint32_t) P.samples; s.sample++) {
-			beginSample(P, s, px, py);
-			while (true) {
-				int hitLeaf = -1;
-				traverseClosest<PHONG>(P.scene, s.o, s.d, s.t, s.hitFace, hitLeaf, s.nNodes, s.nTris, s.hitNormal);
-				rays++;
-				if (s.t != PM_INF_F) shaded++;
-				if (bounce<BRDF, SHADOW, PHONG>(P, s, shadowNodes, shadowRays) != PATH_CONTINUE) break;
+		for (s.frame = 0u; s.frame < (uint32_t) P.frameCount; s.frame++) {
+			initPath(P, s);
+			for (; s.sample < (uint32_t) P.samples; s.sample++) {
+				beginSample(P, s, px, py);
+				while (true) {
+					int hitLeaf = -1;
+					traverseClosest<PHONG>(P.scene, s.o, s.d, s.t, s.hitFace, hitLeaf, s.nNodes, s.nTris, s.hitNormal);
+					rays++;
+					if (s.t != PM_INF_F) shaded++;
+					if (bounce<BRDF, SHADOW, PHONG>(P, s, shadowNodes, shadowRays) != PATH_CONTINUE) break;
+				}
 			}
+			finishPixel(P, s, px, py);
+			nodes += s.nNodes; tris += s.nTris;
 		}
-		finishPixel(P, s, px, py);
-	}
-	else {
-		s.nNodes = 0; s.nTris = 0;
 	}
 	warpAddStat(P.stats + 0, rays);
 	warpAddStat(P.stats + 1, shadowRays);
-	warpAddStat(P.stats + 2, s.nNodes);
-	warpAddStat(P.stats + 3, s.nTris);
+	warpAddStat(P.stats + 2, nodes);
+	warpAddStat(P.stats + 3, tris);
 	warpAddStat(P.stats + 4, shaded);
 	warpAddStat(P.stats + 5, shadowNodes);
 }

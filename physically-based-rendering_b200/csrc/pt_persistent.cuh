@@ -86,7 +86,7 @@ __device__ __forceinline__ void loadPathCG(const WaveState& W, const uint32_t p,
 	s.color = v3(c.x, c.y, c.z); s.seed = c.w;
 	s.finalColor = v3(f.x, f.y, f.z); s.focus = f.w;
 	s.depth = m.x & 0xffffu; s.depthAdded = (int) (m.x >> 16);
-	s.sample = m.y; s.secondaryPaths = m.z;
+	s.sample = m.y; s.secondaryPaths = m.z; s.frame = m.w;
 	s.nNodes = g.x; s.nTris = g.y;
 	if (W.hitN) { const float4 n = __ldcg(W.hitN + p); s.hitNormal = v3(n.x, n.y, n.z); }
 	else s.hitNormal = v3(0.0f, 0.0f, 0.0f);
@@ -102,6 +102,7 @@ __global__ void __launch_bounds__(256) persistRaygenKernel(
 		int px, py;
 		pathToPixel(p, P.width, P.y0, P.y1 - P.y0, px, py);
 		PathState s;
+		s.frame = 0u;
 		initPath(P, s);
 		beginSample(P, s, px, py);
 		storePath(W, (uint32_t) p, s);
@@ -291,21 +292,9 @@ __global__ void __launch_bounds__(128) persistShadeKernel(
 			const uint32_t trisBefore = s.nTris;
 			if (s.t != PM_INF_F) shaded++;
 			const BounceResult r = bounce<BRDF, SHADOW, PHONG>(P, s, shadowNodes, shadowRays);
-			if (r == PATH_CONTINUE) {
-				alive = true;
-			}
-			else {
-				s.sample++;
-				if (s.sample < (uint32_t) P.samples) {
-					beginSample(P, s, px, py);
-					alive = true;
-				}
-				else {
-					finishPixel(P, s, px, py);
-					done = true;
-				}
-			}
 			shadowTris += s.nTris - trisBefore;
+			alive = advancePath(P, s, r, px, py);
+			done = !alive;
 			if (alive) {
 				storePath(W, p, s);
 				W.dbg[p] = make_uint2(s.nNodes, s.nTris);

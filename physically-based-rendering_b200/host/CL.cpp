@@ -117,6 +117,17 @@ void CL::execute( cl_kernel kernel ) {
 }
 
 
+/**
+ * Additive: `frames` consecutive frames of `kernel` in one call (pbr_kernel_launch_batch) -- what a loop of
+ * setKernelArg( 0, seed ), setKernelArg( 1, weight ), execute(), "output becomes input" does, without the
+ * device draining between frames.
+ */
+void CL::executeBatch( cl_kernel kernel, cl_uint frames, const cl_float* seeds, const cl_float* pixelWeights ) {
+	this->checkError( pbr_kernel_launch_batch( mContext, kernel, (int32_t) frames, seeds, pixelWeights ), "clEnqueueNDRangeKernel" );
+	mKernelTime[kernel] = -1.0;
+}
+
+
 /** Reference: CL.cpp:312-316. */
 void CL::finish() {
 	this->checkError( pbr_finish( mContext ), "clFinish" );

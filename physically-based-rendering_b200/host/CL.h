@@ -56,6 +56,7 @@ class CL {
 
 		/** Additive (see include/pbr_b200.h): device-side image copy, tiles, counters, pinned memory. */
 		void copyImage( cl_mem dst, cl_mem src );
+		void executeBatch( cl_kernel kernel, cl_uint frames, const cl_float* seeds, const cl_float* pixelWeights );
 		void setTile( int y0, int y1 );
 		void setDebugImage( bool enabled );
 		void getStats( uint64_t out[6], bool reset );

@@ -129,11 +129,30 @@ void PathTracer::generateImageInto( cl_float* target, cl_float* targetDebug ) {
 }
 
 
+/**
+ * `frames` more frames without a read-back in between, handed to the device as one batch: the seeds and
+ * mixing weights of all of them are fixed up front (wall-clock seeds are spaced by 1/30 s, the step of the
+ * deterministic schedule, instead of by the time the frames happen to take).
+ */
 void PathTracer::renderFrames( cl_uint frames ) {
+	if( frames == 0 ) { return; }
 	mCL->setDebugImage( false );
-	for( cl_uint i = 0; i < frames; i++ ) {
-		this->launchFrame();
+	this->updateEyeBuffer();
+	if( mHaveOutput ) {
+		std::swap( mBufTextureIn, mBufTextureOut );
+		mCL->setKernelArg( mKernelPathTracing, 11, sizeof( cl_mem ), &mBufTextureIn );
+		mCL->setKernelArg( mKernelPathTracing, 12, sizeof( cl_mem ), &mBufTextureOut );
 	}
+	vector<cl_float> seeds( frames ), weights( frames );
+	const cl_float now = this->getTimeSinceStart();
+	for( cl_uint i = 0; i < frames; i++ ) {
+		seeds[i] = mDeterministicSeeds ? this->nextSeed() : now + 0.0333f * (cl_float) i;
+		weights[i] = mSampleCount / (cl_float) ( mSampleCount + 1 );
+		mSampleCount++;
+	}
+	mCL->setKernelArg( mKernelPathTracing, 3, sizeof( camera_cl ), &mStructCam );
+	mCL->executeBatch( mKernelPathTracing, frames, &seeds[0], &weights[0] );
+	mHaveOutput = true;
 }
 
 

@@ -112,6 +112,17 @@ class DeviceScene:
                 dbg = dev.readImageOutput(self.texDebug, p.W, p.H)
         return img, dbg
 
+    def frames_batch(self, nframes, image=None, first=0):
+        """The same frames through pbr_kernel_launch_batch (one call).  Returns (imageOut, imageDebug)."""
+        dev, p, k = self.dev, self.prep, self.kernel
+        img = np.zeros((p.H, p.W, 4), f32) if image is None else image
+        dev.updateImageReadOnly(self.texIn, p.W, p.H, img)
+        dev.setKernelArg(k, 3, p.camera)
+        ks = range(first, first + nframes)
+        dev.executeBatch(k, [S.frame_seed(n) for n in ks], [S.pixel_weight(n) for n in ks])
+        dev.finish()
+        return dev.readImageOutput(self.texOut, p.W, p.H), dev.readImageOutput(self.texDebug, p.W, p.H)
+
     def trace(self, rays, any_hit=False):
         return self.dev.trace(self.bufBVH, self.bufFacesV, self.bufVertices, rays, any_hit=any_hit,
                               lights=self.bufLights, num_lights=self.prep.num_lights)

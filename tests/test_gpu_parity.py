@@ -166,6 +166,46 @@ def test_render_parity_phong_tessellation(device, suzanne, pipeline, brdf, shado
     assert not Hh.images_equal(fimg, want)
 
 
+def _batch_both(device, prep, frames, pipeline):
+    ds = Hh.DeviceScene(device, prep)
+    device.setPipeline(pipeline)
+    device.stats(reset=True)
+    try:
+        got, gdbg = ds.frames_batch(frames)
+        gstats = device.stats(reset=True)
+    finally:
+        device.setPipeline(0)
+    want, wdbg, wstats = prep.oracle_frames(frames)
+    return got, gdbg, gstats, want, wdbg, wstats
+
+
+@pytest.mark.parametrize("pipeline", [0, 1, 2])
+@pytest.mark.parametrize("brdf,shadow,samples", [(1, 0, 1), (0, 1, 2)])
+def test_render_parity_batched_frames(device, suzanne, pipeline, brdf, shadow, samples):
+    """pbr_kernel_launch_batch: pixels run ahead into their next frame, the pixels stay the reference's."""
+    p = Hh.Prepared(suzanne, 112, 80, brdf=brdf, shadow_rays=shadow, samples=samples, max_depth=4)
+    got, gdbg, gstats, want, wdbg, wstats = _batch_both(device, p, 6, pipeline)
+    assert Hh.mean_relative_error(got, want) <= RADIANCE_MRE_TOLERANCE
+    assert Hh.images_equal(got, want)
+    assert Hh.images_equal(gdbg, wdbg)
+    assert np.array_equal(gstats, wstats)
+
+
+def test_render_batched_frames_depth_of_field_and_long_batches(device, suzanne):
+    # depth of field couples pixels across frames: the batch call must fall back to frame-by-frame
+    p = Hh.Prepared(suzanne, 64, 64, samples=2, max_depth=3, focus_point=(32, 20))
+    got, gdbg, gstats, want, wdbg, wstats = _batch_both(device, p, 5, 0)
+    assert Hh.images_equal(got, want)
+    assert np.array_equal(gstats, wstats)
+    # more frames than one device batch holds (PT_MAX_BATCH = 32), continuing an accumulated image
+    p = Hh.Prepared(suzanne, 48, 32, max_depth=3)
+    ds = Hh.DeviceScene(device, p)
+    start, _ = ds.frames(2)
+    seq, _ = ds.frames(35, image=start.copy(), first=2, host_roundtrip=False)
+    bat, _ = ds.frames_batch(35, image=start.copy(), first=2)
+    assert Hh.images_equal(seq, bat)
+
+
 def test_render_parity_soup(device, oracle):
     import pbr_b200
     s = pbr_b200.scenes.soup(50000, seed=5)

@@ -229,8 +229,11 @@ def run_ours(args):
 
     def step_resident():
         r.reset_sample_count()
-        for _ in range(SPP):
-            frame()
+        if world == 1:
+            r.render_frames(SPP)         # one pbr_kernel_launch_batch call, the frames run back to back
+        else:
+            for _ in range(SPP):
+                frame()                  # every frame is combined across ranks (progressive display)
 
     pinned = torch.empty((H, W, 4), dtype=torch.float32).pin_memory()
     pinned_np = pinned.numpy()

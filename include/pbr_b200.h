@@ -119,18 +119,25 @@ int pbr_set_tile(pbr_ctx* ctx, int32_t y0, int32_t y1);
 /* Choose the device pipeline: 0 = wavefront, one traverse + one shade launch per bounce (default);
  * 1 = one-thread-per-pixel megakernel (the reference's launch structure; kept as an on-device cross-check);
  * 2 = persistent: one traversal and one shading kernel resident for the whole frame, exchanging paths
- * through rings in device memory (no per-bounce launch boundaries).  All three write identical pixels. */
+ * through rings in device memory (no per-bounce launch boundaries);
+ * 3 = wavefront with carry-over: a traverse launch ends when its queue runs dry and parks unfinished rays
+ * for the next launch (the launch call then blocks until the frame is nearly done).
+ * All four write identical pixels; 0 is the fastest on every scene measured so far. */
 int pbr_set_pipeline(pbr_ctx* ctx, int32_t mode);
 /* n_frames consecutive frames in one call.  Same pixels as the reference's frame loop
  *     for f in 0..n-1: setKernelArg(0, seeds[f]); setKernelArg(1, pixel_weights[f]); execute();
  *                      imageIn <- imageOut                     (PathTracer::generateImage, PathTracer.cpp:59-71)
  * with the camera and every other argument as currently set; the result is in imageOut (slot 12), imageIn
- * (slot 11) is only read.  Without depth of field a pixel's frames depend only on that pixel, so every pixel
- * starts its next frame the moment it has finished one and the device never drains between frames; with a
- * focus point set (camera.focusPoint >= 0) the frames are run one after the other. */
+ * (slot 11) is only read.  One call instead of 4 n, no host round trip between frames.  Without depth of field a
+ * pixel's frames depend only on that pixel: the frames accumulate in place in imageOut, and with
+ * pbr_set_tuning("batch_interleave", 1) every pixel starts its next frame the moment it has finished one
+ * (up to 32 frames in flight; measured slower than frame-after-frame on the C2 scene).  With a
+ * focus point set (camera.focusPoint >= 0) a frame reads another pixel of the previous one, so the frames
+ * ping-pong between imageOut and a scratch image. */
 int pbr_kernel_launch_batch(pbr_ctx* ctx, pbr_kernel k, int32_t n_frames, const float* seeds, const float* pixel_weights);
 /* Scheduling knobs (never change a pixel): "node_phase_min", "refill_min" (traversal engine), "persist_t",
- * "persist_s" (blocks per SM of the two persistent kernels, persist_t 0 = what fits), "persist_fill".
+ * "persist_s" (blocks per SM of the two persistent kernels, persist_t 0 = what fits), "persist_fill",
+ * "tail_steps_bulk", "tail_steps_flush", "flush_group" (carry-over wavefront), "batch_interleave".
  * The environment variables PBR_NODE_PHASE_MIN, PBR_REFILL_MIN, PBR_PERSIST_T/_S/_FILL, PBR_PIPELINE set
  * the initial values.  Stands where opencl.localgroupsize stands in the reference's config.json. */
 int pbr_set_tuning(pbr_ctx* ctx, const char* key, int32_t value);

@@ -81,10 +81,21 @@ struct pbr_ctx {
 	int numNodesDev = 0;
 
 	/* wavefront state */
-	WaveState wave = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+	WaveState wave = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 	float4* hitN = nullptr;                    /* allocated with the wave state, used when PHONGTESS */
 	QueueCtl qctl = {nullptr, {nullptr, nullptr}};
 	size_t waveCap = 0;
+
+	/* carry-over wavefront (pipeline 3): resume nodes, hit queue, two carry queues, counters, host mailbox */
+	int* waveNode = nullptr;
+	uint32_t* hitQ = nullptr;
+	uint32_t* carryQ[2] = {nullptr, nullptr};
+	uint32_t* cctl = nullptr;                  /* nNew[2], nCarry[2], nHit[2], cursor, - */
+	uint32_t* mailbox = nullptr;               /* pinned, MAILBOX_SLOTS words */
+	cudaEvent_t evGroup[2] = {nullptr, nullptr};
+	int tailStepsBulk = 64, tailStepsFlush = 256, flushGroup = 4;
+	int prevGroupBegin = 0;
+	int batchInterleave = 0;                   /* pbr_kernel_launch_batch: let pixels run ahead into later frames */
 
 	/* can any material extend a path beyond MAX_DEPTH? (decides how many wavefront iterations to launch) */
 	pbr_mem extendCacheMem = 0;
@@ -139,6 +150,8 @@ int newMem(pbr_ctx* ctx, size_t bytes, pbr_mem* out, Mem** mp) {
 	ctx->sceneEpoch++;
 	return PBR_OK;
 }
+
+enum { MAILBOX_SLOTS = 256 };
 
 int gridFor(long long n, int block) { return (int) ((n + block - 1) / block); }
 
@@ -270,7 +283,9 @@ int ensureWave(pbr_ctx* ctx, size_t nPaths) {
 	WaveState& W = ctx->wave;
 	cudaFree(W.rayO); cudaFree(W.rayD); cudaFree(W.colS); cudaFree(W.finF); cudaFree(W.misc); cudaFree(W.dbg); cudaFree(ctx->hitN);
 	cudaFree(ctx->qctl.queue[0]); cudaFree(ctx->qctl.queue[1]);
-	W = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+	cudaFree(ctx->waveNode); cudaFree(ctx->hitQ); cudaFree(ctx->carryQ[0]); cudaFree(ctx->carryQ[1]);
+	ctx->waveNode = nullptr; ctx->hitQ = nullptr; ctx->carryQ[0] = ctx->carryQ[1] = nullptr;
+	W = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 	ctx->hitN = nullptr;
 	ctx->qctl.queue[0] = ctx->qctl.queue[1] = nullptr;
 	ctx->waveCap = 0;
@@ -283,6 +298,17 @@ int ensureWave(pbr_ctx* ctx, size_t nPaths) {
 	CK(cudaMalloc(&ctx->hitN, nPaths * 16));
 	CK(cudaMalloc(&ctx->qctl.queue[0], nPaths * 4));
 	CK(cudaMalloc(&ctx->qctl.queue[1], nPaths * 4));
+	CK(cudaMalloc(&ctx->waveNode, nPaths * 4));
+	CK(cudaMalloc(&ctx->hitQ, nPaths * 4));
+	CK(cudaMalloc(&ctx->carryQ[0], nPaths * 4));
+	CK(cudaMalloc(&ctx->carryQ[1], nPaths * 4));
+	if (!ctx->cctl) {
+		CK(cudaMalloc(&ctx->cctl, 8 * sizeof(uint32_t)));
+		CK(cudaMemset(ctx->cctl, 0, 8 * sizeof(uint32_t)));
+		CK(cudaHostAlloc(&ctx->mailbox, MAILBOX_SLOTS * sizeof(uint32_t), cudaHostAllocMapped));
+		CK(cudaEventCreateWithFlags(&ctx->evGroup[0], cudaEventDisableTiming));
+		CK(cudaEventCreateWithFlags(&ctx->evGroup[1], cudaEventDisableTiming));
+	}
 	ctx->waveCap = nPaths;
 	return PBR_OK;
 }
@@ -417,6 +443,85 @@ int runFrame(pbr_ctx* ctx, const FrameParams& P, int nPaths) {
 		return PBR_OK;
 	}
 
+	if (ctx->pipeline == 3) {
+		/* wavefront with carry-over (traverseCarryKernel): the number of iterations depends on the rays,
+		 * so launches go out in groups and the host looks at the mailbox of the group before the one it
+		 * has just enqueued -- the device never waits for the host */
+		W.node = ctx->waveNode;
+		int occT = 0, occS = 0;
+		CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occT, traverseCarryKernel<PHONG>, 128, 0));
+		CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occS, shadeKernel<BRDF, SHADOW, PHONG>, 128, 0));
+		const int gridT = ctx->smCount * (occT > 0 ? occT : 1);
+		const int gridS = ctx->smCount * (occS > 0 ? occS : 1);
+		uint32_t* c = ctx->cctl;
+		uint32_t* mailboxDev = nullptr;
+		CK(cudaHostGetDevicePointer((void**) &mailboxDev, ctx->mailbox, 0));
+		static const bool dump = getenv("PBR_PROFILE_DUMP") != nullptr;
+		{
+			LaunchScope ls(ctx, K_RAYGEN);
+			raygenCarryKernel<<<ctx->smCount * 8, 256, 0, ctx->stream>>>(P, W, c, nPaths);
+		}
+		const int firstGroup = P.frameCount * P.samples > 1 ? P.frameCount * P.samples : P.maxDepth;
+		int it = 0;
+		for (int group = 0; ; group++) {
+			const int n = group == 0 ? firstGroup : ctx->flushGroup;
+			const int itBegin = it;
+			for (int j = 0; j < n; j++, it++) {
+				const int a = it & 1, b = a ^ 1;
+				ctx->mailbox[it % MAILBOX_SLOTS] = 0xffffffffu;
+				CarryQueues Qc;
+				Qc.qCarryIn = ctx->carryQ[a]; Qc.nCarryIn = c + 2 + a;
+				Qc.qNew = (it == 0) ? nullptr : Q.queue[a]; Qc.nNew = c + 0 + a;
+				Qc.qHit = ctx->hitQ; Qc.nHit = c + 4 + a;
+				Qc.qCarryOut = ctx->carryQ[b]; Qc.nCarryOut = c + 2 + b;
+				Qc.cursor = c + 6;
+				Qc.zeroAtStart = c + 0 + b;
+				Qc.mailbox = mailboxDev + (it % MAILBOX_SLOTS);
+				cudaEvent_t d0 = nullptr, d1 = nullptr, d2 = nullptr;
+				if (dump) { d0 = takeEvent(ctx); d1 = takeEvent(ctx); d2 = takeEvent(ctx); cudaEventRecord(d0, ctx->stream); }
+				{
+					LaunchScope ls(ctx, K_TRAVERSE);
+					traverseCarryKernel<PHONG><<<gridT, 128, 0, ctx->stream>>>(P.scene, W, Qc, ctx->tailStepsBulk, ctx->tailStepsFlush, ctx->stats);
+				}
+				if (dump) cudaEventRecord(d1, ctx->stream);
+				{
+					LaunchScope ls(ctx, K_SHADE);
+					shadeKernel<BRDF, SHADOW, PHONG><<<gridS, 128, 0, ctx->stream>>>(
+						P, W, ctx->hitQ, c + 4 + a, Q.queue[b], c + 0 + b, c + 6, c + 2 + a, c + 4 + b);
+				}
+				if (dump) {
+					cudaEventRecord(d2, ctx->stream);
+					uint32_t h[8];
+					cudaMemcpyAsync(h, c, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream);
+					cudaStreamSynchronize(ctx->stream);
+					float tMs = 0.0f, sMs = 0.0f;
+					cudaEventElapsedTime(&tMs, d0, d1);
+					cudaEventElapsedTime(&sMs, d1, d2);
+					fprintf(stderr, "[carry] it %3d  start %8u  traverse %7.3f ms -> finished %8u parked %8u   shade %6.3f ms -> new %8u\n",
+						it, ((volatile uint32_t*) ctx->mailbox)[it % MAILBOX_SLOTS], tMs, h[4 + a], h[2 + b], sMs, h[0 + b]);
+					ctx->eventPool.push_back(d0); ctx->eventPool.push_back(d1); ctx->eventPool.push_back(d2);
+				}
+			}
+			CK(cudaEventRecord(ctx->evGroup[group & 1], ctx->stream));
+			CK(cudaGetLastError());
+			if (group >= 1 || dump) {
+				/* the group before this one: did one of its launches start with nothing to do? */
+				const int gPrev = dump ? group : group - 1;
+				CK(cudaEventSynchronize(ctx->evGroup[gPrev & 1]));
+				bool done = false;
+				const int pb = dump ? itBegin : ctx->prevGroupBegin, pe = dump ? it : itBegin;
+				for (int k = pb; k < pe; k++) {
+					const uint32_t live = ((volatile uint32_t*) ctx->mailbox)[k % MAILBOX_SLOTS];
+					if (live == 0u) done = true;
+				}
+				if (done) break;
+			}
+			ctx->prevGroupBegin = itBegin;
+			if (it > 1000000) return fail(ctx, PBR_ERR_INVALID, "pathTracing: carry-over wavefront does not terminate");
+		}
+		return PBR_OK;
+	}
+
 	int occT = 0, occS = 0;
 	CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occT, traverseKernel<PHONG>, 128, 0));
 	CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occS, shadeKernel<BRDF, SHADOW, PHONG>, 128, 0));
@@ -523,7 +628,7 @@ int pbr_create(int device, pbr_ctx** out) {
 	if (const char* e = getenv("PBR_PERSIST_T")) { const int v = atoi(e); if (v >= 0 && v <= 16) ctx->persistTBlocks = v; }
 	if (const char* e = getenv("PBR_PERSIST_S")) { const int v = atoi(e); if (v >= 1 && v <= 16) ctx->persistSBlocks = v; }
 	if (const char* e = getenv("PBR_PERSIST_FILL")) { const int v = atoi(e); if (v >= 0 && v <= 100000) ctx->persistFill = v; }
-	if (const char* e = getenv("PBR_PIPELINE")) { const int v = atoi(e); if (v >= 0 && v <= 2) ctx->pipeline = v; }
+	if (const char* e = getenv("PBR_PIPELINE")) { const int v = atoi(e); if (v >= 0 && v <= 3) ctx->pipeline = v; }
 	memset(&ctx->defines, 0, sizeof(ctx->defines));
 	memset(&ctx->args.cam, 0, sizeof(ctx->args.cam));
 	*out = ctx;
@@ -542,6 +647,10 @@ int pbr_destroy(pbr_ctx* ctx) {
 	cudaFree(ctx->qctl.queue[0]); cudaFree(ctx->qctl.queue[1]); cudaFree(ctx->qctl.ctrl);
 	cudaFree(ctx->stats); cudaFree(ctx->cursor64);
 	cudaFree(ctx->pctl); cudaFree(ctx->ring[0]); cudaFree(ctx->ring[1]);
+	cudaFree(ctx->waveNode); cudaFree(ctx->hitQ); cudaFree(ctx->carryQ[0]); cudaFree(ctx->carryQ[1]); cudaFree(ctx->cctl);
+	if (ctx->mailbox) cudaFreeHost(ctx->mailbox);
+	if (ctx->evGroup[0]) cudaEventDestroy(ctx->evGroup[0]);
+	if (ctx->evGroup[1]) cudaEventDestroy(ctx->evGroup[1]);
 	if (ctx->shadeStream) { cudaStreamSynchronize(ctx->shadeStream); cudaStreamDestroy(ctx->shadeStream); }
 	if (ctx->evFork) cudaEventDestroy(ctx->evFork);
 	if (ctx->evJoin) cudaEventDestroy(ctx->evJoin);
@@ -866,9 +975,12 @@ int pbr_kernel_launch_batch(pbr_ctx* ctx, pbr_kernel k, int32_t n_frames, const 
 	CK(cudaEventRecord(ctx->evStart, ctx->stream));
 	const bool depthOfField = a.cam.focusPoint.x >= 0 && a.cam.focusPoint.y >= 0;
 	if (!depthOfField) {
-		/* pixels are independent of each other: chunks of PT_MAX_BATCH frames, later chunks in place */
-		for (int f = 0; f < n_frames; f += PT_MAX_BATCH) {
-			const int n = n_frames - f < PT_MAX_BATCH ? n_frames - f : PT_MAX_BATCH;
+		/* pixels are independent of each other, so everything after frame 0 can run in place in imageOut:
+		 * frame after frame (default: the rays of one bounce of one frame stay together, which the caches
+		 * like), or -- "batch_interleave" -- PT_MAX_BATCH frames per pass, pixels running ahead */
+		const int chunk = ctx->batchInterleave ? PT_MAX_BATCH : 1;
+		for (int f = 0; f < n_frames; f += chunk) {
+			const int n = n_frames - f < chunk ? n_frames - f : chunk;
 			rc = launchFrames(ctx, n, seeds + f, pixel_weights + f, f == 0 ? hIn : hOut, hOut);
 			if (rc) return rc;
 		}
@@ -925,7 +1037,7 @@ int pbr_set_tile(pbr_ctx* ctx, int32_t y0, int32_t y1) {
 }
 
 int pbr_set_pipeline(pbr_ctx* ctx, int32_t mode) {
-	if (!ctx || mode < 0 || mode > 2) return PBR_ERR_INVALID;
+	if (!ctx || mode < 0 || mode > 3) return PBR_ERR_INVALID;
 	ctx->pipeline = mode;
 	return PBR_OK;
 }
@@ -938,6 +1050,10 @@ int pbr_set_tuning(pbr_ctx* ctx, const char* key, int32_t value) {
 	else if (k == "persist_t" && value >= 0 && value <= 16) ctx->persistTBlocks = value;
 	else if (k == "persist_s" && value >= 1 && value <= 16) ctx->persistSBlocks = value;
 	else if (k == "persist_fill" && value >= 0 && value <= 100000) ctx->persistFill = value;
+	else if (k == "tail_steps_bulk" && value >= 1 && value <= 1000000) ctx->tailStepsBulk = value;
+	else if (k == "tail_steps_flush" && value >= 1 && value <= 1000000) ctx->tailStepsFlush = value;
+	else if (k == "flush_group" && value >= 1 && value <= 64) ctx->flushGroup = value;
+	else if (k == "batch_interleave" && (value == 0 || value == 1)) ctx->batchInterleave = value;
 	else return fail(ctx, PBR_ERR_INVALID, "pbr_set_tuning: unknown key or value out of range: " + k);
 	return PBR_OK;
 }

@@ -36,6 +36,7 @@ struct WaveState {
 	uint4* misc;
 	uint2* dbg;
 	float4* hitN;             /* PHONGTESS only: normal of the hit found by traverse */
+	int* node;                /* carry-over wavefront only: node at which the path's ray resumes (1 = new ray) */
 };
 
 /* ctrl[0], ctrl[1]: element counts of queue 0 / 1;  ctrl[2]: work cursor of the traverse kernel */
@@ -50,6 +51,7 @@ __device__ __forceinline__ void storePath(const WaveState& W, const uint32_t p, 
 	W.colS[p] = make_float4(s.color.x, s.color.y, s.color.z, s.seed);
 	W.finF[p] = make_float4(s.finalColor.x, s.finalColor.y, s.finalColor.z, s.focus);
 	W.misc[p] = make_uint4(s.depth | ((uint32_t) s.depthAdded << 16), s.sample, s.secondaryPaths, s.frame);
+	if (W.node) W.node[p] = 1;
 }
 
 __device__ __forceinline__ void loadPath(const WaveState& W, const uint32_t p, PathState& s) {
@@ -297,12 +299,196 @@ __global__ void __launch_bounds__(128) traverseKernel(
 	warpAddStat(stats + 3, tris);
 }
 
+
+/* ------------------------------------------------------------------ traverse with carry-over */
+
+/*
+ * The number of nodes a ray visits has a long tail (C2: mean 150, max > 1 400), a ray is one serial chain
+ * of dependent loads (~0.5 us per node under load), and with persistent warps nearly every warp ends up
+ * holding one of the long rays: a launch of traverseKernel lasts ~0.9 ms however few rays it has, and no
+ * block retires early enough for another kernel to fill in.  Here a launch ends when its queue runs dry:
+ * `tailSteps` node steps after a warp has seen the queue empty it tests the leaves it has pending, retires
+ * the rays that are done and parks the others -- best hit so far in the path state, next node in
+ * WaveState::node -- in the carry queue.  The next launch resumes them first, packed densely with the rays
+ * of the next bounce, so the machine is always full and a long ray only delays its own path.  A resumed ray
+ * continues at exactly the node where it stopped with exactly the state it had: same visits, same hits.
+ *
+ *   in:  carry queue (parked by the previous launch) ++ new queue (written by the previous shade launch)
+ *   out: hit queue (finished rays, for the next shade launch) and the other carry queue
+ */
+struct CarryQueues {
+	const uint32_t* qCarryIn; const uint32_t* nCarryIn;
+	const uint32_t* qNew; const uint32_t* nNew;       /* qNew == NULL: identity (first iteration) */
+	uint32_t* qHit; uint32_t* nHit;
+	uint32_t* qCarryOut; uint32_t* nCarryOut;
+	uint32_t* cursor;
+	uint32_t* zeroAtStart;                             /* a counter nobody uses during this launch */
+	volatile uint32_t* mailbox;                        /* host-visible: how many rays this launch started with */
+};
+
+/* Append path p to a queue for every lane with `push` set; all 32 lanes must call. */
+__device__ __forceinline__ void queueAppend(uint32_t* queue, uint32_t* count, const bool push, const uint32_t p) {
+	const unsigned FULL = 0xffffffffu;
+	const int lane = threadIdx.x & 31;
+	const unsigned m = __ballot_sync(FULL, push);
+	if (m == 0u) return;
+	const int leader = __ffs(m) - 1;
+	uint32_t base = 0;
+	if (lane == leader) base = atomicAdd(count, (uint32_t) __popc(m));
+	base = __shfl_sync(FULL, base, leader);
+	if (push) queue[base + (uint32_t) __popc(m & ((1u << lane) - 1u))] = p;
+}
+
+template <bool PHONG>
+__global__ void __launch_bounds__(128) traverseCarryKernel(
+	const SceneDev S, const WaveState W, const CarryQueues Q, const int tailStepsBulk, const int tailStepsFlush,
+	unsigned long long* stats
+) {
+	const unsigned FULL = 0xffffffffu;
+	const int lane = threadIdx.x & 31;
+	const unsigned ltMask = (1u << lane) - 1u;
+	const unsigned lastNode = (unsigned) (S.numNodes - 1);
+	const uint32_t nCarry = *Q.nCarryIn, count = nCarry + *Q.nNew;
+	if (blockIdx.x == 0 && threadIdx.x == 0) {
+		*Q.zeroAtStart = 0u;
+		*Q.mailbox = count;
+		__threadfence_system();
+	}
+	/* fewer rays than lanes: nothing is waiting behind them, let them run longer before parking */
+	int budget = (count > gridDim.x * blockDim.x) ? tailStepsBulk : tailStepsFlush;
+
+	LaneRay L;
+	L.index = 0;
+	int state = LANE_IDLE;
+	bool exhausted = false;
+	uint32_t p = 0, nodes = 0, tris = 0, rays = 0, trips = 0;
+
+	while (true) {
+		/* retire finished rays */
+		const bool fin = (state == LANE_FINISHED);
+		if (fin) {
+			W.rayO[p].w = L.rt;
+			W.rayD[p].w = __int_as_float(L.hitFace);
+			uint2 g = W.dbg[p];
+			g.x += L.nn; g.y += L.nt;
+			W.dbg[p] = g;
+			if (PHONG) W.hitN[p] = make_float4(L.normal.x, L.normal.y, L.normal.z, 0.0f);
+			nodes += L.nn; tris += L.nt; rays++;
+			state = LANE_IDLE;
+		}
+		queueAppend(Q.qHit, Q.nHit, fin, p);
+
+		/* refill idle lanes: parked rays first, then the new ones */
+		const unsigned need = __ballot_sync(FULL, state == LANE_IDLE);
+		if (!exhausted && (__popc(need) >= S.refillMin || need == FULL)) {
+			const int leader = __ffs(need) - 1;
+			const int n = __popc(need);
+			uint32_t base = 0;
+			if (lane == leader) base = atomicAdd(Q.cursor, (uint32_t) n);
+			base = __shfl_sync(FULL, base, leader);
+			if (state == LANE_IDLE) {
+				const uint32_t i = base + (uint32_t) __popc(need & ltMask);
+				if (i < count) {
+					p = (i < nCarry) ? Q.qCarryIn[i] : (Q.qNew ? Q.qNew[i - nCarry] : i - nCarry);
+					const float4 a = W.rayO[p], b = W.rayD[p];
+					const int node = W.node[p];
+					L.o = v3(a.x, a.y, a.z);
+					L.d = v3(b.x, b.y, b.z);
+					L.invDir = v3(pm::rcp(b.x), pm::rcp(b.y), pm::rcp(b.z));
+					L.rt = a.w;
+					L.tLight = a.w;
+					L.hitFace = __float_as_int(b.w);
+					L.hitLeaf = -1;
+					L.index = node;
+					L.nn = 0;
+					L.nt = 0;
+					L.normal = v3(0.0f, 0.0f, 0.0f);
+					if (node == 1) {
+						if (S.numLights > 0) traverseLights(S, L.o, L.d, L.rt, L.hitFace);
+					}
+					else if (PHONG) {
+						const float4 hn = W.hitN[p];
+						L.normal = v3(hn.x, hn.y, hn.z);
+					}
+					state = ((unsigned) (L.index - 1) < lastNode) ? LANE_STEPPING : LANE_FINISHED;
+				}
+			}
+			if (base + (uint32_t) n >= count) exhausted = true;
+		}
+		if (__ballot_sync(FULL, state != LANE_IDLE) == 0u) break;
+
+		/* a warp that never needs a refill learns from the cursor that the queue is empty */
+		if (!exhausted && (++trips & 7u) == 0u) {
+			uint32_t c = 0;
+			if (lane == 0) c = *((volatile uint32_t*) Q.cursor);
+			exhausted = __shfl_sync(FULL, c, 0) >= count;
+		}
+
+		/* node phase */
+		while (true) {
+			if (state == LANE_STEPPING) {
+				const bool leaf = nodeStep<false>(S, L);
+				const bool inside = (unsigned) (L.index - 1) < lastNode;
+				state = leaf ? LANE_PENDING : (inside ? LANE_STEPPING : LANE_FINISHED);
+			}
+			if (exhausted) budget--;
+			if (__popc(__ballot_sync(FULL, state == LANE_STEPPING)) < S.nodePhaseMin || (exhausted && budget <= 0)) break;
+		}
+
+		/* triangle phase */
+		if (state == LANE_PENDING) {
+			leafStep<false, PHONG>(S, L);
+			state = ((unsigned) (L.index - 1) < lastNode) ? LANE_STEPPING : LANE_FINISHED;
+		}
+
+		/* queue empty and the grace period over: park what is still walking (finished rays retire above) */
+		if (exhausted && budget <= 0) {
+			const bool park = (state == LANE_STEPPING);
+			if (park) {
+				W.rayO[p].w = L.rt;
+				W.rayD[p].w = __int_as_float(L.hitFace);
+				uint2 g = W.dbg[p];
+				g.x += L.nn; g.y += L.nt;
+				W.dbg[p] = g;
+				if (PHONG) W.hitN[p] = make_float4(L.normal.x, L.normal.y, L.normal.z, 0.0f);
+				W.node[p] = L.index;
+				nodes += L.nn; tris += L.nt;
+				state = LANE_IDLE;
+			}
+			queueAppend(Q.qCarryOut, Q.nCarryOut, park, p);
+		}
+	}
+	warpAddStat(stats + 0, rays);
+	warpAddStat(stats + 2, nodes);
+	warpAddStat(stats + 3, tris);
+}
+
+/* raygen for the carry-over wavefront: ctl = nNew[2], nCarry[2], nHit[2], cursor */
+__global__ void __launch_bounds__(256) raygenCarryKernel(const FrameParams P, const WaveState W, uint32_t* ctl, const int nPaths) {
+	const int stride = gridDim.x * blockDim.x;
+	for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < nPaths; p += stride) {
+		int px, py;
+		pathToPixel(p, P.width, P.y0, P.y1 - P.y0, px, py);
+		PathState s;
+		s.frame = 0u;
+		initPath(P, s);
+		beginSample(P, s, px, py);
+		storePath(W, (uint32_t) p, s);
+		W.dbg[p] = make_uint2(0u, 0u);
+	}
+	if (blockIdx.x == 0 && threadIdx.x == 0) {
+		ctl[0] = (uint32_t) nPaths;
+		for (int i = 1; i < 8; i++) ctl[i] = 0u;
+	}
+}
+
 /* ------------------------------------------------------------------ shade */
 
 template <int BRDF, bool SHADOW, bool PHONG>
 __global__ void __launch_bounds__(128) shadeKernel(
 	const FrameParams P, const WaveState W, const uint32_t* __restrict__ queueIn, const uint32_t* __restrict__ countInPtr,
-	uint32_t* __restrict__ queueOut, uint32_t* countOutPtr, uint32_t* cursorToReset
+	uint32_t* __restrict__ queueOut, uint32_t* countOutPtr, uint32_t* cursorToReset,
+	uint32_t* reset1 = nullptr, uint32_t* reset2 = nullptr
 ) {
 	const uint32_t count = *countInPtr;
 	const uint32_t stride = gridDim.x * blockDim.x;
@@ -340,7 +526,11 @@ __global__ void __launch_bounds__(128) shadeKernel(
 			if (alive) queueOut[base + __popc(m & ((1u << lane) - 1u))] = p;
 		}
 	}
-	if (blockIdx.x == 0 && threadIdx.x == 0) *cursorToReset = 0u;
+	if (blockIdx.x == 0 && threadIdx.x == 0) {
+		*cursorToReset = 0u;
+		if (reset1) *reset1 = 0u;
+		if (reset2) *reset2 = 0u;
+	}
 	warpAddStat(P.stats + 4, shaded);
 	if (SHADOW) {
 		warpAddStat(P.stats + 1, shadowRays);

@@ -15,7 +15,11 @@ bench.host_config(cfg, w)
 r = host.Renderer(0)
 r.set_deterministic(True)
 r.load_scene(scenes.soup(w["tris"], seed=12345))
-for k in range(3):
+dev = r.device()
+dev.setPipeline(int(sys.argv[1]) if len(sys.argv) > 1 else 0)
+for k, v in [a.split("=") for a in sys.argv[2:]]:
+    dev.setTuning(k, int(v))
+for k in range(2):
     print("--- single frame", k, file=sys.stderr, flush=True)
     r.render_frames(1)
     r.finish()

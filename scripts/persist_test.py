@@ -51,6 +51,18 @@ dev.setPipeline(0)
 ref, st0 = run("wavefront, frame by frame", batch=False)
 img, st = run("wavefront, batched")
 print("  identical:", Hh.images_equal(ref, img), " stats equal:", [int(a) for a in st] == [int(a) for a in st0], flush=True)
+for bulk, flush, grp in [(64, 256, 4), (16, 256, 4), (256, 256, 4), (64, 64, 4), (64, 1024, 4), (64, 256, 2), (64, 256, 8)]:
+    dev.setPipeline(3)
+    dev.setTuning("tail_steps_bulk", bulk)
+    dev.setTuning("tail_steps_flush", flush)
+    dev.setTuning("flush_group", grp)
+    img, st = run("carry bulk=%d flush=%d grp=%d, frame by frame" % (bulk, flush, grp), batch=False)
+    ok1 = Hh.images_equal(ref, img) and [int(a) for a in st] == [int(a) for a in st0]
+    img, st = run("carry bulk=%d flush=%d grp=%d, batched" % (bulk, flush, grp))
+    ok2 = Hh.images_equal(ref, img) and [int(a) for a in st] == [int(a) for a in st0]
+    print("  identical + stats equal:", ok1, ok2, flush=True)
+if len(sys.argv) > 2:
+    sys.exit(0)
 dev.setPipeline(2)
 img, st = run("persistent S=2, frame by frame", batch=False)
 print("  identical:", Hh.images_equal(ref, img), " stats equal:", [int(a) for a in st] == [int(a) for a in st0], flush=True)

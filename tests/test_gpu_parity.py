@@ -117,7 +117,7 @@ def _render_both(device, prep, frames, pipeline=0):
 
 
 @pytest.mark.parametrize("brdf", [1, 0])
-@pytest.mark.parametrize("pipeline", [0, 1, 2])
+@pytest.mark.parametrize("pipeline", [0, 1, 2, 3])
 def test_render_parity_suzanne(device, suzanne, brdf, pipeline):
     p = Hh.Prepared(suzanne, 128, 96, brdf=brdf, max_depth=4)
     got, gdbg, gstats, want, wdbg, wstats = _render_both(device, p, 4, pipeline)
@@ -148,7 +148,7 @@ def test_render_parity_multisample_and_dof(device, suzanne):
     assert np.array_equal(gstats, wstats)
 
 
-@pytest.mark.parametrize("pipeline", [0, 1, 2])
+@pytest.mark.parametrize("pipeline", [0, 1, 2, 3])
 @pytest.mark.parametrize("brdf,shadow", [(1, 0), (0, 1)])
 def test_render_parity_phong_tessellation(device, suzanne, pipeline, brdf, shadow):
     """render.phong_tessellation > 0: Ogaki-Tokuyoshi direct ray tracing of Phong tessellation
@@ -166,25 +166,29 @@ def test_render_parity_phong_tessellation(device, suzanne, pipeline, brdf, shado
     assert not Hh.images_equal(fimg, want)
 
 
-def _batch_both(device, prep, frames, pipeline):
+def _batch_both(device, prep, frames, pipeline, interleave=1):
     ds = Hh.DeviceScene(device, prep)
     device.setPipeline(pipeline)
+    device.setTuning("batch_interleave", interleave)
     device.stats(reset=True)
     try:
         got, gdbg = ds.frames_batch(frames)
         gstats = device.stats(reset=True)
     finally:
         device.setPipeline(0)
+        device.setTuning("batch_interleave", 0)
     want, wdbg, wstats = prep.oracle_frames(frames)
     return got, gdbg, gstats, want, wdbg, wstats
 
 
-@pytest.mark.parametrize("pipeline", [0, 1, 2])
+@pytest.mark.parametrize("pipeline", [0, 1, 2, 3])
+@pytest.mark.parametrize("interleave", [0, 1])
 @pytest.mark.parametrize("brdf,shadow,samples", [(1, 0, 1), (0, 1, 2)])
-def test_render_parity_batched_frames(device, suzanne, pipeline, brdf, shadow, samples):
-    """pbr_kernel_launch_batch: pixels run ahead into their next frame, the pixels stay the reference's."""
+def test_render_parity_batched_frames(device, suzanne, pipeline, interleave, brdf, shadow, samples):
+    """pbr_kernel_launch_batch, frame after frame or with pixels running ahead into their next frame:
+    the pixels stay the reference's."""
     p = Hh.Prepared(suzanne, 112, 80, brdf=brdf, shadow_rays=shadow, samples=samples, max_depth=4)
-    got, gdbg, gstats, want, wdbg, wstats = _batch_both(device, p, 6, pipeline)
+    got, gdbg, gstats, want, wdbg, wstats = _batch_both(device, p, 6, pipeline, interleave)
     assert Hh.mean_relative_error(got, want) <= RADIANCE_MRE_TOLERANCE
     assert Hh.images_equal(got, want)
     assert Hh.images_equal(gdbg, wdbg)
@@ -202,8 +206,11 @@ def test_render_batched_frames_depth_of_field_and_long_batches(device, suzanne):
     ds = Hh.DeviceScene(device, p)
     start, _ = ds.frames(2)
     seq, _ = ds.frames(35, image=start.copy(), first=2, host_roundtrip=False)
-    bat, _ = ds.frames_batch(35, image=start.copy(), first=2)
-    assert Hh.images_equal(seq, bat)
+    for interleave in (0, 1):
+        device.setTuning("batch_interleave", interleave)
+        bat, _ = ds.frames_batch(35, image=start.copy(), first=2)
+        device.setTuning("batch_interleave", 0)
+        assert Hh.images_equal(seq, bat)
 
 
 def test_render_parity_soup(device, oracle):

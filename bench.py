@@ -362,38 +362,82 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
-def cpu_baseline_sample(w, flat, scene, budget_s=12.0):
-    """The CPU oracle (a port of the reference kernels, oracle/pt_oracle.cpp) on all host cores for a
-    bounded sample of the same workload: whole frames of the full image at 1 spp for about budget_s."""
+def _c2_defines(w, num_nodes, sky):
+    from oracle import scene as S
+    return S.defines(w["width"], w["height"], num_nodes, 0, sky, brdf=1, samples=1, max_depth=3, max_added_depth=5,
+                     shadow_rays=0, antialiasing=0.7)
+
+
+def reference_program_values(w=None):
+    """The program text values (CL::setValues) of the workload the reference arm runs: lets
+    oracle/build_ref.py prebuild the reference kernel for it where /root/reference exists."""
     from oracle import oracle as O
+    from oracle import ref as R
+    from oracle import scene as S
+    import pbr_b200
+    w = dict(WORKLOADS["c2"]) if w is None else w
+    scene = pbr_b200.scenes.soup(w["tris"], seed=12345)
+    bvh = O.build_bvh(scene)
+    _, sky = S.pack_materials(scene["materials"], scene["materialNames"], 1)
+    return R.values_from_defines(_c2_defines(w, bvh["nodes"].shape[0], sky))
+
+
+def cpu_frame_runner(D, px, cam, nodes, facesV, facesN, v4, mats, threads):
+    """One frame of the path on the host CPU.  Prefers the reference's own kernel (oracle/_ref, built from
+    the reference's sources by oracle/build_ref.py: kind "reference"); without it, the restatement
+    (oracle/pt_oracle.cpp: kind "port").  Returns (frame(k, image) -> image, count_rays(k, image) -> int, kind).
+    The ray count of a frame comes from the restatement's counters (same pixels, same rays) and is taken
+    outside the timed region."""
+    from oracle import oracle as O
+    from oracle import ref as R
+    from oracle import scene as S
+
+    def port(k, img):
+        out, _, st = O.path_tracing(D, S.frame_seed(k), S.pixel_weight(k), px, cam, nodes, facesV, facesN, v4, None,
+                                    mats, None, img, nthreads=threads, debug=False)
+        return out, int(st[0]) + int(st[1])
+
+    if R.available(D):
+        R.lib(D)                                                 # build / load outside the timed region
+
+        def frame(k, img):
+            out, _ = R.path_tracing(D, S.frame_seed(k), S.pixel_weight(k), px, cam, nodes, facesV, facesN, v4, None,
+                                    mats, None, img, nthreads=threads)
+            return out
+        return frame, (lambda k, img: port(k, img)[1]), "reference"
+    return (lambda k, img: port(k, img)[0]), (lambda k, img: port(k, img)[1]), "port"
+
+
+def cpu_baseline_sample(w, flat, scene, budget_s=12.0):
+    """The reference kernel on all host cores (see cpu_frame_runner) for a bounded sample of the same
+    workload: whole frames of the full image at 1 spp for about budget_s."""
     from oracle import scene as S
     threads = os.cpu_count() or 1
     W, H = w["width"], w["height"]
     v4 = S.pack_float4(scene["vertices"])
     mats, sky = S.pack_materials(scene["materials"], scene["materialNames"], 1)
-    D = S.defines(W, H, flat["nodes"].shape[0], 0, sky, brdf=1, samples=1, max_depth=3, max_added_depth=5,
-                  shadow_rays=0, antialiasing=0.7)
+    D = _c2_defines(w, flat["nodes"].shape[0], sky)
     cam = S.camera(eye=w["eye"])
     px = S.px_dim(W, H)
+    frame, count_rays, kind = cpu_frame_runner(D, px, cam, flat["nodes"], flat["facesV"], flat["facesN"], v4, mats, threads)
     img = np.zeros((H, W, 4), np.float32)
-    rays = 0
+    inputs = []
     frames = 0
     t0 = time.perf_counter()
     while frames < 1 or (time.perf_counter() - t0) * (frames + 1) / frames < budget_s:
-        k = frames
-        img, _, st = O.path_tracing(D, S.frame_seed(k), S.pixel_weight(k), px, cam, flat["nodes"], flat["facesV"],
-                                    flat["facesN"], v4, None, mats, None, img, nthreads=threads, debug=False)
-        rays += int(st[0]) + int(st[1])
+        inputs.append(img)
+        img = frame(frames, img)
         frames += 1
     sec = time.perf_counter() - t0
-    return {"value": round(rays / sec / 1e6, 3), "unit": "Mrays/s", "cores": threads, "kind": "port",
+    rays = sum(count_rays(k, inputs[k]) for k in range(frames))
+    return {"value": round(rays / sec / 1e6, 3), "unit": "Mrays/s", "cores": threads, "kind": kind,
             "sample": "%d frame(s) of the full %dx%d image at 1 spp (%d rays) in %.1f s" % (frames, W, H, rays, sec)}
 
 
 # ------------------------------------------------------------------------------------------- reference
 
 def run_reference(args):
-    """The reference's algorithm on the host CPU: oracle port, all host threads, rank 0 only."""
+    """The reference's kernel on the host CPU (cpu_frame_runner), all host threads, rank 0 only."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -407,39 +451,37 @@ def run_reference(args):
     bvh = O.build_bvh(scene)                                    # the oracle's own (literal) BVH builder
     v4 = S.pack_float4(scene["vertices"])
     mats, sky = S.pack_materials(scene["materials"], scene["materialNames"], 1)
-    D = S.defines(W, H, bvh["nodes"].shape[0], 0, sky, brdf=1, samples=1, max_depth=3, max_added_depth=5,
-                  shadow_rays=0, antialiasing=0.7)
+    D = _c2_defines(w, bvh["nodes"].shape[0], sky)
     cam = S.camera(eye=w["eye"])
     px = S.px_dim(W, H)
+    frame, count_rays, kind = cpu_frame_runner(D, px, cam, bvh["nodes"], bvh["facesV"], bvh["facesN"], v4, mats, threads)
     img = np.zeros((H, W, 4), np.float32)
-
-    def step(k):
-        nonlocal img
-        img, _, st = O.path_tracing(D, S.frame_seed(k), S.pixel_weight(k), px, cam, bvh["nodes"], bvh["facesV"],
-                                    bvh["facesN"], v4, None, mats, None, img, nthreads=threads, debug=False)
-        return int(st[0]) + int(st[1])
 
     k = 0
     for _ in range(args.warmup):
-        step(k)
+        img = frame(k, img)
         k += 1
-    rays = 0
+    inputs = []
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        rays += step(k)
+        inputs.append((k, img))
+        img = frame(k, img)
         k += 1
     sec = time.perf_counter() - t0
+    rays = sum(count_rays(kk, im) for kk, im in inputs)
     value = round(rays / sec / 1e6, 3)
     sample = "each step = 1 frame of the full %dx%d image at 1 spp (1/%d of the GPU arm's step)" % (W, H, w["spp"])
+    note = ("the reference's own kernel source (source/opencl/pathtracing.cl + pt_*.cl) compiled for the host by "
+            "oracle/build_ref.py, one work-item after the other on all host threads" if kind == "reference" else
+            "CPU restatement of the reference kernels (oracle port); oracle/_ref for this configuration was not "
+            "prebuilt and /root/reference is not present")
     line = {
         "impl": "reference", "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(sec * 1e3 / args.steps, 3),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": w["name"], "triangles": w["tris"], "width": W, "height": H,
-                   "spp_per_step": 1, "max_depth": 3, "max_added_depth": 5, "brdf": 1,
-                   "note": "CPU restatement of the reference kernels (oracle port); the reference itself "
-                           "cannot be built here (no OpenCL ICD / pocl, Boost, GLM, Qt)"},
-        "cpu_baseline": {"value": value, "unit": "Mrays/s", "cores": threads, "kind": "port", "sample": sample},
+                   "spp_per_step": 1, "max_depth": 3, "max_added_depth": 5, "brdf": 1, "note": note},
+        "cpu_baseline": {"value": value, "unit": "Mrays/s", "cores": threads, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }

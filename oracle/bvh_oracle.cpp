@@ -10,8 +10,10 @@
  * std::sort per axis per node) so that it is easy to audit against the source; the product's
  * builder (host/BVH.cpp) is an allocation-free design that must produce the same arrays.
  *
- * PARITY STATUS: unpinned against reference outputs (the reference cannot be built here);
- * soft pin: suzanne.obj has 1082 faces (pathtracing.cl:75).  See oracle/pt_oracle.cpp.
+ * PARITY STATUS: this file (host-side BVH build) is NOT pinned against reference outputs: BVH.cpp
+ * needs Boost / GLM / the reference's build system and cannot be compiled here.  Soft pin:
+ * suzanne.obj has 1082 faces (pathtracing.cl:75).  What IS pinned is the kernel that walks the tree:
+ * oracle/pt_oracle.cpp against the reference's own kernel source (oracle/build_ref.py).
  *
  * Only tests/, __graft_entry__.smoke() and bench.py's baseline legs may load this library.
  */

@@ -11,9 +11,15 @@
  * include/pbr_pinned_math.h; everything else keeps the reference's
  * expression order, with -ffp-contract=off so nothing is fused that the reference does not fuse.
  *
- * PARITY STATUS: the reference ships no tests, golden vectors or known answers for this path
- * and cannot be built or run here (no OpenCL ICD, Boost, GLM, Qt) -- so parity against the
- * reference's own outputs is UNPINNED.  What is pinned: the soft known-answer of
+ * PARITY STATUS: PINNED against outputs of the reference itself.  The reference ships no tests,
+ * golden vectors or known answers for this path and its host program cannot be built here (no
+ * OpenCL ICD, Boost, GLM, Qt) -- but its KERNEL SOURCE can: oracle/build_ref.py assembles the
+ * program text the way CL::combineParts / CL::setValues do and compiles it for the host behind
+ * oracle/ref_shim/cl_compat.h (OpenCL built-ins = the same pinned arithmetic), into oracle/_ref/.
+ * tests/test_oracle_vs_reference.py requires this restatement to equal that build bit for bit:
+ * image and debug image for 12 configurations (both BRDFs, shadow rays, SAMPLES > 1, depth of
+ * field, Phong tessellation, extended depth, three scenes) and t / hitFace / node visits / face
+ * tests for explicit closest-hit and shadow rays.  Also pinned: the soft known-answer of
  * pathtracing.cl:75-76 (suzanne.obj: 1082 faces) and brute-force cross-checks in tests/.
  *
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may

@@ -166,6 +166,26 @@ def test_render_parity_phong_tessellation(device, suzanne, pipeline, brdf, shado
     assert not Hh.images_equal(fimg, want)
 
 
+@pytest.mark.parametrize("name", sorted(__import__("ref_configs").CASES))
+def test_device_equals_reference_kernel(device, name):
+    """The CUDA path against the reference's OWN kernel source compiled for the host (oracle/_ref, built by
+    oracle/build_ref.py where /root/reference exists): image and debug image, bit for bit."""
+    import ref_configs
+    from oracle import ref as R
+    from oracle import scene as S
+    p = ref_configs.prepared(name)
+    if not R.available(p.defines):
+        pytest.skip("oracle/_ref not built for this configuration")
+    ds = Hh.DeviceScene(device, p)
+    got, gdbg = ds.frames(3)
+    img = np.zeros((p.H, p.W, 4), np.float32)
+    for k in range(3):
+        img, dbg = R.path_tracing(p.defines, S.frame_seed(k), S.pixel_weight(k), p.px_dim, p.camera, p.nodes, p.facesV,
+                                  p.facesN, p.vertices4, p.normals4, p.materials, p.lights, img, nthreads=8)
+    assert Hh.images_equal(got, img)
+    assert Hh.images_equal(gdbg, dbg)
+
+
 def _batch_both(device, prep, frames, pipeline, interleave=1):
     ds = Hh.DeviceScene(device, prep)
     device.setPipeline(pipeline)

@@ -13,6 +13,11 @@
  *
  * boost::algorithm::trim / boost::split(.., is_any_of(" \t")) are restated below.
  *
+ * PARITY STATUS: PINNED against the reference's own ObjParser / MtlParser / LightParser compiled from
+ * /root/reference/source (oracle/build_ref_host.py -> oracle/_ref/libref_host.so): every parsed array,
+ * material and light identical for the bundled models, the quirks fixture and generated scenes
+ * (tests/test_oracle_vs_reference_host.py).
+ *
  * Only tests/, __graft_entry__.smoke() and bench.py's baseline legs may load this library.
  */
 #include <ctype.h>

@@ -73,6 +73,9 @@ int pbrh_renderer_load_model(pbrh_renderer* r, const char* filepath, const char*
 int pbrh_renderer_set_deterministic(pbrh_renderer* r, int32_t enabled);
 /* frame k uses seed 0.0333f * (k * stride + offset + 1): disjoint seeds for sample-sharded ranks */
 int pbrh_renderer_set_seed_schedule(pbrh_renderer* r, uint32_t stride, uint32_t offset);
+/* simulated clock: frame with global index g gets the seed the reference derives from its wall clock at
+ * t = ms * (g + 1) milliseconds, (ms * (g + 1)) * 0.001f (PathTracer.cpp:78-82); 0 = off */
+int pbrh_renderer_set_frame_time_ms(pbrh_renderer* r, uint32_t ms);
 int pbrh_renderer_set_tile(pbrh_renderer* r, int32_t y0, int32_t y1);
 /* PathTracer::generateImage: one frame, accumulated image into out[W*H*4]; debug may be NULL */
 int pbrh_renderer_generate_image(pbrh_renderer* r, float* out, float* debug);
@@ -85,6 +88,8 @@ int pbrh_renderer_reset_sample_count(pbrh_renderer* r);
 int pbrh_renderer_set_focus(pbrh_renderer* r, int32_t x, int32_t y);
 int pbrh_renderer_set_eye(pbrh_renderer* r, float x, float y, float z);
 int pbrh_renderer_rotate_camera(pbrh_renderer* r, int32_t move_x, int32_t move_y);
+/* Camera::cameraMove{Forward,Backward,Left,Right,Up,Down} / cameraReset (Camera.cpp:24-88): direction 0..6 */
+int pbrh_renderer_move_camera(pbrh_renderer* r, int32_t direction);
 /* info: width, height, sample count, BVH nodes (all), emitted nodes, faces, lights, skipped */
 int pbrh_renderer_info(pbrh_renderer* r, int64_t info[8], double* bvh_build_seconds, double* last_kernel_ms);
 int pbrh_renderer_stats(pbrh_renderer* r, uint64_t out[6], int32_t reset);

@@ -21,7 +21,8 @@ ROOT = os.path.dirname(HERE)
 OUT = os.path.join(HERE, "_ref")
 REF_SRC = "/root/reference/source"
 SOURCES = ["Cfg.cpp", "Logger.cpp", "MathHelp.cpp", "ObjParser.cpp", "MtlParser.cpp", "LightParser.cpp",
-           "ModelLoader.cpp", "accelstructures/AccelStructure.cpp", "accelstructures/BVH.cpp"]
+           "ModelLoader.cpp", "accelstructures/AccelStructure.cpp", "accelstructures/BVH.cpp",
+           "Camera.cpp", "PathTracer.cpp"]
 SO = os.path.join(OUT, "libref_host.so")
 
 
@@ -32,7 +33,8 @@ def reference_available():
 def build(force=False, verbose=False):
     shim = os.path.join(HERE, "ref_shim", "host")
     driver = os.path.join(HERE, "ref_shim", "host_driver.cpp")
-    deps = [driver] + [os.path.join(dp, f) for dp, _, fs in os.walk(shim) for f in fs]
+    fake_cl = os.path.join(HERE, "ref_shim", "fake_cl.cpp")
+    deps = [driver, fake_cl] + [os.path.join(dp, f) for dp, _, fs in os.walk(shim) for f in fs]
     if os.path.isfile(SO) and not force and all(os.path.getmtime(d) <= os.path.getmtime(SO) for d in deps):
         return SO
     if not reference_available():
@@ -41,8 +43,8 @@ def build(force=False, verbose=False):
         raise FileNotFoundError("reference sources not present (%s) and %s not prebuilt" % (REF_SRC, SO))
     os.makedirs(OUT, exist_ok=True)
     cmd = ["g++", "-O2", "-std=gnu++11", "-ffp-contract=off", "-fPIC", "-shared", "-pthread", "-w", "-Wno-narrowing",
-           "-fpermissive", "-include", os.path.join(shim, "cl_types.h"), "-I", shim, "-I", REF_SRC, driver]
-    cmd += [os.path.join(REF_SRC, s) for s in SOURCES] + ["-o", SO]
+           "-fpermissive", "-include", os.path.join(shim, "cl_types.h"), "-I", shim, "-I", REF_SRC, driver, fake_cl]
+    cmd += [os.path.join(REF_SRC, s) for s in SOURCES] + ["-ldl", "-o", SO]
     if verbose:
         print(" ".join(cmd), flush=True)
     r = subprocess.run(cmd, capture_output=True, text=True)

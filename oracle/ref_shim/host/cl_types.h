@@ -12,11 +12,11 @@
 #define PBR_REF_CL_TYPES_H
 
 #define CL_HPP_           /* skip /root/reference/source/cl.hpp */
+#define GLWIDGET_H        /* skip /root/reference/source/qt/GLWidget.h (Qt, GLEW, GLUT); stand-in below */
 
 /* what the Khronos headers would have brought in (cl_platform.h, cl.hpp) */
 #include <float.h>
 #include <limits.h>
-#include <math.h>
 #include <stddef.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -24,6 +24,10 @@
 #include <string.h>
 #include <sys/types.h>    /* uint (BVH.h) */
 #ifdef __cplusplus
+/* <cmath>, not <math.h>: with the toolchain the reference was written for, an unqualified tan( float ) is the C
+ * function (binary64); libstdc++'s newer <math.h> wrapper would pull the float overloads into the global
+ * namespace and silently change PathTracer::initKernelArgs' pixel size (PathTracer.cpp:90). */
+#include <cmath>
 #include <algorithm>
 #include <iostream>
 #include <limits>
@@ -70,9 +74,46 @@ typedef union {
 	struct { cl_int s0, s1; };
 } cl_int2;
 
+typedef cl_float4 cl_float3;      /* as in cl_platform.h */
+
 typedef union {
 	cl_float s[8] __attribute__((aligned(32)));
 	struct { cl_float s0, s1, s2, s3, s4, s5, s6, s7; };
 } cl_float8;
+
+
+/* ---- the OpenCL objects CL.h declares members of: opaque here, implemented by ref_shim/fake_cl.cpp ---- */
+typedef struct _cl_mem* cl_mem;
+typedef struct _cl_kernel* cl_kernel;
+typedef struct _cl_event* cl_event;
+typedef struct _cl_program* cl_program;
+typedef struct _cl_context* cl_context;
+typedef struct _cl_command_queue* cl_command_queue;
+typedef struct _cl_device_id* cl_device_id;
+typedef struct _cl_platform_id* cl_platform_id;
+typedef cl_ulong cl_mem_flags;
+#define CL_MEM_READ_WRITE (1 << 0)
+#define CL_MEM_WRITE_ONLY (1 << 1)
+#define CL_MEM_READ_ONLY (1 << 2)
+#define CL_MEM_COPY_HOST_PTR (1 << 5)
+#define CL_SUCCESS 0
+#ifdef __cplusplus
+extern "C"
+#endif
+cl_mem clCreateBuffer(cl_context context, cl_mem_flags flags, size_t size, void* host_ptr, cl_int* errcode_ret);
+
+#ifdef __cplusplus
+/* ---- qt/GLWidget.h stand-in: what PathTracer.cpp and Camera.cpp call on their parent widget ---- */
+class CL;
+class PathTracer;
+class GLWidget {
+	public:
+		GLWidget() : mPathTracer(NULL) {}
+		void cameraUpdate();                       /* GLWidget.cpp:78-82: resets the sample count */
+		void createKernelWindow( CL* ) {}
+		void resetRenderTime() {}
+		PathTracer* mPathTracer;
+};
+#endif
 
 #endif

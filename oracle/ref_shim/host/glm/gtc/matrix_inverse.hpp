@@ -1,0 +1,2 @@
+/* stand-in: nothing of glm/gtc/matrix_inverse.hpp is used by the files compiled for the tests */
+#include "../glm.hpp"

@@ -20,6 +20,13 @@
 #include "Cfg.h"
 #include "ModelLoader.h"
 #include "accelstructures/BVH.h"
+#include "Camera.h"
+#include "PathTracer.h"
+
+/* qt/GLWidget.h stand-in (ref_shim/host/cl_types.h); GLWidget.cpp:78-82 */
+void GLWidget::cameraUpdate() {
+	if (mPathTracer) mPathTracer->resetSampleCount();
+}
 
 namespace {
 
@@ -195,6 +202,78 @@ void refhost_bvh_get(void* h, float* nodes, uint32_t* facesV, uint32_t* facesN) 
 	copyOut(L->nodes, nodes);
 	copyOut(L->facesV, facesV);
 	copyOut(L->facesN, facesN);
+}
+
+/* ---- the reference's renderer core: GLWidget's constructor + loadModel + paintGL sequence
+ * (qt/GLWidget.cpp:28-32, 339-387, 504-517) without the widget ---- */
+
+struct Renderer {
+	GLWidget widget;
+	PathTracer* pt;
+	Camera* camera;
+	std::vector<cl_float> image, debug;
+};
+
+void* refhost_renderer_create(const char* configJson, const char* dir, const char* file) {
+	Cfg::get().loadConfigFile(configJson);
+	boost::posix_time::clockOverrideUs() = 0;          /* PathTracer's constructor notes the start time */
+	Renderer* r = new Renderer();
+	r->pt = new PathTracer(&r->widget);
+	r->camera = new Camera(&r->widget);
+	r->widget.mPathTracer = r->pt;
+	r->pt->setCamera(r->camera);
+	/* GLWidget::resizeGL -> setWidthAndHeight( window size ) */
+	r->pt->setWidthAndHeight(Cfg::get().value<cl_uint>(Cfg::WINDOW_WIDTH), Cfg::get().value<cl_uint>(Cfg::WINDOW_HEIGHT));
+
+	ModelLoader* ml = new ModelLoader();
+	ml->loadModel(std::string(dir), std::string(file));
+	ObjParser* op = ml->getObjParser();
+	std::vector<cl_uint> faces = op->getFacesV();
+	std::vector<cl_float> normals = op->getNormals();
+	std::vector<cl_float> vertices = op->getVertices();
+	AccelStructure* accel = new BVH(op->getObjects(), vertices, normals);
+	r->pt->initOpenCLBuffers(vertices, faces, normals, ml, accel);
+	delete ml;
+	delete accel;
+	return r;
+}
+
+/* One PathTracer::generateImage() at time `ms` after start: the seed is ms * 0.001f (PathTracer.cpp:78-82). */
+int refhost_renderer_generate(void* h, long long ms, float* image, float* debug) {
+	Renderer* r = (Renderer*) h;
+	boost::posix_time::clockOverrideUs() = ms * 1000;
+	/* generateImage reads the debug image straight into the caller's storage (GLWidget keeps it sized) */
+	r->debug.resize((size_t) Cfg::get().value<cl_uint>(Cfg::WINDOW_WIDTH) * Cfg::get().value<cl_uint>(Cfg::WINDOW_HEIGHT) * 4);
+	r->image = r->pt->generateImage(&r->debug);
+	if (image && !r->image.empty()) memcpy(image, &r->image[0], r->image.size() * 4);
+	if (debug && !r->debug.empty()) memcpy(debug, &r->debug[0], r->debug.size() * 4);
+	return (int) r->image.size();
+}
+
+/* what: 0 setFocus(a, b); 1 resetSampleCount; 2 updateCameraRot(a, b); 3.. cameraMove{Forward,Backward,Left,Right,Up,Down};
+ * 9 cameraReset; 10 setSpeed(a / 1000) */
+void refhost_renderer_command(void* h, int what, int a, int b) {
+	Renderer* r = (Renderer*) h;
+	switch (what) {
+		case 0: r->pt->setFocus(a, b); break;
+		case 1: r->pt->resetSampleCount(); break;
+		case 2: r->camera->updateCameraRot(a, b); break;
+		case 3: r->camera->cameraMoveForward(); break;
+		case 4: r->camera->cameraMoveBackward(); break;
+		case 5: r->camera->cameraMoveLeft(); break;
+		case 6: r->camera->cameraMoveRight(); break;
+		case 7: r->camera->cameraMoveUp(); break;
+		case 8: r->camera->cameraMoveDown(); break;
+		case 9: r->camera->cameraReset(); break;
+		case 10: r->camera->setSpeed(a / 1000.0f); break;
+	}
+}
+
+void refhost_renderer_free(void* h) {
+	Renderer* r = (Renderer*) h;
+	delete r->pt;
+	delete r->camera;
+	delete r;
 }
 
 void refhost_free(void* h) {

@@ -26,10 +26,10 @@ SYMBOLS = [
     "pbrh_config_get", "pbrh_scene_load", "pbrh_scene_from_arrays", "pbrh_scene_free", "pbrh_scene_get",
     "pbrh_scene_name", "pbrh_flat_build", "pbrh_flat_info", "pbrh_flat_get", "pbrh_flat_free", "pbrh_set_device",
     "pbrh_renderer_create", "pbrh_renderer_destroy", "pbrh_renderer_load_scene", "pbrh_renderer_load_model",
-    "pbrh_renderer_set_deterministic", "pbrh_renderer_set_seed_schedule", "pbrh_renderer_set_tile", "pbrh_renderer_generate_image",
+    "pbrh_renderer_set_deterministic", "pbrh_renderer_set_seed_schedule", "pbrh_renderer_set_frame_time_ms", "pbrh_renderer_set_tile", "pbrh_renderer_generate_image",
     "pbrh_renderer_render_frames", "pbrh_renderer_read_image", "pbrh_renderer_write_image", "pbrh_renderer_finish",
     "pbrh_renderer_reset_sample_count", "pbrh_renderer_set_focus", "pbrh_renderer_set_eye",
-    "pbrh_renderer_rotate_camera", "pbrh_renderer_info", "pbrh_renderer_stats", "pbrh_renderer_flat_get",
+    "pbrh_renderer_rotate_camera", "pbrh_renderer_move_camera", "pbrh_renderer_info", "pbrh_renderer_stats", "pbrh_renderer_flat_get",
     "pbrh_renderer_camera", "pbrh_renderer_trace", "pbrh_renderer_handles",
     "pbrh_write_pfm", "pbrh_write_checkpoint", "pbrh_read_checkpoint",
 ]
@@ -80,6 +80,7 @@ def load_library():
     lib.pbrh_renderer_load_model.argtypes = [vp, C.c_char_p, C.c_char_p]
     lib.pbrh_renderer_set_deterministic.argtypes = [vp, i32]
     lib.pbrh_renderer_set_seed_schedule.argtypes = [vp, u32, u32]
+    lib.pbrh_renderer_set_frame_time_ms.argtypes = [vp, u32]
     lib.pbrh_renderer_set_tile.argtypes = [vp, i32, i32]
     lib.pbrh_renderer_generate_image.argtypes = [vp, f32p, f32p]
     lib.pbrh_renderer_render_frames.argtypes = [vp, i32]
@@ -90,6 +91,7 @@ def load_library():
     lib.pbrh_renderer_set_focus.argtypes = [vp, i32, i32]
     lib.pbrh_renderer_set_eye.argtypes = [vp, C.c_float, C.c_float, C.c_float]
     lib.pbrh_renderer_rotate_camera.argtypes = [vp, i32, i32]
+    lib.pbrh_renderer_move_camera.argtypes = [vp, i32]
     lib.pbrh_renderer_info.argtypes = [vp, vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     lib.pbrh_renderer_stats.argtypes = [vp, vp, i32]
     lib.pbrh_renderer_flat_get.argtypes = [vp, vp, vp, vp]
@@ -282,6 +284,10 @@ class Renderer:
     def set_deterministic(self, enabled=True):
         _ck(self.lib.pbrh_renderer_set_deterministic(self.h, int(enabled)), "setDeterministicSeeds")
 
+    def set_frame_time_ms(self, ms):
+        """Simulated clock: frame k gets the seed of the reference's wall clock at (k + 1) * ms milliseconds."""
+        _ck(self.lib.pbrh_renderer_set_frame_time_ms(self.h, int(ms)), "setFrameTimeMs")
+
     def set_seed_schedule(self, stride, offset):
         _ck(self.lib.pbrh_renderer_set_seed_schedule(self.h, stride, offset), "setSeedSchedule")
 
@@ -324,6 +330,10 @@ class Renderer:
 
     def rotate_camera(self, dx, dy):
         _ck(self.lib.pbrh_renderer_rotate_camera(self.h, dx, dy), "Camera::updateCameraRot")
+
+    def move_camera(self, direction):
+        """0 forward, 1 backward, 2 left, 3 right, 4 up, 5 down, 6 reset (Camera::cameraMove*)."""
+        _ck(self.lib.pbrh_renderer_move_camera(self.h, int(direction)), "Camera::cameraMove")
 
     def info(self):
         a = np.zeros(8, np.int64)

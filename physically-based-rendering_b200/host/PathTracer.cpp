@@ -52,6 +52,7 @@ PathTracer::PathTracer( GLWidget* parent ) {
 	mDeterministicSeeds = false;
 	mSeedStride = 1;
 	mSeedOffset = 0;
+	mFrameTimeMs = 0;
 	mHaveOutput = false;
 	mTimeSinceStart = std::chrono::steady_clock::now();
 
@@ -146,7 +147,7 @@ void PathTracer::renderFrames( cl_uint frames ) {
 	vector<cl_float> seeds( frames ), weights( frames );
 	const cl_float now = this->getTimeSinceStart();
 	for( cl_uint i = 0; i < frames; i++ ) {
-		seeds[i] = mDeterministicSeeds ? this->nextSeed() : now + 0.0333f * (cl_float) i;
+		seeds[i] = ( mDeterministicSeeds || mFrameTimeMs > 0 ) ? this->nextSeed() : now + 0.0333f * (cl_float) i;
 		weights[i] = mSampleCount / (cl_float) ( mSampleCount + 1 );
 		mSampleCount++;
 	}
@@ -191,6 +192,10 @@ cl_float PathTracer::getTimeSinceStart() {
 
 
 cl_float PathTracer::nextSeed() {
+	if( mFrameTimeMs > 0 ) {
+		const long long ms = (long long) mFrameTimeMs * ( (long long) mSampleCount * mSeedStride + mSeedOffset + 1 );
+		return ms * 0.001f;
+	}
 	if( mDeterministicSeeds ) {
 		return 0.0333f * (cl_float) ( mSampleCount * mSeedStride + mSeedOffset + 1 );
 	}

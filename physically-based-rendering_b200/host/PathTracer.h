@@ -72,6 +72,10 @@ class PathTracer {
 		/** Deterministic schedule for sample-sharded multi-GPU runs: frame k of this renderer uses the
 		 *  global index k * stride + offset, i.e. seed = 0.0333f * (k * stride + offset + 1). */
 		void setSeedSchedule( cl_uint stride, cl_uint offset ) { mSeedStride = stride; mSeedOffset = offset; }
+		/** Simulated clock: frame with global index g is "rendered g * ms + ms milliseconds after start", so
+		 *  its seed is what the reference computes from its wall clock, ( ms * ( g + 1 ) ) * 0.001f
+		 *  (reference: PathTracer.cpp:78-82), but reproducible.  0 = off. */
+		void setFrameTimeMs( cl_uint ms ) { mFrameTimeMs = ms; }
 		/** Render `frames` frames back to back without reading anything back. */
 		void renderFrames( cl_uint frames );
 		/** One frame, result read into `target` (W*H*4 floats; pinned memory recommended). */
@@ -129,6 +133,7 @@ class PathTracer {
 		cl_uint mSampleCount;
 		bool mDeterministicSeeds;
 		cl_uint mSeedStride, mSeedOffset;
+		cl_uint mFrameTimeMs;
 		bool mHaveOutput;             // imageOut holds a frame that the next launch must read as imageIn
 
 		cl_float* mTextureOut;        // pinned host copy of the frame, W*H*4

@@ -344,6 +344,11 @@ int pbrh_renderer_set_seed_schedule( pbrh_renderer* r, uint32_t stride, uint32_t
 	return 0;
 }
 
+int pbrh_renderer_set_frame_time_ms( pbrh_renderer* r, uint32_t ms ) {
+	r->widget->getPathTracer()->setFrameTimeMs( ms );
+	return 0;
+}
+
 int pbrh_renderer_set_tile( pbrh_renderer* r, int32_t y0, int32_t y1 ) {
 	NEED_READY
 	r->widget->getPathTracer()->setTileRows( y0, y1 );
@@ -401,6 +406,21 @@ int pbrh_renderer_set_eye( pbrh_renderer* r, float x, float y, float z ) {
 
 int pbrh_renderer_rotate_camera( pbrh_renderer* r, int32_t move_x, int32_t move_y ) {
 	r->widget->getCamera()->updateCameraRot( move_x, move_y );
+	return 0;
+}
+
+int pbrh_renderer_move_camera( pbrh_renderer* r, int32_t direction ) {
+	Camera* c = r->widget->getCamera();
+	switch( direction ) {
+		case 0: c->cameraMoveForward(); break;
+		case 1: c->cameraMoveBackward(); break;
+		case 2: c->cameraMoveLeft(); break;
+		case 3: c->cameraMoveRight(); break;
+		case 4: c->cameraMoveUp(); break;
+		case 5: c->cameraMoveDown(); break;
+		case 6: c->cameraReset(); break;
+		default: return failMsg( "move_camera: direction must be 0..6" );
+	}
 	return 0;
 }
 

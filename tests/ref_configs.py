@@ -58,9 +58,30 @@ def bench_c2_values():
     return bench.reference_program_values()
 
 
+def renderer_program_values():
+    """The configurations of the end-to-end renderer tests (tests/test_gpu_host.py, test_oracle_vs_reference_host.py):
+    the values are whatever the reference's own host code hands to CL::setValues."""
+    from oracle import ref_host as RH
+    import helpers as Hh
+    import test_gpu_host as G
+    import test_oracle_vs_reference_host as T
+    path = Hh.model_path("suzanne.obj")
+    for table, (w, h) in ((G.REF_RENDER, (G.REF_W, G.REF_H)), (T.RENDER_CONFIGS, (88, 56))):
+        for name in sorted(table):
+            kw = dict(table[name])
+            kw.setdefault("max_depth", 4)
+            r = RH.Renderer(path, width=w, height=h, **kw)      # builds the kernel library as a side effect
+            yield r.values
+            r.close()
+
+
 def all_program_values():
     from oracle import ref as R
+    from oracle import ref_host as RH
     for name in CASES:
         yield R.values_from_defines(prepared(name).defines)
+    if RH.available():
+        for v in renderer_program_values():
+            yield v
     if os.environ.get("PBR_REF_SKIP_BENCH") != "1":
         yield bench_c2_values()

@@ -170,3 +170,70 @@ def test_headless_driver(cfg, tmp_path):
     r.render_frames(3)
     assert Hh.images_equal(r.read_image(), img)
     r.close()
+
+
+# ---------------------------------------------------------------------------------------------------------
+# Product versus the reference itself: libpbr_host.so + libpbr_b200.so on the GPU against the reference's own
+# ModelLoader / BVH / PathTracer.cpp / Camera.cpp / kernel source running on the host
+# (oracle/_ref/libref_host.so + oracle/_ref/pt_ref_*.so, built by __graft_entry__.build() where
+# /root/reference exists).
+
+REF_RENDER = {
+    "sa": dict(brdf=1),
+    "schlick_shadow_ms": dict(brdf=0, shadow_rays=1, samples=2),
+    "phong_camera_fov": dict(brdf=1, phong_tess=0.7, eye=(0.3, 0.9, 2.5), center=(0.1, 0.2, 1.0), fov=60.0, antialiasing=0.4),
+}
+REF_W, REF_H = 88, 56
+
+
+def _cam_fields_equal(a, b):
+    return all(np.array_equal(a[f][0, :3], b[f][0, :3]) for f in ("eye", "w", "u", "v")) and \
+        np.array_equal(a["focusPoint"], b["focusPoint"]) and np.array_equal(a["lense"], b["lense"])
+
+
+@pytest.mark.parametrize("name", sorted(REF_RENDER))
+def test_product_equals_reference_renderer(cfg, name):
+    from oracle import oracle as O
+    from oracle import ref_host as RH
+    from pbr_b200 import host
+    kw = dict(REF_RENDER[name], max_depth=4)
+    path = os.path.join(MODELS, "suzanne.obj")
+    if not RH.available():
+        pytest.skip("oracle/_ref/libref_host.so not built")
+    try:
+        ref = RH.Renderer(path, width=REF_W, height=REF_H, nthreads=8, **kw)
+    except FileNotFoundError:
+        pytest.skip("reference kernel for this configuration not prebuilt")
+    cfg.update({"window.width": REF_W, "window.height": REF_H, "render.brdf": kw["brdf"], "render.max_depth": 4,
+                "render.shadow_rays": kw.get("shadow_rays", 0), "render.samples": kw.get("samples", 1),
+                "render.phong_tessellation": kw.get("phong_tess", 0.0), "render.antialiasing": kw.get("antialiasing", 0.7),
+                "camera.perspective.fov": kw.get("fov", 45.0)})
+    for axis, e, c in zip("xyz", kw.get("eye", (0.0, 1.0, 3.0)), kw.get("center", (0.0, 0.0, 1.0))):
+        cfg.update({"camera.eye." + axis: e, "camera.center." + axis: c})
+    r = host.Renderer(0)
+    r.set_frame_time_ms(33)                      # frame k is "rendered" 33 (k + 1) ms after start, on both sides
+    r.load_model(MODELS + "/", "suzanne.obj")
+    try:
+        for k in range(3):
+            got, gdbg = r.generate_image(debug=True)
+            want, wdbg = ref.generate_image(33 * (k + 1))
+            assert Hh.images_equal(got, want) and Hh.images_equal(gdbg, wdbg), "frame %d" % k
+        cam, px = r.camera()
+        assert px == ref.kernel_arg(2, np.float32)[0]
+        assert _cam_fields_equal(cam, ref.kernel_arg(3).view(O.CAMERA_DTYPE))
+        # Camera.cpp: rotate, move, focus -- every change resets the accumulation on both sides
+        for what, args, ours in [(2, (37, -12), lambda: r.rotate_camera(37, -12)), (3, (), lambda: r.move_camera(0)),
+                                 (5, (), lambda: r.move_camera(2)), (7, (), lambda: r.move_camera(4)),
+                                 (0, (40, 25), lambda: r.set_focus(40, 25)), (4, (), lambda: r.move_camera(1)),
+                                 (9, (), lambda: r.move_camera(6))]:
+            ref.command(what, *args)
+            ours()
+            for k in range(2):
+                got, _ = r.generate_image()
+                want, _ = ref.generate_image(33 * (k + 1))
+                assert Hh.images_equal(got, want), "after camera command %d, frame %d" % (what, k)
+            cam, _ = r.camera()
+            assert _cam_fields_equal(cam, ref.kernel_arg(3).view(O.CAMERA_DTYPE)), "camera after command %d" % what
+    finally:
+        r.close()
+        ref.close()

@@ -104,3 +104,62 @@ def test_generated_scenes_parse_and_bvh(cfg, tmp_path, gen, kw):
     _same_scene(loader().to_dict(), ref_scene)
     _same_flat(_product_flat(cfg, loader, kw), ref_flat)
     assert ref_flat["info"]["faces"] == scene["facesV"].size // 3 > 1000
+
+
+# ---------------------------------------------------------------------------------------------------------
+# The reference's renderer core end to end: ModelLoader -> BVH -> PathTracer.cpp (buffers, kernel arguments,
+# camera, per-frame seed and weight) -> the reference kernel, all of it the reference's own code.
+
+RENDER_CONFIGS = {
+    "sa": dict(brdf=1),
+    "schlick_shadow_ms": dict(brdf=0, shadow_rays=1, samples=2),
+    "phong_camera_fov": dict(brdf=1, phong_tess=0.7, eye=(0.3, 0.9, 2.5), center=(0.1, 0.2, 1.0), fov=60.0, antialiasing=0.4),
+    "sa_bvh1": dict(brdf=1, max_faces=1, skip_ahead_compare=0.5, max_depth=5, max_added_depth=2),
+}
+
+
+def _prepared_for(path, W, H, kw):
+    import helpers as Hh
+    kw = dict(kw)
+    bvh_kw = {k: kw.pop(k) for k in ("max_faces", "skip_ahead", "skip_ahead_compare", "sah_faces_limit") if k in kw}
+    pt = kw.pop("phong_tess", 0.0)
+    kw.setdefault("max_depth", 4)
+    scene = O.load_obj(path, kw.get("shadow_rays", 0))
+    return Hh.Prepared(scene, W, H, phong_tessellation=pt, bvh_kwargs=bvh_kw, **kw)
+
+
+@pytest.mark.parametrize("name", sorted(RENDER_CONFIGS))
+def test_reference_renderer_equals_oracle_pipeline(name):
+    """PathTracer.cpp's host arithmetic (camera basis, pixel size with its binary64 tangent, material / light
+    packing, SKY_LIGHT / NUM_LIGHTS / BVH_NUM_NODES texts, seed and mixing weight per frame) against the
+    restatement in oracle/scene.py + tests/helpers.py, through the image it produces."""
+    import helpers as Hh
+    from oracle import scene as S
+    kw = dict(RENDER_CONFIGS[name])
+    kw.setdefault("max_depth", 4)
+    path = os.path.join(MODELS, "suzanne.obj")
+    W, H = 88, 56
+    r = RH.Renderer(path, width=W, height=H, **kw)
+    try:
+        p = _prepared_for(path, W, H, kw)
+        assert int(r.values["BVH_NUM_NODES"]) == p.nodes.shape[0] and int(r.values["NUM_LIGHTS"]) == p.num_lights
+        img_o = np.zeros((H, W, 4), np.float32)
+        for k, ms in enumerate((33, 67, 100)):
+            img_r, dbg_r = r.generate_image(ms)
+            seed = np.float32(ms) * np.float32(0.001)
+            img_o, dbg_o, _ = O.path_tracing(p.defines, seed, S.pixel_weight(k), p.px_dim, p.camera, p.nodes, p.facesV,
+                                             p.facesN, p.vertices4, p.normals4, p.materials, p.lights, img_o, nthreads=4)
+            assert Hh.images_equal(img_r, img_o) and Hh.images_equal(dbg_r, dbg_o), "frame %d" % k
+        # the kernel arguments themselves
+        assert r.kernel_arg(2, np.float32)[0] == p.px_dim
+        cam = r.kernel_arg(3).view(O.CAMERA_DTYPE)
+        for f in ("eye", "w", "u", "v"):
+            assert np.array_equal(cam[f][0, :3], p.camera[f][0, :3]), f
+        assert np.array_equal(cam["focusPoint"], p.camera["focusPoint"]) and np.array_equal(cam["lense"], p.camera["lense"])
+        assert np.array_equal(r.kernel_arg(4, np.float32).view(np.uint32), p.nodes.ravel().view(np.uint32))
+        assert np.array_equal(r.kernel_arg(5, np.uint32), p.facesV.ravel())
+        assert np.array_equal(r.kernel_arg(9, np.float32), np.asarray(p.materials, np.float32).ravel())
+        if p.num_lights:
+            assert np.array_equal(r.kernel_arg(10, np.float32), p.lights.ravel())
+    finally:
+        r.close()

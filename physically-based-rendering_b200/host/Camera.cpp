@@ -11,9 +11,15 @@ Camera::Camera( GLWidget* parent ) {
 
 
 /* One step of `speed` along the view axes (reference: Camera.cpp:20-75).  rot.x turns around the
- * vertical axis, rot.y tilts; the forward vector is (sin x cos y, -sin y, -cos x cos y). */
+ * vertical axis, rot.y tilts; the forward vector is (sin x cos y, -sin y, -cos x cos y).
+ *
+ * The reference calls unqualified sin( float ) / cos( float ) / fabs() with only <cmath> included: with the
+ * toolchain it was written for these are the C functions, i.e. the expressions are evaluated in binary64 and
+ * rounded when stored.  Spelled out here with explicit doubles, so that the result does not depend on which
+ * overloads a standard library happens to put into the global namespace (checked against the reference's own
+ * Camera.cpp in tests/test_gpu_host.py::test_product_equals_reference_renderer). */
 void Camera::cameraMoveBackward() {
-	const float rx = MathHelp::degToRad( mCamera.rot.x ), ry = MathHelp::degToRad( mCamera.rot.y );
+	const double rx = MathHelp::degToRad( mCamera.rot.x ), ry = MathHelp::degToRad( mCamera.rot.y );
 	mCamera.eye.x -= sin( rx ) * cos( ry ) * mCameraSpeed;
 	mCamera.eye.y += sin( ry ) * mCameraSpeed;
 	mCamera.eye.z += cos( rx ) * cos( ry ) * mCameraSpeed;
@@ -28,7 +34,7 @@ void Camera::cameraMoveDown() {
 
 
 void Camera::cameraMoveForward() {
-	const float rx = MathHelp::degToRad( mCamera.rot.x ), ry = MathHelp::degToRad( mCamera.rot.y );
+	const double rx = MathHelp::degToRad( mCamera.rot.x ), ry = MathHelp::degToRad( mCamera.rot.y );
 	mCamera.eye.x += sin( rx ) * cos( ry ) * mCameraSpeed;
 	mCamera.eye.y -= sin( ry ) * mCameraSpeed;
 	mCamera.eye.z -= cos( rx ) * cos( ry ) * mCameraSpeed;
@@ -37,7 +43,7 @@ void Camera::cameraMoveForward() {
 
 
 void Camera::cameraMoveLeft() {
-	const float rx = MathHelp::degToRad( mCamera.rot.x );
+	const double rx = MathHelp::degToRad( mCamera.rot.x );
 	mCamera.eye.x -= cos( rx ) * mCameraSpeed;
 	mCamera.eye.z -= sin( rx ) * mCameraSpeed;
 	this->updateParent();
@@ -45,7 +51,7 @@ void Camera::cameraMoveLeft() {
 
 
 void Camera::cameraMoveRight() {
-	const float rx = MathHelp::degToRad( mCamera.rot.x );
+	const double rx = MathHelp::degToRad( mCamera.rot.x );
 	mCamera.eye.x += cos( rx ) * mCameraSpeed;
 	mCamera.eye.z += sin( rx ) * mCameraSpeed;
 	this->updateParent();
@@ -121,7 +127,7 @@ void Camera::updateCameraRot( int moveX, int moveY ) {
 	if( mCamera.rot.y > 90.0f ) { mCamera.rot.y = 90.0f; }
 	else if( mCamera.rot.y < -90.0f ) { mCamera.rot.y = -90.0f; }
 
-	const float rx = MathHelp::degToRad( mCamera.rot.x ), ry = MathHelp::degToRad( mCamera.rot.y );
+	const double rx = MathHelp::degToRad( mCamera.rot.x ), ry = MathHelp::degToRad( mCamera.rot.y );
 
 	mCamera.center.x = sin( rx ) - fabs( sin( ry ) ) * sin( rx );
 	mCamera.center.y = sin( ry );

@@ -229,7 +229,7 @@ def test_product_equals_reference_renderer(cfg, name):
             ref.command(what, *args)
             ours()
             for k in range(2):
-                got, _ = r.generate_image()
+                got = r.generate_image()
                 want, _ = ref.generate_image(33 * (k + 1))
                 assert Hh.images_equal(got, want), "after camera command %d, frame %d" % (what, k)
             cam, _ = r.camera()

@@ -64,6 +64,9 @@ def parse_args():
     ap.add_argument("--spp", type=int)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--verify", action="store_true",
+                    help="N > 1, spp sharding: rank 0 re-renders every rank's frames alone and compares the mean with "
+                         "the combined image of the pipelined step")
     return ap.parse_args()
 
 
@@ -217,15 +220,34 @@ def run_ours(args):
         return views[ptr]
 
     display = torch.empty((H, W, 4), dtype=torch.float32, device=dev_t) if world > 1 else None
+    # N > 1: the cross-rank combine of frame k (a copy + one collective) runs on its own stream while frame k+1
+    # is traced.  Frame k+1 only READS the image frame k wrote; frame k+2 overwrites it, so it waits for the
+    # combine of frame k (two events, by parity).
+    render_stream = torch.cuda.current_stream()
+    display_stream = torch.cuda.Stream() if world > 1 else None
+    combined = [None, None]
+    frame_no = [0]
 
     def frame():
+        j = frame_no[0]
+        frame_no[0] += 1
+        if world > 1 and combined[j & 1] is not None:
+            render_stream.wait_event(combined[j & 1])
         r.render_frames(1)
         if world > 1:
             img = image_tensor()
+            rendered = torch.cuda.Event()
+            rendered.record(render_stream)
+            with torch.cuda.stream(display_stream):
+                display_stream.wait_event(rendered)
+                if tiles:
+                    multigpu.combine_tiles(img, rank, world)
+                else:
+                    multigpu.combine_spp(img, world, out=display)
+                combined[j & 1] = torch.cuda.Event()
+                combined[j & 1].record(display_stream)
             if tiles:
-                multigpu.combine_tiles(img, rank, world)
-            else:
-                multigpu.combine_spp(img, world, out=display)
+                render_stream.wait_event(combined[j & 1])      # the gathered rows are the next frame's input
 
     def step_resident():
         r.reset_sample_count()
@@ -234,6 +256,7 @@ def run_ours(args):
         else:
             for _ in range(SPP):
                 frame()                  # every frame is combined across ranks (progressive display)
+            render_stream.wait_stream(display_stream)
 
     pinned = torch.empty((H, W, 4), dtype=torch.float32).pin_memory()
     pinned_np = pinned.numpy()
@@ -245,7 +268,12 @@ def run_ours(args):
                 r.generate_image(out=pinned_np)              # launch + read-back into pinned memory
             else:
                 frame()
-                pinned.copy_(display if not tiles else image_tensor(), non_blocking=False)
+                if rank == 0:                                # one consumer of the displayed frame: rank 0's host
+                    with torch.cuda.stream(display_stream):
+                        pinned.copy_(display if not tiles else image_tensor(), non_blocking=True)
+                    display_stream.synchronize()
+        if world > 1:
+            render_stream.wait_stream(display_stream)
 
     def sync_all():
         if world > 1:
@@ -328,10 +356,36 @@ def run_ours(args):
         e2e = {
             "value": round((e_stats[0] + e_stats[1]) / e2e_s / 1e6, 2), "unit": "Mrays/s",
             "h2d_bytes_per_step": SPP * (4 + 4 + 80),          # seed, pixelWeight, camera per frame
-            "d2h_bytes_per_step": SPP * W * H * 16,            # accumulated frame per frame
+            "d2h_bytes_per_step": SPP * W * H * 16,            # accumulated frame per frame (N > 1: rank 0 reads it)
             "ms_per_step": round(e2e_s * 1e3 / args.steps, 3),
-            "api": "PathTracer::generateImage (libpbr_host.so), pinned host image",
+            "api": "PathTracer::generateImage (libpbr_host.so), pinned host image" if world == 1 else
+                   "PathTracer::renderFrames(1) per rank + combine on a side stream; rank 0 reads every combined "
+                   "frame into pinned host memory",
         }
+
+    # ---- optional: is the pipelined multi-GPU image the right one? ---------------------------------
+    verify = None
+    if args.verify and world > 1 and not tiles:
+        step_resident()
+        sync_all()
+        if rank == 0:
+            shown = display.clone()
+            acc = torch.zeros_like(shown, dtype=torch.float64)
+            for rr in range(world):
+                r.set_seed_schedule(world, rr)
+                r.reset_sample_count()
+                r.render_frames(SPP)
+                torch.cuda.synchronize()
+                acc += image_tensor().double()
+            r.set_seed_schedule(world, rank)
+            want = (acc / world)[..., :3]
+            got = shown[..., :3].double()
+            ok = torch.isfinite(want) & torch.isfinite(got)
+            diff = (want - got).abs()[ok]
+            verify = {"max_abs_diff": float(diff.max()), "mean": float(want[ok].mean()),
+                      "pixels_compared": int(ok.all(dim=2).sum()), "what": "combined image of one pipelined step vs "
+                      "the mean of all ranks' accumulations re-rendered on rank 0"}
+        sync_all()
 
     # ---- CPU baseline (rank 0, N = 1 only) ---------------------------------------------------------
     cpu_baseline = None
@@ -353,7 +407,7 @@ def run_ours(args):
                     (info["emitted_nodes"] * 32 + info["faces"] * 48) / 1e6, W * H * 104 / 1e6, W * H * 48 / 1e6),
             },
             "samples_per_s": round(samples_per_s), "rays_per_step": round(rays_all / args.steps),
-            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches_all),
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches_all), "verify": verify,
             "roofline": roofline, "cpu_baseline": cpu_baseline,
         }
         print(json.dumps(line), flush=True)

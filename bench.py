@@ -261,11 +261,18 @@ def run_ours(args):
     pinned = torch.empty((H, W, 4), dtype=torch.float32).pin_memory()
     pinned_np = pinned.numpy()
 
-    def step_e2e():
-        r.reset_sample_count()
-        for _ in range(SPP):
+    def step_e2e(last=False):
+        if world > 1:
+            r.reset_sample_count()
+        for i in range(SPP):
             if world == 1:
-                r.generate_image(out=pinned_np)              # launch + read-back into pinned memory
+                # one generateImage() per frame, every frame read back into pinned memory; with render-ahead the
+                # next frame is traced while this one is copied.  The accumulation simply continues from step to
+                # step (no reset: a reset would discard the frame traced ahead), and the very last call of the
+                # run switches render-ahead off first, so no frame is traced that is not delivered.
+                if last and i == SPP - 1:
+                    r.set_render_ahead(False)
+                r.generate_image(out=pinned_np)
             else:
                 frame()
                 if rank == 0:                                # one consumer of the displayed frame: rank 0's host
@@ -343,13 +350,17 @@ def run_ours(args):
     # ---- end to end through the host API ---------------------------------------------------------
     e2e = None
     if not args.no_e2e:
-        for _ in range(max(1, args.warmup // 2)):
-            step_e2e()
+        if world == 1:
+            r.reset_sample_count()
+        for i in range(max(1, args.warmup // 2)):
+            step_e2e(last=True)
         sync_all()
         dev.stats(reset=True)
+        if world == 1:
+            r.set_render_ahead(True)
         t0 = time.perf_counter()
-        for _ in range(args.steps):
-            step_e2e()
+        for i in range(args.steps):
+            step_e2e(last=(i == args.steps - 1))
         torch.cuda.synchronize()
         e2e_s = max_over_ranks(time.perf_counter() - t0)
         e_stats = sum_over_ranks(dev.stats(reset=True).astype(np.float64))
@@ -358,7 +369,8 @@ def run_ours(args):
             "h2d_bytes_per_step": SPP * (4 + 4 + 80),          # seed, pixelWeight, camera per frame
             "d2h_bytes_per_step": SPP * W * H * 16,            # accumulated frame per frame (N > 1: rank 0 reads it)
             "ms_per_step": round(e2e_s * 1e3 / args.steps, 3),
-            "api": "PathTracer::generateImage (libpbr_host.so), pinned host image" if world == 1 else
+            "api": "PathTracer::generateImage (libpbr_host.so) per frame, every frame into a pinned host image, "
+                   "setRenderAhead(true): the next frame is traced while this one is copied" if world == 1 else
                    "PathTracer::renderFrames(1) per rank + combine on a side stream; rank 0 reads every combined "
                    "frame into pinned host memory",
         }

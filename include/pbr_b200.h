@@ -72,6 +72,11 @@ int pbr_image_create(pbr_ctx* ctx, size_t width, size_t height, const float* hos
 int pbr_image_write(pbr_ctx* ctx, pbr_mem image, size_t width, size_t height, const float* host);
 /* CL::readImageOutput = clEnqueueReadImage, blocking (CL.cpp:581-594). */
 int pbr_image_read(pbr_ctx* ctx, pbr_mem image, size_t width, size_t height, float* host);
+/* Additive: the same read-back split in two, so that work enqueued between the two calls (the next frame)
+ * overlaps the copy.  _begin orders the copy after everything enqueued so far and runs it on a stream of
+ * its own (host should be pinned: pbr_host_alloc); _end blocks until it has landed.  One read in flight. */
+int pbr_image_read_begin(pbr_ctx* ctx, pbr_mem image, size_t width, size_t height, float* host);
+int pbr_image_read_end(pbr_ctx* ctx);
 /* Additive: device-side copy src -> dst.  Replaces the per-frame host round trip
  * readImageOutput(imageOut) ; updateImageReadOnly(imageIn) of PathTracer::generateImage
  * (PathTracer.cpp:61-66) when the host copy has not been modified in between. */

@@ -76,6 +76,8 @@ int pbrh_renderer_set_seed_schedule(pbrh_renderer* r, uint32_t stride, uint32_t 
 /* simulated clock: frame with global index g gets the seed the reference derives from its wall clock at
  * t = ms * (g + 1) milliseconds, (ms * (g + 1)) * 0.001f (PathTracer.cpp:78-82); 0 = off */
 int pbrh_renderer_set_frame_time_ms(pbrh_renderer* r, uint32_t ms);
+/* generate_image starts tracing the next frame before it waits for the copy of this one (PathTracer::setRenderAhead) */
+int pbrh_renderer_set_render_ahead(pbrh_renderer* r, int32_t enabled);
 int pbrh_renderer_set_tile(pbrh_renderer* r, int32_t y0, int32_t y1);
 /* PathTracer::generateImage: one frame, accumulated image into out[W*H*4]; debug may be NULL */
 int pbrh_renderer_generate_image(pbrh_renderer* r, float* out, float* debug);

@@ -21,7 +21,7 @@ SYMBOLS = [
     "pbr_free_buffers", "pbr_host_alloc", "pbr_host_free",
     "pbr_set_define", "pbr_program_load", "pbr_kernel_get", "pbr_kernel_set_arg", "pbr_kernel_launch",
     "pbr_finish", "pbr_kernel_time_ms",
-    "pbr_set_tile", "pbr_set_pipeline", "pbr_set_tuning", "pbr_kernel_launch_batch", "pbr_set_debug_image", "pbr_stats",
+    "pbr_image_read_begin", "pbr_image_read_end", "pbr_set_tile", "pbr_set_pipeline", "pbr_set_tuning", "pbr_kernel_launch_batch", "pbr_set_debug_image", "pbr_stats",
     "pbr_trace", "pbr_trace_device", "pbr_pinned_math_eval",
     "pbr_set_stream", "pbr_profile_enable", "pbr_profile_read",
 ]
@@ -84,6 +84,8 @@ def load_library():
         "pbr_finish": [vp],
         "pbr_kernel_time_ms": [vp, u64, C.POINTER(C.c_double)],
         "pbr_set_tile": [vp, i32, i32],
+        "pbr_image_read_begin": [vp, u64, sz, sz, vp],
+        "pbr_image_read_end": [vp],
         "pbr_set_pipeline": [vp, i32],
         "pbr_set_tuning": [vp, C.c_char_p, i32],
         "pbr_kernel_launch_batch": [vp, u64, i32, vp, vp],

@@ -44,6 +44,9 @@ struct pbr_ctx {
 	int smCount = 0;
 	cudaStream_t stream = nullptr;
 	cudaStream_t ownStream = nullptr;
+	cudaStream_t copyStream = nullptr;         /* pbr_image_read_begin / _end */
+	cudaEvent_t evCopy = nullptr;
+	bool copyInFlight = false;
 	cudaEvent_t evStart = nullptr, evStop = nullptr;
 
 	/* per-kernel profiling */
@@ -657,6 +660,8 @@ int pbr_destroy(pbr_ctx* ctx) {
 	cudaEventDestroy(ctx->evStart); cudaEventDestroy(ctx->evStop);
 	for (const pbr_ctx::Timed& t : ctx->timedInFlight) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
 	for (cudaEvent_t e : ctx->eventPool) cudaEventDestroy(e);
+	if (ctx->copyStream) { cudaStreamSynchronize(ctx->copyStream); cudaStreamDestroy(ctx->copyStream); }
+	if (ctx->evCopy) cudaEventDestroy(ctx->evCopy);
 	cudaStreamDestroy(ctx->ownStream);
 	delete ctx;
 	return PBR_OK;
@@ -756,6 +761,33 @@ int pbr_image_read(pbr_ctx* ctx, pbr_mem image, size_t width, size_t height, flo
 	CK(cudaMemcpyAsync(host, m->dptr, m->bytes, cudaMemcpyDeviceToHost, ctx->stream));
 	CK(cudaStreamSynchronize(ctx->stream));
 	return checkPersistAbort(ctx);
+}
+
+int pbr_image_read_begin(pbr_ctx* ctx, pbr_mem image, size_t width, size_t height, float* host) {
+	if (!ctx) return PBR_ERR_INVALID;
+	Mem* m = getMem(ctx, image);
+	if (!m || !m->image || width != m->width || height != m->height || !host)
+		return fail(ctx, PBR_ERR_INVALID, "pbr_image_read_begin: bad image or size");
+	if (ctx->copyInFlight) return fail(ctx, PBR_ERR_NOT_READY, "pbr_image_read_begin: a read is already in flight");
+	CK(cudaSetDevice(ctx->device));
+	if (!ctx->copyStream) {
+		CK(cudaStreamCreateWithFlags(&ctx->copyStream, cudaStreamNonBlocking));
+		CK(cudaEventCreateWithFlags(&ctx->evCopy, cudaEventDisableTiming));
+	}
+	CK(cudaEventRecord(ctx->evCopy, ctx->stream));
+	CK(cudaStreamWaitEvent(ctx->copyStream, ctx->evCopy, 0));
+	CK(cudaMemcpyAsync(host, m->dptr, m->bytes, cudaMemcpyDeviceToHost, ctx->copyStream));
+	ctx->copyInFlight = true;
+	return PBR_OK;
+}
+
+int pbr_image_read_end(pbr_ctx* ctx) {
+	if (!ctx) return PBR_ERR_INVALID;
+	if (!ctx->copyInFlight) return PBR_OK;
+	CK(cudaSetDevice(ctx->device));
+	ctx->copyInFlight = false;
+	CK(cudaStreamSynchronize(ctx->copyStream));
+	return PBR_OK;
 }
 
 int pbr_image_copy(pbr_ctx* ctx, pbr_mem dst, pbr_mem src) {

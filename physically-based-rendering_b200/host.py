@@ -26,7 +26,7 @@ SYMBOLS = [
     "pbrh_config_get", "pbrh_scene_load", "pbrh_scene_from_arrays", "pbrh_scene_free", "pbrh_scene_get",
     "pbrh_scene_name", "pbrh_flat_build", "pbrh_flat_info", "pbrh_flat_get", "pbrh_flat_free", "pbrh_set_device",
     "pbrh_renderer_create", "pbrh_renderer_destroy", "pbrh_renderer_load_scene", "pbrh_renderer_load_model",
-    "pbrh_renderer_set_deterministic", "pbrh_renderer_set_seed_schedule", "pbrh_renderer_set_frame_time_ms", "pbrh_renderer_set_tile", "pbrh_renderer_generate_image",
+    "pbrh_renderer_set_deterministic", "pbrh_renderer_set_seed_schedule", "pbrh_renderer_set_frame_time_ms", "pbrh_renderer_set_render_ahead", "pbrh_renderer_set_tile", "pbrh_renderer_generate_image",
     "pbrh_renderer_render_frames", "pbrh_renderer_read_image", "pbrh_renderer_write_image", "pbrh_renderer_finish",
     "pbrh_renderer_reset_sample_count", "pbrh_renderer_set_focus", "pbrh_renderer_set_eye",
     "pbrh_renderer_rotate_camera", "pbrh_renderer_move_camera", "pbrh_renderer_info", "pbrh_renderer_stats", "pbrh_renderer_flat_get",
@@ -81,6 +81,7 @@ def load_library():
     lib.pbrh_renderer_set_deterministic.argtypes = [vp, i32]
     lib.pbrh_renderer_set_seed_schedule.argtypes = [vp, u32, u32]
     lib.pbrh_renderer_set_frame_time_ms.argtypes = [vp, u32]
+    lib.pbrh_renderer_set_render_ahead.argtypes = [vp, i32]
     lib.pbrh_renderer_set_tile.argtypes = [vp, i32, i32]
     lib.pbrh_renderer_generate_image.argtypes = [vp, f32p, f32p]
     lib.pbrh_renderer_render_frames.argtypes = [vp, i32]
@@ -287,6 +288,10 @@ class Renderer:
     def set_frame_time_ms(self, ms):
         """Simulated clock: frame k gets the seed of the reference's wall clock at (k + 1) * ms milliseconds."""
         _ck(self.lib.pbrh_renderer_set_frame_time_ms(self.h, int(ms)), "setFrameTimeMs")
+
+    def set_render_ahead(self, enabled=True):
+        """generate_image() traces the next frame while this one is copied to the host (PathTracer::setRenderAhead)."""
+        _ck(self.lib.pbrh_renderer_set_render_ahead(self.h, int(enabled)), "setRenderAhead")
 
     def set_seed_schedule(self, stride, offset):
         _ck(self.lib.pbrh_renderer_set_seed_schedule(self.h, stride, offset), "setSeedSchedule")

@@ -205,6 +205,17 @@ void CL::readImageOutput( cl_mem image, size_t width, size_t height, cl_float* o
 }
 
 
+/** Additive: readImageOutput in two halves; what is enqueued in between overlaps the copy. */
+void CL::readImageOutputBegin( cl_mem image, size_t width, size_t height, cl_float* outputTarget ) {
+	this->checkError( pbr_image_read_begin( mContext, image, width, height, outputTarget ), "clEnqueueReadImage" );
+}
+
+
+void CL::readImageOutputEnd() {
+	this->checkError( pbr_image_read_end( mContext ), "clWaitForEvents" );
+}
+
+
 /** Reference: CL.cpp:604-607. */
 void CL::setKernelArg( cl_kernel kernel, cl_uint index, size_t size, void* data ) {
 	this->checkError( pbr_kernel_set_arg( mContext, kernel, index, size, data ), "clSetKernelArg" );

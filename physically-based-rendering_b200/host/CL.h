@@ -56,6 +56,8 @@ class CL {
 
 		/** Additive (see include/pbr_b200.h): device-side image copy, tiles, counters, pinned memory. */
 		void copyImage( cl_mem dst, cl_mem src );
+		void readImageOutputBegin( cl_mem image, size_t width, size_t height, cl_float* outputTarget );
+		void readImageOutputEnd();
 		void executeBatch( cl_kernel kernel, cl_uint frames, const cl_float* seeds, const cl_float* pixelWeights );
 		void setTile( int y0, int y1 );
 		void setDebugImage( bool enabled );

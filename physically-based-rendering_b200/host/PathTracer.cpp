@@ -53,6 +53,9 @@ PathTracer::PathTracer( GLWidget* parent ) {
 	mSeedStride = 1;
 	mSeedOffset = 0;
 	mFrameTimeMs = 0;
+	mRenderAhead = false;
+	mAheadLaunched = false;
+	mSampleCountBeforeAhead = 0;
 	mHaveOutput = false;
 	mTimeSinceStart = std::chrono::steady_clock::now();
 
@@ -124,9 +127,49 @@ vector<cl_float> PathTracer::generateImage( vector<cl_float>* textureDebug ) {
 
 
 void PathTracer::generateImageInto( cl_float* target, cl_float* targetDebug ) {
-	mCL->setDebugImage( targetDebug != NULL );
-	this->launchFrame();
-	this->readImage( target, targetDebug );
+	if( targetDebug != NULL ) {
+		this->dropFrameAhead();          /* a frame traced ahead has no debug image */
+	}
+	if( !mAheadLaunched ) {
+		mCL->setDebugImage( targetDebug != NULL );
+		this->launchFrame();
+	}
+	mAheadLaunched = false;
+
+	if( mRenderAhead && targetDebug == NULL ) {
+		/* copy this frame out on the copy stream while the next one is traced: the next frame only reads
+		 * the image that is being copied (it is its imageIn) and writes the other one */
+		mCL->readImageOutputBegin( mBufTextureOut, mWidth, mHeight, target );
+		mSampleCountBeforeAhead = mSampleCount;
+		mCL->setDebugImage( false );
+		this->launchFrame();
+		mAheadLaunched = true;
+		mCL->readImageOutputEnd();
+		return;
+	}
+	mCL->readImageOutput( mBufTextureOut, mWidth, mHeight, target );
+	if( targetDebug != NULL ) {
+		mCL->readImageOutput( mBufTextureDebug, mWidth, mHeight, targetDebug );
+	}
+}
+
+
+void PathTracer::setRenderAhead( bool enabled ) {
+	mRenderAhead = enabled;          /* a frame already traced ahead stays valid: the next call returns it */
+}
+
+
+/**
+ * The frame traced ahead is not wanted after all: undo launchFrame's bookkeeping, so that the image returned
+ * last is the current output again.  (The device work is simply wasted; stream order keeps it harmless.)
+ */
+void PathTracer::dropFrameAhead() {
+	if( !mAheadLaunched ) { return; }
+	mAheadLaunched = false;
+	std::swap( mBufTextureIn, mBufTextureOut );
+	mCL->setKernelArg( mKernelPathTracing, 11, sizeof( cl_mem ), &mBufTextureIn );
+	mCL->setKernelArg( mKernelPathTracing, 12, sizeof( cl_mem ), &mBufTextureOut );
+	mSampleCount = mSampleCountBeforeAhead;
 }
 
 
@@ -136,6 +179,10 @@ void PathTracer::generateImageInto( cl_float* target, cl_float* targetDebug ) {
  * deterministic schedule, instead of by the time the frames happen to take).
  */
 void PathTracer::renderFrames( cl_uint frames ) {
+	if( mAheadLaunched && frames > 0 ) {
+		mAheadLaunched = false;          /* the frame traced ahead is the first of these */
+		frames--;
+	}
 	if( frames == 0 ) { return; }
 	mCL->setDebugImage( false );
 	this->updateEyeBuffer();
@@ -158,6 +205,7 @@ void PathTracer::renderFrames( cl_uint frames ) {
 
 
 void PathTracer::readImage( cl_float* target, cl_float* targetDebug ) {
+	this->dropFrameAhead();
 	mCL->readImageOutput( mBufTextureOut, mWidth, mHeight, target );
 	if( targetDebug != NULL ) {
 		mCL->readImageOutput( mBufTextureDebug, mWidth, mHeight, targetDebug );
@@ -166,6 +214,7 @@ void PathTracer::readImage( cl_float* target, cl_float* targetDebug ) {
 
 
 void PathTracer::writeImage( const cl_float* source, cl_uint sampleCount ) {
+	this->dropFrameAhead();
 	mCL->updateImageReadOnly( mBufTextureOut, mWidth, mHeight, (cl_float*) source );
 	mSampleCount = sampleCount;
 	mHaveOutput = true;
@@ -173,6 +222,7 @@ void PathTracer::writeImage( const cl_float* source, cl_uint sampleCount ) {
 
 
 void PathTracer::setTileRows( int y0, int y1 ) {
+	this->dropFrameAhead();
 	mCL->setTile( y0, y1 );
 }
 
@@ -291,6 +341,7 @@ void PathTracer::initOpenCLBuffers(
 	this->initKernelArgs();
 	mSampleCount = 0;
 	mHaveOutput = false;
+	mAheadLaunched = false;
 }
 
 
@@ -544,6 +595,7 @@ void PathTracer::moveSun( const int key ) {
 
 /** Reset the sample counter: the next frame ignores the history (reference: PathTracer.cpp:576-578). */
 void PathTracer::resetSampleCount() {
+	this->dropFrameAhead();
 	mSampleCount = 0;
 }
 

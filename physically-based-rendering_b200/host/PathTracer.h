@@ -68,14 +68,14 @@ class PathTracer {
 
 		/* ---- additive ---- */
 		/** Use seed_k = 0.0333f * (k + 1) for frame k instead of wall-clock seconds. */
-		void setDeterministicSeeds( bool enabled ) { mDeterministicSeeds = enabled; }
+		void setDeterministicSeeds( bool enabled ) { this->dropFrameAhead(); mDeterministicSeeds = enabled; }
 		/** Deterministic schedule for sample-sharded multi-GPU runs: frame k of this renderer uses the
 		 *  global index k * stride + offset, i.e. seed = 0.0333f * (k * stride + offset + 1). */
-		void setSeedSchedule( cl_uint stride, cl_uint offset ) { mSeedStride = stride; mSeedOffset = offset; }
+		void setSeedSchedule( cl_uint stride, cl_uint offset ) { this->dropFrameAhead(); mSeedStride = stride; mSeedOffset = offset; }
 		/** Simulated clock: frame with global index g is "rendered g * ms + ms milliseconds after start", so
 		 *  its seed is what the reference computes from its wall clock, ( ms * ( g + 1 ) ) * 0.001f
 		 *  (reference: PathTracer.cpp:78-82), but reproducible.  0 = off. */
-		void setFrameTimeMs( cl_uint ms ) { mFrameTimeMs = ms; }
+		void setFrameTimeMs( cl_uint ms ) { this->dropFrameAhead(); mFrameTimeMs = ms; }
 		/** Render `frames` frames back to back without reading anything back. */
 		void renderFrames( cl_uint frames );
 		/** One frame, result read into `target` (W*H*4 floats; pinned memory recommended). */
@@ -85,7 +85,12 @@ class PathTracer {
 		/** Replace the accumulated frame on the device (resume from a checkpoint). */
 		void writeImage( const cl_float* source, cl_uint sampleCount );
 		void setTileRows( int y0, int y1 );
-		cl_uint getSampleCount() const { return mSampleCount; }
+		cl_uint getSampleCount() const { return mAheadLaunched ? mSampleCountBeforeAhead : mSampleCount; }
+		/** Render ahead: generateImage() starts tracing the NEXT frame before it waits for the copy of this one,
+		 *  so the read-back is hidden behind the next frame.  Anything that changes what the next frame should
+		 *  look like (camera, focus, sample count, tile, seeds) discards the frame traced ahead.  Off by default:
+		 *  then a frame is only ever traced inside the call that returns it, as upstream. */
+		void setRenderAhead( bool enabled );
 		cl_uint getWidth() const { return mWidth; }
 		cl_uint getHeight() const { return mHeight; }
 		CL* getCL() { return mCL; }
@@ -134,6 +139,9 @@ class PathTracer {
 		bool mDeterministicSeeds;
 		cl_uint mSeedStride, mSeedOffset;
 		cl_uint mFrameTimeMs;
+		bool mRenderAhead, mAheadLaunched;
+		cl_uint mSampleCountBeforeAhead;
+		void dropFrameAhead();
 		bool mHaveOutput;             // imageOut holds a frame that the next launch must read as imageIn
 
 		cl_float* mTextureOut;        // pinned host copy of the frame, W*H*4

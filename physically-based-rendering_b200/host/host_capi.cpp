@@ -344,6 +344,11 @@ int pbrh_renderer_set_seed_schedule( pbrh_renderer* r, uint32_t stride, uint32_t
 	return 0;
 }
 
+int pbrh_renderer_set_render_ahead( pbrh_renderer* r, int32_t enabled ) {
+	r->widget->getPathTracer()->setRenderAhead( enabled != 0 );
+	return 0;
+}
+
 int pbrh_renderer_set_frame_time_ms( pbrh_renderer* r, uint32_t ms ) {
 	r->widget->getPathTracer()->setFrameTimeMs( ms );
 	return 0;

@@ -237,3 +237,41 @@ def test_product_equals_reference_renderer(cfg, name):
     finally:
         r.close()
         ref.close()
+
+
+def test_render_ahead_returns_the_same_frames(cfg):
+    """PathTracer::setRenderAhead: the next frame is traced while this one is copied out.  Same frames, also
+    across everything that invalidates the frame traced ahead (camera, focus, reset, renderFrames, readImage)."""
+    from pbr_b200 import host
+    cfg.update({"window.width": 120, "window.height": 72, "render.max_depth": 4})
+
+    def session(ahead):
+        r = host.Renderer(0)
+        r.set_deterministic(True)
+        r.load_model(MODELS + "/", "suzanne.obj")
+        r.set_render_ahead(ahead)
+        out = []
+        for _ in range(4):
+            out.append(r.generate_image().copy())
+        assert r.info()["sample_count"] == 4
+        r.rotate_camera(25, -8)                      # drops the frame traced ahead, restarts the accumulation
+        for _ in range(2):
+            out.append(r.generate_image().copy())
+        r.set_focus(60, 30)
+        out.append(r.generate_image().copy())
+        img, dbg = r.generate_image(debug=True)      # debug image: traced inside the call
+        out += [img.copy(), dbg.copy()]
+        out.append(r.generate_image().copy())
+        r.render_frames(3)                           # the frame traced ahead is the first of the three
+        out.append(r.read_image().copy())
+        assert r.info()["sample_count"] == 6
+        out.append(r.generate_image().copy())
+        out.append(r.read_image().copy())            # the frame returned last, not the one traced ahead
+        out.append(r.generate_image().copy())
+        r.close()
+        return out
+
+    plain, ahead = session(False), session(True)
+    assert len(plain) == len(ahead)
+    for i, (a, b) in enumerate(zip(plain, ahead)):
+        assert Hh.images_equal(a, b), "image %d differs with render-ahead" % i

@@ -246,8 +246,8 @@ def run_ours(args):
                     multigpu.combine_spp(img, world, out=display)
                 combined[j & 1] = torch.cuda.Event()
                 combined[j & 1].record(display_stream)
-            if tiles:
-                render_stream.wait_event(combined[j & 1])      # the gathered rows are the next frame's input
+            # (rows: the next frame only needs this rank's own rows of the previous image, which it wrote
+            #  itself; the gathered rows are for display)
 
     def step_resident():
         r.reset_sample_count()
@@ -377,6 +377,22 @@ def run_ours(args):
 
     # ---- optional: is the pipelined multi-GPU image the right one? ---------------------------------
     verify = None
+    if args.verify and world > 1 and tiles:
+        step_resident()
+        sync_all()
+        if rank == 0:
+            shown = image_tensor().clone()
+            r.set_tile(0, H)
+            r.reset_sample_count()
+            r.render_frames(SPP)
+            torch.cuda.synchronize()
+            want = image_tensor()
+            same = (shown == want) | (torch.isnan(shown) & torch.isnan(want))
+            verify = {"bit_identical_pixels": int(same.all(dim=2).sum()), "pixels": W * H,
+                      "what": "all-gathered image of one pipelined step vs the same frames rendered whole on rank 0"}
+            y0, y1 = multigpu.tile_rows(H, rank, world)
+            r.set_tile(y0, y1)
+        sync_all()
     if args.verify and world > 1 and not tiles:
         step_resident()
         sync_all()

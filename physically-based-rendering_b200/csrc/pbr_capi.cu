@@ -98,6 +98,7 @@ struct pbr_ctx {
 	cudaEvent_t evGroup[2] = {nullptr, nullptr};
 	int tailStepsBulk = 64, tailStepsFlush = 256, flushGroup = 4;
 	int prevGroupBegin = 0;
+	int traverseBlocks = 0;                    /* tuning: cap on resident traverse blocks per SM (0 = all that fit) */
 	int batchInterleave = 0;                   /* pbr_kernel_launch_batch: let pixels run ahead into later frames */
 
 	/* can any material extend a path beyond MAX_DEPTH? (decides how many wavefront iterations to launch) */
@@ -528,6 +529,7 @@ int runFrame(pbr_ctx* ctx, const FrameParams& P, int nPaths) {
 	int occT = 0, occS = 0;
 	CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occT, traverseKernel<PHONG>, 128, 0));
 	CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occS, shadeKernel<BRDF, SHADOW, PHONG>, 128, 0));
+	if (ctx->traverseBlocks > 0 && ctx->traverseBlocks < occT) occT = ctx->traverseBlocks;
 	const int gridT = ctx->smCount * (occT > 0 ? occT : 1);
 	const int gridS = ctx->smCount * (occS > 0 ? occS : 1);
 
@@ -1086,6 +1088,7 @@ int pbr_set_tuning(pbr_ctx* ctx, const char* key, int32_t value) {
 	else if (k == "tail_steps_flush" && value >= 1 && value <= 1000000) ctx->tailStepsFlush = value;
 	else if (k == "flush_group" && value >= 1 && value <= 64) ctx->flushGroup = value;
 	else if (k == "batch_interleave" && (value == 0 || value == 1)) ctx->batchInterleave = value;
+	else if (k == "traverse_blocks" && value >= 0 && value <= 32) ctx->traverseBlocks = value;
 	else return fail(ctx, PBR_ERR_INVALID, "pbr_set_tuning: unknown key or value out of range: " + k);
 	return PBR_OK;
 }

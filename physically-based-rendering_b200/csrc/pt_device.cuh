@@ -43,7 +43,8 @@ using pm::v3;
 
 struct SceneDev {
 	const float4* nodes;          /* 2 x float4 per node */
-	const float4* tris;           /* 4 x float4 (64 B) per face; PHONGTESS: 6 x float4 (a b c an bn cn) */
+	const float4* tris;           /* 2 x float4 (32 B) per face; PHONGTESS: 6 x float4 (a b c an bn cn) */
+	const float2* trisB;          /* + 8 B per face (edge2.y, edge2.z); unused with PHONGTESS */
 	const pbr_light* lights;
 	float phongAlpha;             /* PHONGTESS_ALPHA */
 	int numNodes;
@@ -92,15 +93,18 @@ __device__ __forceinline__ void loadNode(const float4* nodes, int index, float4&
 		: "l"(nodes + 2 * (size_t) index));
 }
 
-#define PT_TRI_STRIDE 4           /* float4s per triangle record */
+#define PT_TRI_STRIDE 2           /* float4s per triangle record in `tris` */
 
-/* (a.xyz, material bits) + edge1 with one 256-bit load, edge2 with one 128-bit load. */
-__device__ __forceinline__ void loadTri(const float4* tris, int face, float4& A, float4& E1, float4& E2) {
-	const float4* p = tris + PT_TRI_STRIDE * (size_t) face;
+/* 40 bytes per face in two arrays, so that the randomly accessed part of the scene stays as small as it can
+ * (the walk is served from L2, and its hit rate falls off beyond ~60 MB, scripts/micro/chase.cu):
+ * (a.xyz, material bits, edge1.xyz, edge2.x) with one 256-bit load, (edge2.y, edge2.z) with one 64-bit load. */
+__device__ __forceinline__ void loadTri(const SceneDev& S, int face, float4& A, float4& E1, float4& E2) {
+	const float4* p = S.tris + PT_TRI_STRIDE * (size_t) face;
 	asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
 		: "=f"(A.x), "=f"(A.y), "=f"(A.z), "=f"(A.w), "=f"(E1.x), "=f"(E1.y), "=f"(E1.z), "=f"(E1.w)
 		: "l"(p));
-	E2 = __ldg(p + 2);
+	const float2 yz = __ldg(S.trisB + face);
+	E2 = make_float4(E1.w, yz.x, yz.y, 0.0f);
 }
 
 __device__ __forceinline__ vec3 f4xyz(const float4& f) { return v3(f.x, f.y, f.z); }
@@ -113,12 +117,12 @@ __device__ __forceinline__ vec3 p4xyz(const pbr_float4& f) { return v3(f.x, f.y,
 /* flatTriAndRayIntersect (pt_intersect.cl:92-129) + intersectFace (pt_bvh.cl:10-24) on a
  * pre-gathered triangle record.  Updates (rt, hitFace, hitLeaf) when the face is closer. */
 __device__ __forceinline__ void intersectFace(
-	const float4* __restrict__ tris, const int face, const int leaf,
+	const SceneDev& S, const int face, const int leaf,
 	const vec3 o, const vec3 d, const float tNear,
 	float& rt, int& hitFace, int& hitLeaf
 ) {
 	float4 A, E1, E2;
-	loadTri(tris, face, A, E1, E2);
+	loadTri(S, face, A, E1, E2);
 
 	const float f = fmaxf(0.0f, tNear - 0.001f);
 	const vec3 closeOrigin = pm::fma3(d, f, o);
@@ -506,11 +510,11 @@ __device__ __forceinline__ void traverseClosest(
 
 		if (loW >= 0) {
 			if (PHONG) intersectFacePhong(S, loW, cur, o, d, tNear, tFar, rt, hitFace, hitLeaf, hitNormal);
-			else intersectFace(S.tris, loW, cur, o, d, tNear, rt, hitFace, hitLeaf);
+			else intersectFace(S, loW, cur, o, d, tNear, rt, hitFace, hitLeaf);
 			nTris++;
 			if (hiW != -1) {
 				if (PHONG) intersectFacePhong(S, hiW, cur, o, d, tNear, tFar, rt, hitFace, hitLeaf, hitNormal);
-				else intersectFace(S.tris, hiW, cur, o, d, tNear, rt, hitFace, hitLeaf);
+				else intersectFace(S, hiW, cur, o, d, tNear, rt, hitFace, hitLeaf);
 				nTris++;
 			}
 		}
@@ -549,11 +553,11 @@ __device__ __forceinline__ void traverseAny(
 
 		if (loW >= 0) {
 			if (PHONG) intersectFacePhong(S, loW, cur, o, d, tNear, tFar, rt, hitFace, hitLeaf, hitNormal);
-			else intersectFace(S.tris, loW, cur, o, d, tNear, rt, hitFace, hitLeaf);
+			else intersectFace(S, loW, cur, o, d, tNear, rt, hitFace, hitLeaf);
 			nTris++;
 			if (hiW != -1) {
 				if (PHONG) intersectFacePhong(S, hiW, cur, o, d, tNear, tFar, rt, hitFace, hitLeaf, hitNormal);
-				else intersectFace(S.tris, hiW, cur, o, d, tNear, rt, hitFace, hitLeaf);
+				else intersectFace(S, hiW, cur, o, d, tNear, rt, hitFace, hitLeaf);
 				nTris++;
 			}
 			if (rt < tLight) break;
@@ -964,7 +968,7 @@ __device__ __forceinline__ BounceResult bounce(const FrameParams& P, PathState& 
 	}
 	else {
 		float4 A, E1, E2;
-		loadTri(S.tris, s.hitFace, A, E1, E2);
+		loadTri(S, s.hitFace, A, E1, E2);
 		mtlIndex = (uint32_t) __float_as_int(A.w);
 		normal = pm::normalize(pm::cross(f4xyz(E1), f4xyz(E2)));
 	}

@@ -182,11 +182,11 @@ __device__ __forceinline__ bool nodeStep(const SceneDev& S, LaneRay& L) {
 template <bool ANY_HIT, bool PHONG>
 __device__ __forceinline__ void leafStep(const SceneDev& S, LaneRay& L) {
 	if (PHONG) intersectFacePhong(S, L.leafF0, L.leafCur, L.o, L.d, L.leafTNear, L.leafTFar, L.rt, L.hitFace, L.hitLeaf, L.normal);
-	else intersectFace(S.tris, L.leafF0, L.leafCur, L.o, L.d, L.leafTNear, L.rt, L.hitFace, L.hitLeaf);
+	else intersectFace(S, L.leafF0, L.leafCur, L.o, L.d, L.leafTNear, L.rt, L.hitFace, L.hitLeaf);
 	L.nt++;
 	if (L.leafF1 != -1) {
 		if (PHONG) intersectFacePhong(S, L.leafF1, L.leafCur, L.o, L.d, L.leafTNear, L.leafTFar, L.rt, L.hitFace, L.hitLeaf, L.normal);
-		else intersectFace(S.tris, L.leafF1, L.leafCur, L.o, L.d, L.leafTNear, L.rt, L.hitFace, L.hitLeaf);
+		else intersectFace(S, L.leafF1, L.leafCur, L.o, L.d, L.leafTNear, L.rt, L.hitFace, L.hitLeaf);
 		L.nt++;
 	}
 	if (ANY_HIT && L.rt < L.tLight) L.index = -1;     /* `break` of traverseShadows (pt_bvh.cl:170-172) */
@@ -639,7 +639,7 @@ __global__ void repackNodesKernel(const float4* __restrict__ src, const int numS
 /* facesV[f] + vertices[] -> (a, material), b - a, c - a   (pt_intersect.cl:146-149, :98-99) */
 __global__ void repackTrisKernel(
 	const uint4* __restrict__ facesV, const int numFaces, const float4* __restrict__ vertices, const int numVertices,
-	float4* __restrict__ tris
+	float4* __restrict__ tris, float2* __restrict__ trisB
 ) {
 	const int f = blockIdx.x * blockDim.x + threadIdx.x;
 	if (f >= numFaces) return;
@@ -647,9 +647,8 @@ __global__ void repackTrisKernel(
 	const uint32_t last = (uint32_t) (numVertices - 1);
 	const float4 a = vertices[min(fv.x, last)], b = vertices[min(fv.y, last)], c = vertices[min(fv.z, last)];
 	tris[PT_TRI_STRIDE * (size_t) f] = make_float4(a.x, a.y, a.z, __int_as_float((int) fv.w));
-	tris[PT_TRI_STRIDE * (size_t) f + 1] = make_float4(b.x - a.x, b.y - a.y, b.z - a.z, 0.0f);
-	tris[PT_TRI_STRIDE * (size_t) f + 2] = make_float4(c.x - a.x, c.y - a.y, c.z - a.z, 0.0f);
-	tris[PT_TRI_STRIDE * (size_t) f + 3] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+	tris[PT_TRI_STRIDE * (size_t) f + 1] = make_float4(b.x - a.x, b.y - a.y, b.z - a.z, c.x - a.x);
+	trisB[f] = make_float2(c.y - a.y, c.z - a.z);
 }
 
 /* PHONGTESS: facesV[f], facesN[f] + vertices[], normals[] -> (a, material), (b, allNormalsEqual), (c, 0),

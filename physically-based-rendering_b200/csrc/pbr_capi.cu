@@ -391,145 +391,137 @@ int updateCanExtendDepth(pbr_ctx* ctx, pbr_mem hMaterials, int brdf) {
 	return PBR_OK;
 }
 
+/* pipeline 2: two kernels resident together for the whole frame (pt_persistent.cuh) */
 template <int BRDF, bool SHADOW, bool PHONG>
-int runFrame(pbr_ctx* ctx, const FrameParams& P, int nPaths) {
-	if (ctx->pipeline == 1) {
-		{
-			LaunchScope ls(ctx, K_OTHER);
-			megaKernel<BRDF, SHADOW, PHONG><<<gridFor(nPaths, 128), 128, 0, ctx->stream>>>(P, nPaths);
-		}
-		CK(cudaGetLastError());
-		return PBR_OK;
-	}
-	int rc = ensureWave(ctx, (size_t) nPaths);
+int runPersistent(pbr_ctx* ctx, const FrameParams& P, WaveState W, int nPaths) {
+	int rc = ensureRings(ctx, (size_t) nPaths);
 	if (rc) return rc;
-	WaveState W = ctx->wave;
-	W.hitN = PHONG ? ctx->hitN : nullptr;
+	const uint32_t mask = (uint32_t) ctx->ringCap - 1u;
+	/* Both kernels must be resident at once: give the shading kernel its blocks per SM and the
+	 * traversal kernel what is left of the register file and the thread slots. */
+	static int regsT = 0, regsS = 0;
+	if (regsT == 0) {
+		cudaFuncAttributes aT, aS;
+		CK(cudaFuncGetAttributes(&aT, persistTraverseKernel<PHONG>));
+		CK(cudaFuncGetAttributes(&aS, persistShadeKernel<BRDF, SHADOW, PHONG>));
+		regsT = (aT.numRegs + 7) / 8 * 8 * 128;
+		regsS = (aS.numRegs + 7) / 8 * 8 * 128;
+	}
+	int sB = ctx->persistSBlocks, tB = ctx->persistTBlocks;
+	while (sB > 1 && sB * regsS + regsT > 65536) sB--;
+	const int room = (65536 - sB * regsS) / regsT;
+	if (tB <= 0 || tB > room) tB = room;
+	if (tB + sB > 16) tB = 16 - sB;
+	if (tB < 1) return fail(ctx, PBR_ERR_INVALID, "pathTracing: persistent pipeline does not fit on an SM");
+	{
+		LaunchScope ls(ctx, K_RAYGEN);
+		persistRaygenKernel<<<ctx->smCount * 8, 256, 0, ctx->stream>>>(P, W, ctx->pctl, ctx->ring[0], nPaths);
+	}
+	CK(cudaEventRecord(ctx->evFork, ctx->stream));
+	CK(cudaStreamWaitEvent(ctx->shadeStream, ctx->evFork, 0));
+	{
+		LaunchScope ls(ctx, K_SHADE, ctx->shadeStream);
+		persistShadeKernel<BRDF, SHADOW, PHONG><<<ctx->smCount * sB, 128, 0, ctx->shadeStream>>>(
+			P, W, ctx->pctl, ctx->ring[0], ctx->ring[1], mask, ctx->persistFill);
+	}
+	CK(cudaEventRecord(ctx->evJoin, ctx->shadeStream));
+	{
+		LaunchScope ls(ctx, K_TRAVERSE);
+		persistTraverseKernel<PHONG><<<ctx->smCount * tB, 128, 0, ctx->stream>>>(
+			P.scene, W, ctx->pctl, ctx->ring[0], ctx->ring[1], mask, ctx->stats);
+	}
+	CK(cudaStreamWaitEvent(ctx->stream, ctx->evJoin, 0));
+	CK(cudaGetLastError());
+	ctx->persistUsed = true;
+	return PBR_OK;
+}
+
+/* pipeline 3: wavefront with carry-over (traverseCarryKernel) */
+template <int BRDF, bool SHADOW, bool PHONG>
+int runCarryOver(pbr_ctx* ctx, const FrameParams& P, WaveState W, int nPaths) {
 	const QueueCtl& Q = ctx->qctl;
-
-	if (ctx->pipeline == 2) {
-		/* two kernels resident together for the whole frame (pt_persistent.cuh) */
-		rc = ensureRings(ctx, (size_t) nPaths);
-		if (rc) return rc;
-		const uint32_t mask = (uint32_t) ctx->ringCap - 1u;
-		/* Both kernels must be resident at once: give the shading kernel its blocks per SM and the
-		 * traversal kernel what is left of the register file and the thread slots. */
-		static int regsT = 0, regsS = 0;
-		if (regsT == 0) {
-			cudaFuncAttributes aT, aS;
-			CK(cudaFuncGetAttributes(&aT, persistTraverseKernel<PHONG>));
-			CK(cudaFuncGetAttributes(&aS, persistShadeKernel<BRDF, SHADOW, PHONG>));
-			regsT = (aT.numRegs + 7) / 8 * 8 * 128;
-			regsS = (aS.numRegs + 7) / 8 * 8 * 128;
+	/* wavefront with carry-over (traverseCarryKernel): the number of iterations depends on the rays,
+	 * so launches go out in groups and the host looks at the mailbox of the group before the one it
+	 * has just enqueued -- the device never waits for the host */
+	W.node = ctx->waveNode;
+	int occT = 0, occS = 0;
+	CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occT, traverseCarryKernel<PHONG>, 128, 0));
+	CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occS, shadeKernel<BRDF, SHADOW, PHONG>, 128, 0));
+	const int gridT = ctx->smCount * (occT > 0 ? occT : 1);
+	const int gridS = ctx->smCount * (occS > 0 ? occS : 1);
+	uint32_t* c = ctx->cctl;
+	uint32_t* mailboxDev = nullptr;
+	CK(cudaHostGetDevicePointer((void**) &mailboxDev, ctx->mailbox, 0));
+	static const bool dump = getenv("PBR_PROFILE_DUMP") != nullptr;
+	{
+		LaunchScope ls(ctx, K_RAYGEN);
+		raygenCarryKernel<<<ctx->smCount * 8, 256, 0, ctx->stream>>>(P, W, c, nPaths);
+	}
+	const int firstGroup = P.frameCount * P.samples > 1 ? P.frameCount * P.samples : P.maxDepth;
+	int it = 0;
+	for (int group = 0; ; group++) {
+		const int n = group == 0 ? firstGroup : ctx->flushGroup;
+		const int itBegin = it;
+		for (int j = 0; j < n; j++, it++) {
+			const int a = it & 1, b = a ^ 1;
+			ctx->mailbox[it % MAILBOX_SLOTS] = 0xffffffffu;
+			CarryQueues Qc;
+			Qc.qCarryIn = ctx->carryQ[a]; Qc.nCarryIn = c + 2 + a;
+			Qc.qNew = (it == 0) ? nullptr : Q.queue[a]; Qc.nNew = c + 0 + a;
+			Qc.qHit = ctx->hitQ; Qc.nHit = c + 4 + a;
+			Qc.qCarryOut = ctx->carryQ[b]; Qc.nCarryOut = c + 2 + b;
+			Qc.cursor = c + 6;
+			Qc.zeroAtStart = c + 0 + b;
+			Qc.mailbox = mailboxDev + (it % MAILBOX_SLOTS);
+			cudaEvent_t d0 = nullptr, d1 = nullptr, d2 = nullptr;
+			if (dump) { d0 = takeEvent(ctx); d1 = takeEvent(ctx); d2 = takeEvent(ctx); cudaEventRecord(d0, ctx->stream); }
+			{
+				LaunchScope ls(ctx, K_TRAVERSE);
+				traverseCarryKernel<PHONG><<<gridT, 128, 0, ctx->stream>>>(P.scene, W, Qc, ctx->tailStepsBulk, ctx->tailStepsFlush, ctx->stats);
+			}
+			if (dump) cudaEventRecord(d1, ctx->stream);
+			{
+				LaunchScope ls(ctx, K_SHADE);
+				shadeKernel<BRDF, SHADOW, PHONG><<<gridS, 128, 0, ctx->stream>>>(
+					P, W, ctx->hitQ, c + 4 + a, Q.queue[b], c + 0 + b, c + 6, c + 2 + a, c + 4 + b);
+			}
+			if (dump) {
+				cudaEventRecord(d2, ctx->stream);
+				uint32_t h[8];
+				cudaMemcpyAsync(h, c, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream);
+				cudaStreamSynchronize(ctx->stream);
+				float tMs = 0.0f, sMs = 0.0f;
+				cudaEventElapsedTime(&tMs, d0, d1);
+				cudaEventElapsedTime(&sMs, d1, d2);
+				fprintf(stderr, "[carry] it %3d  start %8u  traverse %7.3f ms -> finished %8u parked %8u   shade %6.3f ms -> new %8u\n",
+					it, ((volatile uint32_t*) ctx->mailbox)[it % MAILBOX_SLOTS], tMs, h[4 + a], h[2 + b], sMs, h[0 + b]);
+				ctx->eventPool.push_back(d0); ctx->eventPool.push_back(d1); ctx->eventPool.push_back(d2);
+			}
 		}
-		int sB = ctx->persistSBlocks, tB = ctx->persistTBlocks;
-		while (sB > 1 && sB * regsS + regsT > 65536) sB--;
-		const int room = (65536 - sB * regsS) / regsT;
-		if (tB <= 0 || tB > room) tB = room;
-		if (tB + sB > 16) tB = 16 - sB;
-		if (tB < 1) return fail(ctx, PBR_ERR_INVALID, "pathTracing: persistent pipeline does not fit on an SM");
-		{
-			LaunchScope ls(ctx, K_RAYGEN);
-			persistRaygenKernel<<<ctx->smCount * 8, 256, 0, ctx->stream>>>(P, W, ctx->pctl, ctx->ring[0], nPaths);
-		}
-		CK(cudaEventRecord(ctx->evFork, ctx->stream));
-		CK(cudaStreamWaitEvent(ctx->shadeStream, ctx->evFork, 0));
-		{
-			LaunchScope ls(ctx, K_SHADE, ctx->shadeStream);
-			persistShadeKernel<BRDF, SHADOW, PHONG><<<ctx->smCount * sB, 128, 0, ctx->shadeStream>>>(
-				P, W, ctx->pctl, ctx->ring[0], ctx->ring[1], mask, ctx->persistFill);
-		}
-		CK(cudaEventRecord(ctx->evJoin, ctx->shadeStream));
-		{
-			LaunchScope ls(ctx, K_TRAVERSE);
-			persistTraverseKernel<PHONG><<<ctx->smCount * tB, 128, 0, ctx->stream>>>(
-				P.scene, W, ctx->pctl, ctx->ring[0], ctx->ring[1], mask, ctx->stats);
-		}
-		CK(cudaStreamWaitEvent(ctx->stream, ctx->evJoin, 0));
+		CK(cudaEventRecord(ctx->evGroup[group & 1], ctx->stream));
 		CK(cudaGetLastError());
-		ctx->persistUsed = true;
-		return PBR_OK;
-	}
-
-	if (ctx->pipeline == 3) {
-		/* wavefront with carry-over (traverseCarryKernel): the number of iterations depends on the rays,
-		 * so launches go out in groups and the host looks at the mailbox of the group before the one it
-		 * has just enqueued -- the device never waits for the host */
-		W.node = ctx->waveNode;
-		int occT = 0, occS = 0;
-		CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occT, traverseCarryKernel<PHONG>, 128, 0));
-		CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occS, shadeKernel<BRDF, SHADOW, PHONG>, 128, 0));
-		const int gridT = ctx->smCount * (occT > 0 ? occT : 1);
-		const int gridS = ctx->smCount * (occS > 0 ? occS : 1);
-		uint32_t* c = ctx->cctl;
-		uint32_t* mailboxDev = nullptr;
-		CK(cudaHostGetDevicePointer((void**) &mailboxDev, ctx->mailbox, 0));
-		static const bool dump = getenv("PBR_PROFILE_DUMP") != nullptr;
-		{
-			LaunchScope ls(ctx, K_RAYGEN);
-			raygenCarryKernel<<<ctx->smCount * 8, 256, 0, ctx->stream>>>(P, W, c, nPaths);
-		}
-		const int firstGroup = P.frameCount * P.samples > 1 ? P.frameCount * P.samples : P.maxDepth;
-		int it = 0;
-		for (int group = 0; ; group++) {
-			const int n = group == 0 ? firstGroup : ctx->flushGroup;
-			const int itBegin = it;
-			for (int j = 0; j < n; j++, it++) {
-				const int a = it & 1, b = a ^ 1;
-				ctx->mailbox[it % MAILBOX_SLOTS] = 0xffffffffu;
-				CarryQueues Qc;
-				Qc.qCarryIn = ctx->carryQ[a]; Qc.nCarryIn = c + 2 + a;
-				Qc.qNew = (it == 0) ? nullptr : Q.queue[a]; Qc.nNew = c + 0 + a;
-				Qc.qHit = ctx->hitQ; Qc.nHit = c + 4 + a;
-				Qc.qCarryOut = ctx->carryQ[b]; Qc.nCarryOut = c + 2 + b;
-				Qc.cursor = c + 6;
-				Qc.zeroAtStart = c + 0 + b;
-				Qc.mailbox = mailboxDev + (it % MAILBOX_SLOTS);
-				cudaEvent_t d0 = nullptr, d1 = nullptr, d2 = nullptr;
-				if (dump) { d0 = takeEvent(ctx); d1 = takeEvent(ctx); d2 = takeEvent(ctx); cudaEventRecord(d0, ctx->stream); }
-				{
-					LaunchScope ls(ctx, K_TRAVERSE);
-					traverseCarryKernel<PHONG><<<gridT, 128, 0, ctx->stream>>>(P.scene, W, Qc, ctx->tailStepsBulk, ctx->tailStepsFlush, ctx->stats);
-				}
-				if (dump) cudaEventRecord(d1, ctx->stream);
-				{
-					LaunchScope ls(ctx, K_SHADE);
-					shadeKernel<BRDF, SHADOW, PHONG><<<gridS, 128, 0, ctx->stream>>>(
-						P, W, ctx->hitQ, c + 4 + a, Q.queue[b], c + 0 + b, c + 6, c + 2 + a, c + 4 + b);
-				}
-				if (dump) {
-					cudaEventRecord(d2, ctx->stream);
-					uint32_t h[8];
-					cudaMemcpyAsync(h, c, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream);
-					cudaStreamSynchronize(ctx->stream);
-					float tMs = 0.0f, sMs = 0.0f;
-					cudaEventElapsedTime(&tMs, d0, d1);
-					cudaEventElapsedTime(&sMs, d1, d2);
-					fprintf(stderr, "[carry] it %3d  start %8u  traverse %7.3f ms -> finished %8u parked %8u   shade %6.3f ms -> new %8u\n",
-						it, ((volatile uint32_t*) ctx->mailbox)[it % MAILBOX_SLOTS], tMs, h[4 + a], h[2 + b], sMs, h[0 + b]);
-					ctx->eventPool.push_back(d0); ctx->eventPool.push_back(d1); ctx->eventPool.push_back(d2);
-				}
+		if (group >= 1 || dump) {
+			/* the group before this one: did one of its launches start with nothing to do? */
+			const int gPrev = dump ? group : group - 1;
+			CK(cudaEventSynchronize(ctx->evGroup[gPrev & 1]));
+			bool done = false;
+			const int pb = dump ? itBegin : ctx->prevGroupBegin, pe = dump ? it : itBegin;
+			for (int k = pb; k < pe; k++) {
+				const uint32_t live = ((volatile uint32_t*) ctx->mailbox)[k % MAILBOX_SLOTS];
+				if (live == 0u) done = true;
 			}
-			CK(cudaEventRecord(ctx->evGroup[group & 1], ctx->stream));
-			CK(cudaGetLastError());
-			if (group >= 1 || dump) {
-				/* the group before this one: did one of its launches start with nothing to do? */
-				const int gPrev = dump ? group : group - 1;
-				CK(cudaEventSynchronize(ctx->evGroup[gPrev & 1]));
-				bool done = false;
-				const int pb = dump ? itBegin : ctx->prevGroupBegin, pe = dump ? it : itBegin;
-				for (int k = pb; k < pe; k++) {
-					const uint32_t live = ((volatile uint32_t*) ctx->mailbox)[k % MAILBOX_SLOTS];
-					if (live == 0u) done = true;
-				}
-				if (done) break;
-			}
-			ctx->prevGroupBegin = itBegin;
-			if (it > 1000000) return fail(ctx, PBR_ERR_INVALID, "pathTracing: carry-over wavefront does not terminate");
+			if (done) break;
 		}
-		return PBR_OK;
+		ctx->prevGroupBegin = itBegin;
+		if (it > 1000000) return fail(ctx, PBR_ERR_INVALID, "pathTracing: carry-over wavefront does not terminate");
 	}
+	return PBR_OK;
+}
 
+/* pipeline 0 (default): one traverse + one shade launch per bounce */
+template <int BRDF, bool SHADOW, bool PHONG>
+int runWavefront(pbr_ctx* ctx, const FrameParams& P, WaveState W, int nPaths) {
+	const QueueCtl& Q = ctx->qctl;
 	int occT = 0, occS = 0;
 	CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occT, traverseKernel<PHONG>, 128, 0));
 	CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occS, shadeKernel<BRDF, SHADOW, PHONG>, 128, 0));
@@ -572,6 +564,27 @@ int runFrame(pbr_ctx* ctx, const FrameParams& P, int nPaths) {
 	if (dump) { cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2); }
 	CK(cudaGetLastError());
 	return PBR_OK;
+}
+
+template <int BRDF, bool SHADOW, bool PHONG>
+int runFrame(pbr_ctx* ctx, const FrameParams& P, int nPaths) {
+	if (ctx->pipeline == 1) {
+		{
+			LaunchScope ls(ctx, K_OTHER);
+			megaKernel<BRDF, SHADOW, PHONG><<<gridFor(nPaths, 128), 128, 0, ctx->stream>>>(P, nPaths);
+		}
+		CK(cudaGetLastError());
+		return PBR_OK;
+	}
+	int rc = ensureWave(ctx, (size_t) nPaths);
+	if (rc) return rc;
+	WaveState W = ctx->wave;
+	W.hitN = PHONG ? ctx->hitN : nullptr;
+	switch (ctx->pipeline) {
+		case 2: return runPersistent<BRDF, SHADOW, PHONG>(ctx, P, W, nPaths);
+		case 3: return runCarryOver<BRDF, SHADOW, PHONG>(ctx, P, W, nPaths);
+		default: return runWavefront<BRDF, SHADOW, PHONG>(ctx, P, W, nPaths);
+	}
 }
 
 bool parseSky(const char* v, pbr_float4* out) {

@@ -260,6 +260,9 @@ def run_ours(args):
 
     pinned = torch.empty((H, W, 4), dtype=torch.float32).pin_memory()
     pinned_np = pinned.numpy()
+    pinned2 = [pinned, torch.empty((H, W, 4), dtype=torch.float32).pin_memory()] if world > 1 and rank == 0 else None
+    landed = [None, None]
+    delivered = [0]
 
     def step_e2e(last=False):
         if world > 1:
@@ -275,12 +278,24 @@ def run_ours(args):
                 r.generate_image(out=pinned_np)
             else:
                 frame()
-                if rank == 0:                                # one consumer of the displayed frame: rank 0's host
+                if rank == 0:
+                    # one consumer of the displayed frame: rank 0's host.  The copy of frame j is enqueued behind its
+                    # combine; the host then waits for the copy of frame j - 1, so that it never stalls the launches
+                    # of the frame being traced (every frame is delivered, one frame later; two pinned buffers).
+                    j = delivered[0]
+                    delivered[0] += 1
                     with torch.cuda.stream(display_stream):
-                        pinned.copy_(display if not tiles else image_tensor(), non_blocking=True)
-                    display_stream.synchronize()
+                        pinned2[j & 1].copy_(display if not tiles else image_tensor(), non_blocking=True)
+                        landed[j & 1] = torch.cuda.Event()
+                        landed[j & 1].record(display_stream)
+                    if tiles:
+                        combined[(frame_no[0] - 1) & 1] = landed[j & 1]   # the copy reads the image frame + 2 overwrites
+                    if landed[(j - 1) & 1] is not None:
+                        landed[(j - 1) & 1].synchronize()
         if world > 1:
             render_stream.wait_stream(display_stream)
+            if rank == 0:
+                display_stream.synchronize()                 # the last frame of the step has landed too
 
     def sync_all():
         if world > 1:
@@ -372,7 +387,7 @@ def run_ours(args):
             "api": "PathTracer::generateImage (libpbr_host.so) per frame, every frame into a pinned host image, "
                    "setRenderAhead(true): the next frame is traced while this one is copied" if world == 1 else
                    "PathTracer::renderFrames(1) per rank + combine on a side stream; rank 0 reads every combined "
-                   "frame into pinned host memory",
+                   "frame into pinned host memory (double-buffered: it waits for frame j - 1 while frame j + 1 is traced)",
         }
 
     # ---- optional: is the pipelined multi-GPU image the right one? ---------------------------------

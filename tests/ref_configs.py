@@ -29,6 +29,17 @@ CASES = {
     "suzanne_sa_close": ("suzanne.obj", dict(width=64, height=48, brdf=1, shadow_rays=1, max_depth=6, max_added_depth=2,
                                              eye=(0.3, 0.8, 1.6), center=(0.2, 0.3, 1.0), antialiasing=0.333)),
     "soup_sa": (("soup", 20000, 5), dict(width=96, height=64, brdf=1, eye=(0.0, 0.0, 3.5))),
+    # tests/material_scene.py: partial transparency, anisotropic lobes, rough / isotropy in (0, 1), an orb light
+    "materials_sa": ("@materials", dict(width=96, height=64, brdf=1, shadow_rays=1, max_depth=5, max_added_depth=3,
+                                        eye=(0.3, 1.1, 3.2), center=(-0.05, 0.25, 1.0))),
+    "materials_sa_opaque": ("@materials_opaque", dict(width=96, height=64, brdf=1, shadow_rays=1, max_depth=5, max_added_depth=3,
+                                                      eye=(0.3, 1.1, 3.2), center=(-0.05, 0.25, 1.0))),
+    "materials_schlick": ("@materials", dict(width=96, height=64, brdf=0, shadow_rays=1, max_depth=5, max_added_depth=3,
+                                             eye=(0.3, 1.1, 3.2), center=(-0.05, 0.25, 1.0))),
+    "materials_sa_ms_noshadow": ("@materials_opaque", dict(width=64, height=48, brdf=1, samples=3, max_depth=6, max_added_depth=4,
+                                                    eye=(-0.8, 0.7, 2.6), center=(0.2, 0.15, 1.0))),
+    "materials_schlick_phong": ("@materials", dict(width=64, height=48, brdf=0, max_depth=4, phong_tessellation=0.6,
+                                                   eye=(0.3, 1.1, 3.2), center=(-0.05, 0.25, 1.0))),
 }
 
 _SCENES = {}
@@ -41,8 +52,13 @@ def scene_of(spec):
         if isinstance(spec, tuple):
             import pbr_b200
             _SCENES[spec] = pbr_b200.scenes.soup(spec[1], seed=spec[2])
+        elif spec in ("@materials", "@materials_opaque"):
+            import tempfile
+            import material_scene
+            with tempfile.TemporaryDirectory() as d:
+                _SCENES[spec] = O.load_obj(material_scene.write(d, transparent=(spec == "@materials")), 1)
         else:
-            _SCENES[spec] = O.load_obj(Hh.model_path(spec))
+            _SCENES[spec] = O.load_obj(Hh.model_path(spec), 1)      # with the .lights; used when shadow_rays = 1
     return _SCENES[spec]
 
 

@@ -96,6 +96,10 @@ def all_program_values():
     from oracle import ref_host as RH
     for name in CASES:
         yield R.values_from_defines(prepared(name).defines)
+    import test_random_parity as T
+    for brdf in (1, 0):
+        for seed in range(T.TRIALS):
+            yield R.values_from_defines(T._trial(seed, brdf).defines)
     if RH.available():
         for v in renderer_program_values():
             yield v

@@ -49,6 +49,20 @@ for k in (1, 2, 4, 8):
 out.append("\nRows sharded + all-gather per frame overlapped with the next frame (strong scaling of one 1080p image, 2 GPUs): %.0f Mrays/s, "
            "%d of %d pixels bit-identical to one GPU (`--shard tiles --verify`); every launch keeps its ~0.9 ms latency floor, so half the "
            "rays are not half the time." % (tiles["value"], tiles["verify"]["bit_identical_pixels"], tiles["verify"]["pixels"]))
+n8path = os.path.join(P, "configs_%s_n8.json" % tag)
+if os.path.isfile(n8path):
+    c8 = load("configs_%s_n8.json" % tag)
+    out.append("\nC4 and C5 on 8 GPUs (scripts/run_configs.py under torchrun; C4: rows sharded, one all-gather of the 133 MB frame per "
+               "frame; C5: ray array split contiguously):\n")
+    out.append("| | 1 GPU | 8 GPUs |")
+    out.append("|---|---|---|")
+    out.append("| C4 10M-triangle grid, 3840x2160 | %.0f Mrays/s, %.2f ms/frame | %.0f Mrays/s, %.2f ms/frame (strong scaling of one "
+               "image: %.1fx) |" % (c["c4"]["gpu_mrays_per_s"], c["c4"]["gpu_ms_per_frame"], c8["c4"]["gpu_mrays_per_s"],
+               c8["c4"]["gpu_ms_per_frame"], c8["c4"]["gpu_mrays_per_s"] / c["c4"]["gpu_mrays_per_s"]))
+    for r1, r8 in zip(c["c5"]["sweep"], c8["c5"]["sweep"]):
+        out.append("| C5 %d M rays, primary / shadow | %.0f / %.0f Mrays/s | %.0f / %.0f Mrays/s, bit-exact %s / %s |" % (
+            r1["requested_mrays"], r1["primary"]["mrays_per_s"], r1["shadow"]["mrays_per_s"], r8["primary"]["mrays_per_s"],
+            r8["shadow"]["mrays_per_s"], r8["primary"]["hit_face_leaf_t_bit_exact"], r8["shadow"]["hit_face_leaf_t_bit_exact"]))
 out.append("Pipelines on C2, ms per 1080p frame: wavefront 4.58 (default) | persistent kernels 4.92 | carry-over 5.5 | wavefront with "
            "interleaved frame batches 5.2 -- all bit-identical (DESIGN.md section 6).")
 with open(os.path.join(P, "RESULTS_%s.md" % tag), "w") as f:

@@ -121,6 +121,10 @@ int pbr_kernel_time_ms(pbr_ctx* ctx, pbr_kernel k, double* ms);
 
 /* Restrict launches to image rows [y0, y1) -- tile sharding across GPUs. Default: all. */
 int pbr_set_tile(pbr_ctx* ctx, int32_t y0, int32_t y1);
+/* Interleaved variant for load balance: this context renders the stripes of `stripe_rows` rows with
+ * (row / stripe_rows) % world == rank; IMG_HEIGHT must be a multiple of stripe_rows * world.  stripe_rows <= 0
+ * switches back to pbr_set_tile's contiguous rows. */
+int pbr_set_tile_stripes(pbr_ctx* ctx, int32_t stripe_rows, int32_t world, int32_t rank);
 /* Choose the device pipeline: 0 = wavefront, one traverse + one shade launch per bounce (default);
  * 1 = one-thread-per-pixel megakernel (the reference's launch structure; kept as an on-device cross-check);
  * 2 = persistent: one traversal and one shading kernel resident for the whole frame, exchanging paths

@@ -79,6 +79,8 @@ int pbrh_renderer_set_frame_time_ms(pbrh_renderer* r, uint32_t ms);
 /* generate_image starts tracing the next frame before it waits for the copy of this one (PathTracer::setRenderAhead) */
 int pbrh_renderer_set_render_ahead(pbrh_renderer* r, int32_t enabled);
 int pbrh_renderer_set_tile(pbrh_renderer* r, int32_t y0, int32_t y1);
+/* interleaved stripes of rows for load balance (pbr_set_tile_stripes); stripe_rows <= 0 = off */
+int pbrh_renderer_set_tile_stripes(pbrh_renderer* r, int32_t stripe_rows, int32_t world, int32_t rank);
 /* PathTracer::generateImage: one frame, accumulated image into out[W*H*4]; debug may be NULL */
 int pbrh_renderer_generate_image(pbrh_renderer* r, float* out, float* debug);
 /* n frames resident on the device, nothing read back */

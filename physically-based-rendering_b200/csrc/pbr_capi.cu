@@ -69,6 +69,7 @@ struct pbr_ctx {
 
 	KernelArgs args;
 	int tileY0 = -1, tileY1 = -1;
+	int stripeRows = 0, stripeWorld = 1, stripeRank = 0;
 	pbr_mem scratchImage = 0;                  /* pbr_kernel_launch_batch with depth of field */
 	int pipeline = 0;
 	bool debugImage = true;
@@ -971,6 +972,14 @@ static int launchFrames(pbr_ctx* ctx, int n, const float* seeds, const float* we
 	P.width = D.img_width; P.height = D.img_height;
 	P.y0 = ctx->tileY0 < 0 ? 0 : ctx->tileY0;
 	P.y1 = ctx->tileY1 < 0 ? D.img_height : ctx->tileY1;
+	P.stripeRows = 0; P.stripeWorld = 1; P.stripeRank = 0;
+	if (ctx->stripeRows > 0) {
+		if (D.img_height % (ctx->stripeRows * ctx->stripeWorld) != 0)
+			return fail(ctx, PBR_ERR_INVALID, "pbr_set_tile_stripes: IMG_HEIGHT is not a multiple of stripe_rows * world");
+		P.stripeRows = ctx->stripeRows; P.stripeWorld = ctx->stripeWorld; P.stripeRank = ctx->stripeRank;
+		P.y0 = 0;
+		P.y1 = D.img_height / ctx->stripeWorld;
+	}
 	if (P.y0 < 0 || P.y1 > D.img_height || P.y0 >= P.y1) return fail(ctx, PBR_ERR_INVALID, "tile rows outside the image");
 	P.maxDepth = D.max_depth; P.maxAddedDepth = D.max_added_depth; P.samples = D.samples;
 	P.antiAliasing = D.anti_aliasing;
@@ -1085,6 +1094,14 @@ int pbr_set_tile(pbr_ctx* ctx, int32_t y0, int32_t y1) {
 	if (!ctx) return PBR_ERR_INVALID;
 	ctx->tileY0 = y0;
 	ctx->tileY1 = y1;
+	return PBR_OK;
+}
+
+int pbr_set_tile_stripes(pbr_ctx* ctx, int32_t stripe_rows, int32_t world, int32_t rank) {
+	if (!ctx) return PBR_ERR_INVALID;
+	if (stripe_rows <= 0) { ctx->stripeRows = 0; ctx->stripeWorld = 1; ctx->stripeRank = 0; return PBR_OK; }
+	if (world < 1 || rank < 0 || rank >= world) return fail(ctx, PBR_ERR_INVALID, "pbr_set_tile_stripes: bad world / rank");
+	ctx->stripeRows = stripe_rows; ctx->stripeWorld = world; ctx->stripeRank = rank;
 	return PBR_OK;
 }
 

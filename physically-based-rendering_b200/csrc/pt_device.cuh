@@ -68,6 +68,9 @@ struct FrameParams {
 	float seed, pixelWeight, pxDim;
 	int width, height;            /* IMG_WIDTH / IMG_HEIGHT */
 	int y0, y1;                   /* rows rendered by this launch */
+	/* interleaved row sharding: stripeRows > 0 means local row r (y0 = 0, y1 = HEIGHT / stripeWorld) is image row
+	 * (r / stripeRows) * stripeRows * stripeWorld + stripeRank * stripeRows + r % stripeRows */
+	int stripeRows, stripeWorld, stripeRank;
 	int maxDepth, maxAddedDepth, samples;
 	float antiAliasing;
 	float4 skyLight;
@@ -923,6 +926,15 @@ __device__ __forceinline__ void beginSample(const FrameParams& P, PathState& s, 
 				s.d = pm::normalize(hitFocalPlane - s.o);
 			}
 		}
+	}
+}
+
+/* Pixel of a path of this launch: pathToPixel over the launch's rows, then the stripe interleave if one is set. */
+__device__ __forceinline__ void pixelOf(const FrameParams& P, const int p, int& px, int& py) {
+	pathToPixel(p, P.width, P.y0, P.y1 - P.y0, px, py);
+	if (P.stripeRows > 0) {
+		const int r = py - P.y0;
+		py = (r / P.stripeRows) * (P.stripeRows * P.stripeWorld) + P.stripeRank * P.stripeRows + (r % P.stripeRows);
 	}
 }
 

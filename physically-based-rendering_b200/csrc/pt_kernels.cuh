@@ -83,7 +83,7 @@ __global__ void __launch_bounds__(256) raygenKernel(const FrameParams P, const W
 	const int stride = gridDim.x * blockDim.x;
 	for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < nPaths; p += stride) {
 		int px, py;
-		pathToPixel(p, P.width, P.y0, P.y1 - P.y0, px, py);
+		pixelOf(P, p, px, py);
 		PathState s;
 		s.frame = 0u;
 		initPath(P, s);
@@ -468,7 +468,7 @@ __global__ void __launch_bounds__(256) raygenCarryKernel(const FrameParams P, co
 	const int stride = gridDim.x * blockDim.x;
 	for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < nPaths; p += stride) {
 		int px, py;
-		pathToPixel(p, P.width, P.y0, P.y1 - P.y0, px, py);
+		pixelOf(P, p, px, py);
 		PathState s;
 		s.frame = 0u;
 		initPath(P, s);
@@ -505,7 +505,7 @@ __global__ void __launch_bounds__(128) shadeKernel(
 			PathState s;
 			loadPath(W, p, s);
 			int px, py;
-			pathToPixel((int) p, P.width, P.y0, P.y1 - P.y0, px, py);
+			pixelOf(P, (int) p, px, py);
 
 			if (s.t != PM_INF_F) shaded++;
 			const uint32_t nTrisIn = s.nTris;
@@ -550,7 +550,7 @@ __global__ void __launch_bounds__(128) megaKernel(const FrameParams P, const int
 	s.hitNormal = v3(0.0f, 0.0f, 0.0f);
 	if (p < nPaths) {
 		int px, py;
-		pathToPixel(p, P.width, P.y0, P.y1 - P.y0, px, py);
+		pixelOf(P, p, px, py);
 		for (s.frame = 0u; s.frame < (uint32_t) P.frameCount; s.frame++) {
 			initPath(P, s);
 			for (; s.sample < (uint32_t) P.samples; s.sample++) {

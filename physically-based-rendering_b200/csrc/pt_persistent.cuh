@@ -100,7 +100,7 @@ __global__ void __launch_bounds__(256) persistRaygenKernel(
 	const int stride = gridDim.x * blockDim.x;
 	for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < nPaths; p += stride) {
 		int px, py;
-		pathToPixel(p, P.width, P.y0, P.y1 - P.y0, px, py);
+		pixelOf(P, p, px, py);
 		PathState s;
 		s.frame = 0u;
 		initPath(P, s);
@@ -288,7 +288,7 @@ __global__ void __launch_bounds__(128) persistShadeKernel(
 			PathState s;
 			loadPathCG(W, p, s);
 			int px, py;
-			pathToPixel((int) p, P.width, P.y0, P.y1 - P.y0, px, py);
+			pixelOf(P, (int) p, px, py);
 			const uint32_t trisBefore = s.nTris;
 			if (s.t != PM_INF_F) shaded++;
 			const BounceResult r = bounce<BRDF, SHADOW, PHONG>(P, s, shadowNodes, shadowRays);

@@ -26,7 +26,7 @@ SYMBOLS = [
     "pbrh_config_get", "pbrh_scene_load", "pbrh_scene_from_arrays", "pbrh_scene_free", "pbrh_scene_get",
     "pbrh_scene_name", "pbrh_flat_build", "pbrh_flat_info", "pbrh_flat_get", "pbrh_flat_free", "pbrh_set_device",
     "pbrh_renderer_create", "pbrh_renderer_destroy", "pbrh_renderer_load_scene", "pbrh_renderer_load_model",
-    "pbrh_renderer_set_deterministic", "pbrh_renderer_set_seed_schedule", "pbrh_renderer_set_frame_time_ms", "pbrh_renderer_set_render_ahead", "pbrh_renderer_set_tile", "pbrh_renderer_generate_image",
+    "pbrh_renderer_set_deterministic", "pbrh_renderer_set_seed_schedule", "pbrh_renderer_set_frame_time_ms", "pbrh_renderer_set_render_ahead", "pbrh_renderer_set_tile", "pbrh_renderer_set_tile_stripes", "pbrh_renderer_generate_image",
     "pbrh_renderer_render_frames", "pbrh_renderer_read_image", "pbrh_renderer_write_image", "pbrh_renderer_finish",
     "pbrh_renderer_reset_sample_count", "pbrh_renderer_set_focus", "pbrh_renderer_set_eye",
     "pbrh_renderer_rotate_camera", "pbrh_renderer_move_camera", "pbrh_renderer_info", "pbrh_renderer_stats", "pbrh_renderer_flat_get",
@@ -82,6 +82,7 @@ def load_library():
     lib.pbrh_renderer_set_seed_schedule.argtypes = [vp, u32, u32]
     lib.pbrh_renderer_set_frame_time_ms.argtypes = [vp, u32]
     lib.pbrh_renderer_set_render_ahead.argtypes = [vp, i32]
+    lib.pbrh_renderer_set_tile_stripes.argtypes = [vp, i32, i32, i32]
     lib.pbrh_renderer_set_tile.argtypes = [vp, i32, i32]
     lib.pbrh_renderer_generate_image.argtypes = [vp, f32p, f32p]
     lib.pbrh_renderer_render_frames.argtypes = [vp, i32]
@@ -295,6 +296,9 @@ class Renderer:
 
     def set_seed_schedule(self, stride, offset):
         _ck(self.lib.pbrh_renderer_set_seed_schedule(self.h, stride, offset), "setSeedSchedule")
+
+    def set_tile_stripes(self, stripe_rows, world=1, rank=0):
+        _ck(self.lib.pbrh_renderer_set_tile_stripes(self.h, stripe_rows, world, rank), "setTileStripes")
 
     def set_tile(self, y0, y1):
         _ck(self.lib.pbrh_renderer_set_tile(self.h, y0, y1), "setTileRows")

@@ -252,6 +252,11 @@ void CL::setTile( int y0, int y1 ) {
 }
 
 
+void CL::setTileStripes( int stripeRows, int world, int rank ) {
+	this->checkError( pbr_set_tile_stripes( mContext, stripeRows, world, rank ), "pbr_set_tile_stripes" );
+}
+
+
 void CL::setDebugImage( bool enabled ) {
 	this->checkError( pbr_set_debug_image( mContext, enabled ? 1 : 0 ), "pbr_set_debug_image" );
 }

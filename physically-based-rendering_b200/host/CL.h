@@ -60,6 +60,7 @@ class CL {
 		void readImageOutputEnd();
 		void executeBatch( cl_kernel kernel, cl_uint frames, const cl_float* seeds, const cl_float* pixelWeights );
 		void setTile( int y0, int y1 );
+		void setTileStripes( int stripeRows, int world, int rank );
 		void setDebugImage( bool enabled );
 		void getStats( uint64_t out[6], bool reset );
 		void* allocHost( size_t bytes );

@@ -227,6 +227,12 @@ void PathTracer::setTileRows( int y0, int y1 ) {
 }
 
 
+void PathTracer::setTileStripes( int stripeRows, int world, int rank ) {
+	this->dropFrameAhead();
+	mCL->setTileStripes( stripeRows, world, rank );
+}
+
+
 double PathTracer::getLastKernelMs() {
 	map<cl_kernel, double> times = mCL->getKernelTimes();
 	return times.count( mKernelPathTracing ) ? times[mKernelPathTracing] : 0.0;

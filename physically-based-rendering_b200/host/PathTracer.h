@@ -85,6 +85,8 @@ class PathTracer {
 		/** Replace the accumulated frame on the device (resume from a checkpoint). */
 		void writeImage( const cl_float* source, cl_uint sampleCount );
 		void setTileRows( int y0, int y1 );
+		/** Interleaved rows for load balance: stripes of `stripeRows` rows, stripe index % world == rank. */
+		void setTileStripes( int stripeRows, int world, int rank );
 		cl_uint getSampleCount() const { return mAheadLaunched ? mSampleCountBeforeAhead : mSampleCount; }
 		/** Render ahead: generateImage() starts tracing the NEXT frame before it waits for the copy of this one,
 		 *  so the read-back is hidden behind the next frame.  Anything that changes what the next frame should

@@ -344,6 +344,12 @@ int pbrh_renderer_set_seed_schedule( pbrh_renderer* r, uint32_t stride, uint32_t
 	return 0;
 }
 
+int pbrh_renderer_set_tile_stripes( pbrh_renderer* r, int32_t stripe_rows, int32_t world, int32_t rank ) {
+	NEED_READY
+	r->widget->getPathTracer()->setTileStripes( stripe_rows, world, rank );
+	return 0;
+}
+
 int pbrh_renderer_set_render_ahead( pbrh_renderer* r, int32_t enabled ) {
 	r->widget->getPathTracer()->setRenderAhead( enabled != 0 );
 	return 0;

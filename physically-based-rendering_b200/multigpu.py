@@ -77,6 +77,30 @@ def combine_tiles(image, rank, world, group=None):
     return image
 
 
+def stripe_rows_for(height, world, want=8):
+    """Largest stripe height <= want such that height is a multiple of stripe * world (0 if world does not divide)."""
+    if height % world:
+        return 0
+    local = height // world
+    for s in range(min(want, local), 0, -1):
+        if local % s == 0:
+            return s
+    return 0
+
+
+def combine_stripes(image, rank, world, stripe, group=None):
+    """Interleaved row sharding (pbr_set_tile_stripes): image [H, W, 4] holds this rank's stripes on entry and the
+    whole frame on return.  One all-gather per frame; the stripes are packed / unpacked with two strided copies."""
+    height, width, ch = image.shape
+    groups = height // (stripe * world)
+    v = image.view(groups, world, stripe, width, ch)
+    send = v[:, rank].contiguous()
+    recv = torch.empty((world,) + tuple(send.shape), dtype=image.dtype, device=image.device)
+    dist.all_gather_into_tensor(recv.view(-1), send.view(-1), group=group)
+    v.copy_(recv.permute(1, 0, 2, 3, 4))
+    return image
+
+
 def combine_spp(image, world, out=None, group=None):
     """Mean over ranks of the per-rank running averages: out = all_reduce_sum(image) / world.
     `image` is left untouched (it keeps accumulating); one collective per frame."""

@@ -52,12 +52,12 @@ out.append("\nRows sharded + all-gather per frame overlapped with the next frame
 n8path = os.path.join(P, "configs_%s_n8.json" % tag)
 if os.path.isfile(n8path):
     c8 = load("configs_%s_n8.json" % tag)
-    out.append("\nC4 and C5 on 8 GPUs (scripts/run_configs.py under torchrun; C4: rows sharded, one all-gather of the 133 MB frame per "
-               "frame; C5: ray array split contiguously):\n")
+    out.append("\nC4 and C5 on 8 GPUs (scripts/run_configs.py under torchrun; C4: rows sharded in interleaved stripes of 6 rows, "
+               "one all-gather of the 133 MB frame per frame, overlapped with the next frame; C5: ray array split contiguously):\n")
     out.append("| | 1 GPU | 8 GPUs |")
     out.append("|---|---|---|")
     out.append("| C4 10M-triangle grid, 3840x2160 | %.0f Mrays/s, %.2f ms/frame | %.0f Mrays/s, %.2f ms/frame (strong scaling of one "
-               "image: %.1fx) |" % (c["c4"]["gpu_mrays_per_s"], c["c4"]["gpu_ms_per_frame"], c8["c4"]["gpu_mrays_per_s"],
+               "image: %.1fx; each of a frame's three traverse launches keeps its ~0.5-0.9 ms latency floor) |" % (c["c4"]["gpu_mrays_per_s"], c["c4"]["gpu_ms_per_frame"], c8["c4"]["gpu_mrays_per_s"],
                c8["c4"]["gpu_ms_per_frame"], c8["c4"]["gpu_mrays_per_s"] / c["c4"]["gpu_mrays_per_s"]))
     for r1, r8 in zip(c["c5"]["sweep"], c8["c5"]["sweep"]):
         out.append("| C5 %d M rays, primary / shadow | %.0f / %.0f Mrays/s | %.0f / %.0f Mrays/s, bit-exact %s / %s |" % (

@@ -177,20 +177,49 @@ def run_c4(cfg, quick, dist):
     r.load_scene(scene)
     load_s = time.perf_counter() - t0
     info = r.info()
-    y0, y1 = multigpu.tile_rows(H, RANK, WORLD)
-    r.set_tile(y0, y1)
+    # rows interleaved in stripes: a height field seen from above its horizon has cheap sky rows and expensive
+    # ground rows, so contiguous blocks would leave most ranks waiting for the one with the ground
+    stripe = multigpu.stripe_rows_for(H, WORLD, want=8) if WORLD > 1 else 0
+    if stripe > 0:
+        r.set_tile_stripes(stripe, WORLD, RANK)
+    else:
+        y0, y1 = multigpu.tile_rows(H, RANK, WORLD)
+        r.set_tile(y0, y1)
     dev = r.device()
     img_t = None
     if dist is not None:
         dev.setStream(torch.cuda.current_stream().cuda_stream)
 
+    # the gather of frame k runs on a side stream while frame k + 1 is traced (frame k + 1 reads only this rank's own
+    # rows of image k; frame k + 2, which overwrites that image, waits for the gather of frame k) -- as in bench.py
+    render_stream = torch.cuda.current_stream() if dist is not None else None
+    gather_stream = torch.cuda.Stream() if dist is not None else None
+    gathered = [None, None]
+    views = {}
+    count = [0]
+
     def frame():
+        j = count[0]
+        count[0] += 1
+        if dist is not None and gathered[j & 1] is not None:
+            render_stream.wait_event(gathered[j & 1])
         r.render_frames(1)
         if dist is not None:
             _, hd = r.handles()
             ptr, _ = dev.devicePtr(hd["image"])
-            t = multigpu.DeviceImage(ptr, H, W, torch.device("cuda", LOCAL)).tensor
-            multigpu.combine_tiles(t, RANK, WORLD)
+            if ptr not in views:
+                views[ptr] = multigpu.DeviceImage(ptr, H, W, torch.device("cuda", LOCAL)).tensor
+            t = views[ptr]
+            rendered = torch.cuda.Event()
+            rendered.record(render_stream)
+            with torch.cuda.stream(gather_stream):
+                gather_stream.wait_event(rendered)
+                if stripe > 0:
+                    multigpu.combine_stripes(t, RANK, WORLD, stripe)
+                else:
+                    multigpu.combine_tiles(t, RANK, WORLD)
+                gathered[j & 1] = torch.cuda.Event()
+                gathered[j & 1].record(gather_stream)
 
     for _ in range(2):
         frame()
@@ -227,8 +256,9 @@ def run_c4(cfg, quick, dist):
         prep = prepared_like(cfg, scene, flat, 64, 64)
         want, _ = prep.oracle_trace(rays, nthreads=THREADS)
         out = {
-            "config": "C4 displaced grid %d tris (%d objects) %dx%d %dspp, rows sharded over %d rank(s)" % (
-                info["faces"], len(scene["objFaceCounts"]), W, H, SPP, WORLD),
+            "config": "C4 displaced grid %d tris (%d objects) %dx%d %dspp, rows sharded over %d rank(s)%s" % (
+                info["faces"], len(scene["objFaceCounts"]), W, H, SPP, WORLD,
+                " in interleaved stripes of %d rows" % stripe if stripe > 0 else ""),
             "gpu_mrays_per_s": (st[0] + st[1]) / sec / 1e6, "gpu_ms_per_frame": sec * 1e3 / SPP,
             "gpu_samples_per_s": SPP * W * H / sec, "nodes_per_ray": st[2] / max(1.0, st[0]),
             "scene_gen_s": gen_s, "load_s": load_s, "bvh_build_s": info["bvh_build_seconds"], "bvh_nodes": info["emitted_nodes"],

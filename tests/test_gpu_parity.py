@@ -258,6 +258,28 @@ def test_non_multiple_image_size_and_tiles(device, suzanne):
         stitched[y0:y1] = part[y0:y1]
     device.setTile(-1, -1)
     assert Hh.images_equal(stitched, full)
+    # interleaved stripes (pbr_set_tile_stripes): 3 "ranks", stripes of 4 and of 2 rows, every pipeline
+    for stripe, pipeline in ((4, 0), (2, 0), (4, 2), (4, 3), (8, 1)):
+        world = 48 // (stripe * (4 if stripe < 8 else 2))
+        world = max(world, 2)
+        if 48 % (stripe * world):
+            continue
+        stitched = np.zeros_like(full)
+        device.setPipeline(pipeline)
+        try:
+            for rank in range(world):
+                device.setTileStripes(stripe, world, rank)
+                part, _ = ds.frames(1)
+                mine = ((np.arange(48) // stripe) % world) == rank
+                stitched[mine] = part[mine]
+        finally:
+            device.setTileStripes(0)
+            device.setPipeline(0)
+        assert Hh.images_equal(stitched, full), "stripes of %d rows, pipeline %d" % (stripe, pipeline)
+    device.setTileStripes(5, 2, 0)
+    with pytest.raises(Exception):
+        ds.frames(1)                                   # 48 is not a multiple of 5 * 2
+    device.setTileStripes(0)
 
 
 def test_device_resident_accumulation_equals_host_roundtrip(device, suzanne):

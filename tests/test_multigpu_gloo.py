@@ -55,6 +55,18 @@ def _worker(rank, world, port, mode, out_dir):
             multigpu.combine_tiles(t, rank, world)          # ONE collective per frame
             img = t.numpy().copy()
             shown = img
+        elif mode == "stripes":
+            # what a rank holds after rendering with pbr_set_tile_stripes: its own stripes of the frame, the rest stale
+            stripe = multigpu.stripe_rows_for(H, world, want=5)
+            full, _, _ = O.path_tracing(p.defines, multigpu.frame_seed(k), multigpu.pixel_weight(k), p.px_dim, p.camera,
+                                        p.nodes, p.facesV, p.facesN, p.vertices4, p.normals4, p.materials, p.lights,
+                                        img, nthreads=1)
+            mine = ((np.arange(H) // stripe) % world) == rank
+            part = np.where(mine[:, None, None], full, np.float32(-7.0)).astype(np.float32)
+            t = torch.from_numpy(part)
+            multigpu.combine_stripes(t, rank, world, stripe)  # ONE collective per frame
+            img = t.numpy().copy()
+            shown = img
         else:
             g = multigpu.global_frame_index(k, rank, world)
             img, _, _ = O.path_tracing(p.defines, multigpu.frame_seed(g), multigpu.pixel_weight(k), p.px_dim, p.camera,
@@ -99,6 +111,15 @@ def test_seed_schedule_is_disjoint():
 
 def test_tile_sharding_is_bit_identical_to_one_process(tmp_path):
     shown, _ = _run("tiles", tmp_path)
+    want, _, _ = _prepared().oracle_frames(FRAMES, nthreads=2)
+    for img in shown:
+        assert Hh.images_equal(img, want)
+
+
+def test_stripe_sharding_is_bit_identical_to_one_process(tmp_path):
+    from pbr_b200 import multigpu
+    assert multigpu.stripe_rows_for(H, 2, want=5) > 0 and multigpu.stripe_rows_for(2160, 8, want=8) == 6
+    shown, _ = _run("stripes", tmp_path)
     want, _, _ = _prepared().oracle_frames(FRAMES, nthreads=2)
     for img in shown:
         assert Hh.images_equal(img, want)

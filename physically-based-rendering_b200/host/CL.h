@@ -27,64 +27,61 @@ using std::vector;
 
 
 class CL {
-
 	public:
 		CL( const bool silent = false );
 		~CL();
+		/** The device on which the next CL() is created (multi-GPU: one process per GPU). */
+		static void setDefaultDevice( int device ) { sDefaultDevice = device; }
+		pbr_ctx* getContext() { return mContext; }
 
+		/* --- buffers and images (reference: CL.h:26-38, CL.cpp:135-197, 714-753) */
 		template<typename T> cl_mem createBuffer( vector<T> object, size_t objectSize ) {
 			return this->createBufferFromPtr( object.empty() ? NULL : &object[0], objectSize );
 		}
-		/** Additive: same as createBuffer without the by-value vector copy. */
-		cl_mem createBufferFromPtr( const void* data, size_t objectSize );
-
+		cl_mem createBufferFromPtr( const void* data, size_t objectSize );      /* additive: no by-value vector */
 		cl_mem createEmptyBuffer( size_t size, int flags = 0 );
+		cl_mem updateBuffer( cl_mem buffer, size_t size, void* data );
 		cl_mem createImage2DReadOnly( size_t width, size_t height, cl_float* data );
 		cl_mem createImage2DWriteOnly( size_t width, size_t height );
+		cl_mem updateImageReadOnly( cl_mem image, size_t width, size_t height, cl_float* data );
+		void readImageOutput( cl_mem image, size_t width, size_t height, cl_float* outputTarget );
+		void freeBuffers();
+
+		/* --- program and kernel (reference: CL.cpp:205-217, 289-316, 554-571, 604-617) */
+		void setReplacement( string before, string after );
+		void loadProgram( string filepath );
 		cl_kernel createKernel( const char* functionName );
+		void setKernelArg( cl_kernel kernel, cl_uint index, size_t size, void* data );
 		void execute( cl_kernel kernel );
 		void finish();
-		void freeBuffers();
 		map<cl_kernel, string> getKernelNames();
 		map<cl_kernel, double> getKernelTimes();
-		void loadProgram( string filepath );
-		void readImageOutput( cl_mem image, size_t width, size_t height, cl_float* outputTarget );
-		void setKernelArg( cl_kernel kernel, cl_uint index, size_t size, void* data );
-		void setReplacement( string before, string after );
-		cl_mem updateBuffer( cl_mem buffer, size_t size, void* data );
-		cl_mem updateImageReadOnly( cl_mem image, size_t width, size_t height, cl_float* data );
 
-		/** Additive (see include/pbr_b200.h): device-side image copy, tiles, counters, pinned memory. */
-		void copyImage( cl_mem dst, cl_mem src );
+		/* --- additive (include/pbr_b200.h): batches, split read-back, device-side copy, row sharding, counters,
+		 *     pinned host memory */
+		void executeBatch( cl_kernel kernel, cl_uint frames, const cl_float* seeds, const cl_float* pixelWeights );
 		void readImageOutputBegin( cl_mem image, size_t width, size_t height, cl_float* outputTarget );
 		void readImageOutputEnd();
-		void executeBatch( cl_kernel kernel, cl_uint frames, const cl_float* seeds, const cl_float* pixelWeights );
+		void copyImage( cl_mem dst, cl_mem src );
 		void setTile( int y0, int y1 );
 		void setTileStripes( int stripeRows, int world, int rank );
 		void setDebugImage( bool enabled );
 		void getStats( uint64_t out[6], bool reset );
 		void* allocHost( size_t bytes );
 		void freeHost( void* ptr );
-		pbr_ctx* getContext() { return mContext; }
-		/** The device on which the next CL() is created (multi-GPU: one process per GPU). */
-		static void setDefaultDevice( int device ) { sDefaultDevice = device; }
 
 	protected:
 		bool checkError( int err, const char* functionName );
 		pbr_defines getValues();
 
 	private:
-		bool mDoCheckErrors;
-		cl_uint mWorkHeight;
-		cl_uint mWorkWidth;
 		pbr_ctx* mContext;
-
+		cl_uint mWorkWidth, mWorkHeight;
+		bool mDoCheckErrors;
 		vector<cl_kernel> mKernels;
 		map<cl_kernel, string> mKernelNames;
 		map<cl_kernel, double> mKernelTime;
-
 		static int sDefaultDevice;
-
 };
 
 #endif

@@ -1,5 +1,8 @@
 #include "Camera.h"
 
+using std::string;
+using std::vector;
+
 #include "qt/GLWidget.h"
 
 
@@ -18,50 +21,39 @@ Camera::Camera( GLWidget* parent ) {
  * rounded when stored.  Spelled out here with explicit doubles, so that the result does not depend on which
  * overloads a standard library happens to put into the global namespace (checked against the reference's own
  * Camera.cpp in tests/test_gpu_host.py::test_product_equals_reference_renderer). */
-void Camera::cameraMoveBackward() {
+void Camera::stepAlongView( double sign ) {
 	const double rx = MathHelp::degToRad( mCamera.rot.x ), ry = MathHelp::degToRad( mCamera.rot.y );
-	mCamera.eye.x -= sin( rx ) * cos( ry ) * mCameraSpeed;
-	mCamera.eye.y += sin( ry ) * mCameraSpeed;
-	mCamera.eye.z += cos( rx ) * cos( ry ) * mCameraSpeed;
+	const double fx = sin( rx ) * cos( ry ) * mCameraSpeed;
+	const double fy = sin( ry ) * mCameraSpeed;
+	const double fz = cos( rx ) * cos( ry ) * mCameraSpeed;
+	/* forward = ( +fx, -fy, -fz ); a - b and a + ( -b ) are the same binary64 sum, rounded once when stored */
+	mCamera.eye.x = (float) ( (double) mCamera.eye.x + sign * fx );
+	mCamera.eye.y = (float) ( (double) mCamera.eye.y - sign * fy );
+	mCamera.eye.z = (float) ( (double) mCamera.eye.z - sign * fz );
 	this->updateParent();
 }
 
 
-void Camera::cameraMoveDown() {
-	mCamera.eye.y -= mCameraSpeed;
-	this->updateParent();
-}
-
-
-void Camera::cameraMoveForward() {
-	const double rx = MathHelp::degToRad( mCamera.rot.x ), ry = MathHelp::degToRad( mCamera.rot.y );
-	mCamera.eye.x += sin( rx ) * cos( ry ) * mCameraSpeed;
-	mCamera.eye.y -= sin( ry ) * mCameraSpeed;
-	mCamera.eye.z -= cos( rx ) * cos( ry ) * mCameraSpeed;
-	this->updateParent();
-}
-
-
-void Camera::cameraMoveLeft() {
+void Camera::stepSideways( double sign ) {
 	const double rx = MathHelp::degToRad( mCamera.rot.x );
-	mCamera.eye.x -= cos( rx ) * mCameraSpeed;
-	mCamera.eye.z -= sin( rx ) * mCameraSpeed;
+	mCamera.eye.x = (float) ( (double) mCamera.eye.x + sign * ( cos( rx ) * mCameraSpeed ) );
+	mCamera.eye.z = (float) ( (double) mCamera.eye.z + sign * ( sin( rx ) * mCameraSpeed ) );
 	this->updateParent();
 }
 
 
-void Camera::cameraMoveRight() {
-	const double rx = MathHelp::degToRad( mCamera.rot.x );
-	mCamera.eye.x += cos( rx ) * mCameraSpeed;
-	mCamera.eye.z += sin( rx ) * mCameraSpeed;
+void Camera::stepVertically( float sign ) {
+	mCamera.eye.y += sign * mCameraSpeed;
 	this->updateParent();
 }
 
 
-void Camera::cameraMoveUp() {
-	mCamera.eye.y += mCameraSpeed;
-	this->updateParent();
-}
+void Camera::cameraMoveForward() { this->stepAlongView( 1.0 ); }
+void Camera::cameraMoveBackward() { this->stepAlongView( -1.0 ); }
+void Camera::cameraMoveRight() { this->stepSideways( 1.0 ); }
+void Camera::cameraMoveLeft() { this->stepSideways( -1.0 ); }
+void Camera::cameraMoveUp() { this->stepVertically( 1.0f ); }
+void Camera::cameraMoveDown() { this->stepVertically( -1.0f ); }
 
 
 /** Eye and center from the config; the center is used as a normalised direction (Camera.cpp:80-95). */

@@ -13,53 +13,49 @@
 #include "MathHelp.h"
 #include "glm_lite.h"
 
-using std::vector;
+class GLWidget;
 
-
+/* eye position; viewing direction as a unit offset (`center`, see getAdjustedCenter_glmVec3); rot in degrees */
 struct camera_t {
-	glm::vec3 eye;
-	glm::vec3 center;
-	glm::vec3 up;
-	glm::vec3 right;
+	glm::vec3 eye, center, up, right;
 	glm::vec2 rot;
 };
 
-
-class GLWidget;
-
-
 class Camera {
-
 	public:
-		Camera( GLWidget* parent );
-		void cameraMoveBackward();
-		void cameraMoveDown();
-		void cameraMoveForward();
-		void cameraMoveLeft();
-		void cameraMoveRight();
-		void cameraMoveUp();
+		explicit Camera( GLWidget* parent );
+
+		/* --- one step of getSpeed() along the view axes; cameraReset() re-reads camera.* from the config */
+		void cameraMoveForward();   void cameraMoveBackward();
+		void cameraMoveLeft();      void cameraMoveRight();
+		void cameraMoveUp();        void cameraMoveDown();
 		void cameraReset();
-		glm::vec3 getAdjustedCenter_glmVec3();
-		glm::vec3 getCenter_glmVec3();
-		vector<float> getEye();
+		void updateCameraRot( int moveX, int moveY );   /* mouse deltas in pixels = degrees */
+		void setEye( float x, float y, float z );       /* additive: headless drivers have no key events */
+
+		/* --- speed of the steps above */
+		float getSpeed();
+		void setSpeed( float speed );
+
+		/* --- what PathTracer::updateEyeBuffer and the overlay read */
 		glm::vec3 getEye_glmVec3();
+		std::vector<float> getEye();
+		glm::vec3 getCenter_glmVec3();
+		glm::vec3 getAdjustedCenter_glmVec3();          /* ( eye.x + c.x, eye.y - c.y, eye.z - c.z ) */
+		glm::vec3 getUp_glmVec3();
 		float getRotX();
 		float getRotY();
-		float getSpeed();
-		glm::vec3 getUp_glmVec3();
-		void setSpeed( float speed );
-		void updateCameraRot( int moveX, int moveY );
-		/** Additive: place the eye directly (headless drivers have no key events). */
-		void setEye( float x, float y, float z );
 
 	protected:
 		void updateParent();
+		void stepAlongView( double sign );
+		void stepSideways( double sign );
+		void stepVertically( float sign );
 
 	private:
-		GLWidget* mParent;
-		float mCameraSpeed;
 		camera_t mCamera;
-
+		float mCameraSpeed;
+		GLWidget* mParent;
 };
 
 #endif

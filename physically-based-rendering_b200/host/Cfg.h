@@ -42,42 +42,15 @@ class Cfg {
 			mValues[key] = os.str();
 		}
 
-		static const char* ACCEL_STRUCT;
-		static const char* BVH_MAXFACES;
-		static const char* BVH_SAHFACESLIMIT;
-		static const char* BVH_SKIPAHEAD;
-		static const char* BVH_SKIPAHEAD_CMP;
-		static const char* CAM_CENTER_X;
-		static const char* CAM_CENTER_Y;
-		static const char* CAM_CENTER_Z;
-		static const char* CAM_EYE_X;
-		static const char* CAM_EYE_Y;
-		static const char* CAM_EYE_Z;
-		static const char* CAM_LENSE_APERTURE;
-		static const char* CAM_LENSE_FOCALLENGTH;
-		static const char* CAM_SPEED;
-		static const char* IMPORT_PATH;
-		static const char* INFO_KERNELTIMES;
-		static const char* LOG_LEVEL;
-		static const char* OPENCL_BUILDOPTIONS;
-		static const char* OPENCL_CHECKERRORS;
-		static const char* OPENCL_LOCALGROUPSIZE;
-		static const char* OPENCL_PROGRAM;
-		static const char* PERS_FOV;
-		static const char* PERS_ZFAR;
-		static const char* PERS_ZNEAR;
-		static const char* RENDER_ANTIALIAS;
-		static const char* RENDER_BRDF;
-		static const char* RENDER_INTERVAL;
-		static const char* RENDER_MAXADDEDDEPTH;
-		static const char* RENDER_MAXDEPTH;
-		static const char* RENDER_PHONGTESS;
-		static const char* RENDER_SAMPLES;
-		static const char* RENDER_SHADOWRAYS;
-		static const char* SHADER_NAME;
-		static const char* SHADER_PATH;
-		static const char* WINDOW_HEIGHT;
-		static const char* WINDOW_WIDTH;
+		/* the dotted keys of config.json (Cfg.cpp:4-39) */
+		static const char *ACCEL_STRUCT, *IMPORT_PATH, *INFO_KERNELTIMES, *LOG_LEVEL;
+		static const char *BVH_MAXFACES, *BVH_SAHFACESLIMIT, *BVH_SKIPAHEAD, *BVH_SKIPAHEAD_CMP;
+		static const char *CAM_EYE_X, *CAM_EYE_Y, *CAM_EYE_Z, *CAM_CENTER_X, *CAM_CENTER_Y, *CAM_CENTER_Z;
+		static const char *CAM_LENSE_APERTURE, *CAM_LENSE_FOCALLENGTH, *CAM_SPEED, *PERS_FOV, *PERS_ZFAR, *PERS_ZNEAR;
+		static const char *OPENCL_BUILDOPTIONS, *OPENCL_CHECKERRORS, *OPENCL_LOCALGROUPSIZE, *OPENCL_PROGRAM;
+		static const char *RENDER_ANTIALIAS, *RENDER_BRDF, *RENDER_INTERVAL, *RENDER_MAXADDEDDEPTH, *RENDER_MAXDEPTH;
+		static const char *RENDER_PHONGTESS, *RENDER_SAMPLES, *RENDER_SHADOWRAYS;
+		static const char *SHADER_NAME, *SHADER_PATH, *WINDOW_HEIGHT, *WINDOW_WIDTH;
 
 	private:
 		Cfg() { loadDefaults(); }

@@ -1,5 +1,8 @@
 #include "LightParser.h"
 
+using std::string;
+using std::vector;
+
 #include <fstream>
 #include <sstream>
 

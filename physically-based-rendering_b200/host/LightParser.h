@@ -12,33 +12,23 @@
 #include "cl_types.h"
 #include "Logger.h"
 
-using std::string;
-using std::vector;
-
-// Light types:
-// 1: Point light
-// 2: Orb light
 struct light_t {
-	string lightName;
-	cl_uint type;
-	cl_float4 pos;
-	cl_float4 rgb;
+	std::string lightName;
+	cl_uint type;                /* 1 point light, 2 orb light */
+	cl_float4 pos, rgb;
 	cl_float radius;
 };
 
-
 class LightParser {
-
 	public:
-		vector<light_t> getLights();
-		void load( string file );
-		/** Additive: install lights that were not read from a file (synthetic scenes). */
-		void setLights( const vector<light_t>& lights );
+		void load( std::string file );
+		std::vector<light_t> getLights();
 		static light_t getEmptyLight();
+		/** Additive: install lights that were not read from a file (synthetic scenes). */
+		void setLights( const std::vector<light_t>& lights );
 
 	private:
-		vector<light_t> mLights;
-
+		std::vector<light_t> mLights;
 };
 
 #endif

@@ -12,26 +12,27 @@
 
 #define LOG_INDENT 4
 
-class Logger {
+/* Every level comes as a (const char*) and a (std::string) overload, like upstream. */
+#define PBR_LOGGER_LEVEL( name ) \
+	static void name( const char* msg, const char* prefix = "* " ); \
+	static void name( std::string msg, const char* prefix = "* " );
 
+class Logger {
 	public:
+		PBR_LOGGER_LEVEL( logError )
+		PBR_LOGGER_LEVEL( logWarning )
+		PBR_LOGGER_LEVEL( logInfo )
+		PBR_LOGGER_LEVEL( logDebug )
+		PBR_LOGGER_LEVEL( logDebugVerbose )
+
+		static int indent( int indent );     /* set the indentation of the following lines; returns it */
 		static int getIndent();
-		static int indent( int indent );
-		static void logDebug( const char* msg, const char* prefix = "* " );
-		static void logDebug( std::string msg, const char* prefix = "* " );
-		static void logDebugVerbose( const char* msg, const char* prefix = "* " );
-		static void logDebugVerbose( std::string msg, const char* prefix = "* " );
-		static void logError( const char* msg, const char* prefix = "* " );
-		static void logError( std::string msg, const char* prefix = "* " );
-		static void logInfo( const char* msg, const char* prefix = "* " );
-		static void logInfo( std::string msg, const char* prefix = "* " );
-		static void logWarning( const char* msg, const char* prefix = "* " );
-		static void logWarning( std::string msg, const char* prefix = "* " );
 
 	private:
 		static void emit( int minLevel, const char* color, const char* msg, const char* prefix );
 		static int mIndent;
-
 };
+
+#undef PBR_LOGGER_LEVEL
 
 #endif

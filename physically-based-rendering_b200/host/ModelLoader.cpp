@@ -1,5 +1,8 @@
 #include "ModelLoader.h"
 
+using std::string;
+using std::vector;
+
 
 ModelLoader::ModelLoader() {
 	mObjParser = new ObjParser();
@@ -11,26 +14,29 @@ ModelLoader::~ModelLoader() {
 }
 
 
-/**
- * The faces of one object as (v0, v1, v2, global face index); the global index is
- * `offset + position in the object` (reference: ModelLoader.cpp:28-41).
- */
-void ModelLoader::getFacesOfObject( const object3D& object, vector<cl_uint4>* faces, cl_int offset ) {
-	faces->reserve( faces->size() + object.facesV.size() / 3 );
-	for( size_t i = 0; i + 2 < object.facesV.size(); i += 3 ) {
-		cl_uint4 f = { object.facesV[i], object.facesV[i + 1], object.facesV[i + 2], (cl_uint) ( offset + (cl_int) faces->size() ) };
-		faces->push_back( f );
+namespace {
+
+/* Index triples of one object -> ( i0, i1, i2, offset + running count of `out` ). */
+void appendTriples( const vector<cl_uint>& triples, vector<cl_uint4>* out, cl_int offset ) {
+	out->reserve( out->size() + triples.size() / 3 );
+	for( size_t i = 0; i + 2 < triples.size(); i += 3 ) {
+		cl_uint4 entry = { triples[i], triples[i + 1], triples[i + 2], (cl_uint) ( offset + (cl_int) out->size() ) };
+		out->push_back( entry );
 	}
+}
+
+}
+
+
+/** The faces of one object with their scene-wide face number in .w (reference: ModelLoader.cpp:28-41). */
+void ModelLoader::getFacesOfObject( const object3D& object, vector<cl_uint4>* faces, cl_int offset ) {
+	appendTriples( object.facesV, faces, offset );
 }
 
 
 /** Same for the normal indices (reference: ModelLoader.cpp:44-57). */
 void ModelLoader::getFaceNormalsOfObject( const object3D& object, vector<cl_uint4>* faceNormals, cl_int offset ) {
-	faceNormals->reserve( faceNormals->size() + object.facesVN.size() / 3 );
-	for( size_t i = 0; i + 2 < object.facesVN.size(); i += 3 ) {
-		cl_uint4 fn = { object.facesVN[i], object.facesVN[i + 1], object.facesVN[i + 2], (cl_uint) ( offset + (cl_int) faceNormals->size() ) };
-		faceNormals->push_back( fn );
-	}
+	appendTriples( object.facesVN, faceNormals, offset );
 }
 
 

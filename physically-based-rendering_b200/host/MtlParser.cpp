@@ -1,5 +1,8 @@
 #include "MtlParser.h"
 
+using std::string;
+using std::vector;
+
 #include <fstream>
 #include <sstream>
 

@@ -13,43 +13,26 @@
 #include "cl_types.h"
 #include "Logger.h"
 
-using std::string;
-using std::vector;
-
 struct material_t {
-	string mtlName;
-	cl_float4 Ka;
-	cl_float4 Kd;
-	cl_float4 Ks;
-	cl_float d;
-	cl_float Ni;
-	cl_float Ns;
+	std::string mtlName;
+	cl_float4 Ka, Kd, Ks;        /* ambient (unused by the kernel), diffuse, specular colour */
+	cl_float d, Ni, Ns;          /* opacity, index of refraction, Phong exponent (unused) */
 	cl_char illum;
-	// Light source yes/no
-	cl_char light;
-	// BRDF: Schlick
-	cl_float rough;
-	cl_float p;
-	// BRDF: Shirley-Ashikhmin
-	cl_float nu;
-	cl_float nv;
-	cl_float Rs;
-	cl_float Rd;
+	cl_char light;               /* 1 = emitter; parsed, ignored by the kernel */
+	cl_float rough, p;           /* Schlick: roughness, isotropy */
+	cl_float nu, nv, Rs, Rd;     /* Shirley-Ashikhmin: lobe exponents, specular / diffuse weight */
 };
 
-
 class MtlParser {
-
 	public:
-		vector<material_t> getMaterials();
-		void load( string file );
+		void load( std::string file );
+		std::vector<material_t> getMaterials();
+		static material_t getEmptyMaterial();           /* the defaults of MtlParser.cpp:11-36 */
 		/** Additive: install materials that were not read from a file (synthetic scenes). */
-		void setMaterials( const vector<material_t>& materials );
-		static material_t getEmptyMaterial();
+		void setMaterials( const std::vector<material_t>& materials );
 
 	private:
-		vector<material_t> mMaterials;
-
+		std::vector<material_t> mMaterials;
 };
 
 #endif

@@ -19,46 +19,45 @@
 
 #include "cl_types.h"
 #include "Logger.h"
-#include "MtlParser.h"
 #include "LightParser.h"
+#include "MtlParser.h"
 
 using std::string;
 using std::vector;
 
-
+/* one `o` block: its triangles as flat index triples (vertex indices, normal indices) */
 struct object3D {
 	string oName;
-	vector<cl_uint> facesV;
-	vector<cl_uint> facesVN;
+	vector<cl_uint> facesV, facesVN;
 };
 
-
 class ObjParser {
-
 	public:
 		ObjParser();
 		~ObjParser();
 		void load( string filepath, string filename );
-		vector<cl_int> getFacesMtl();
+
+		/* --- the reference's accessors: copies, as upstream */
+		vector<cl_float> getVertices();
+		vector<cl_float> getNormals();
+		vector<cl_float> getTextureCoordinates();
 		vector<cl_uint> getFacesV();
 		vector<cl_uint> getFacesVN();
 		vector<cl_uint> getFacesVT();
-		vector<light_t> getLights();
-		vector<material_t> getMaterials();
-		vector<cl_float> getNormals();
+		vector<cl_int> getFacesMtl();
 		vector<object3D> getObjects();
-		vector<cl_float> getTextureCoordinates();
-		vector<cl_float> getVertices();
+		vector<material_t> getMaterials();
+		vector<light_t> getLights();
 
-		/** Additive: reference-free access for large scenes (the reference returns copies). */
-		const vector<cl_int>& facesMtl() const { return mFacesMtl; }
+		/* --- additive: the same arrays by reference (large scenes) */
+		const vector<cl_float>& vertices() const { return mVertices; }
+		const vector<cl_float>& normals() const { return mNormals; }
 		const vector<cl_uint>& facesV() const { return mFacesV; }
 		const vector<cl_uint>& facesVN() const { return mFacesVN; }
-		const vector<cl_float>& normals() const { return mNormals; }
-		const vector<cl_float>& vertices() const { return mVertices; }
+		const vector<cl_int>& facesMtl() const { return mFacesMtl; }
 		const vector<object3D>& objects() const { return mObjects; }
 
-		/** Additive: install an already parsed scene (synthetic generators, tests). */
+		/* --- additive: install an already parsed scene (synthetic generators, tests) */
 		void setScene(
 			const vector<cl_float>& vertices, const vector<cl_float>& normals,
 			const vector<cl_uint>& facesV, const vector<cl_uint>& facesVN, const vector<cl_int>& facesMtl,
@@ -66,22 +65,16 @@ class ObjParser {
 		);
 
 	protected:
-		void loadLights( string file );
 		void loadMtl( string file );
+		void loadLights( string file );
 
 	private:
-		LightParser* mLightParser;
-		MtlParser* mMtlParser;
-
-		vector<object3D> mObjects;
+		vector<cl_float> mVertices, mNormals, mTextures;
+		vector<cl_uint> mFacesV, mFacesVN, mFacesVT;
 		vector<cl_int> mFacesMtl;
-		vector<cl_uint> mFacesV;
-		vector<cl_uint> mFacesVN;
-		vector<cl_uint> mFacesVT;
-		vector<cl_float> mNormals;
-		vector<cl_float> mTextures;
-		vector<cl_float> mVertices;
-
+		vector<object3D> mObjects;
+		MtlParser* mMtlParser;
+		LightParser* mLightParser;
 };
 
 #endif

@@ -147,7 +147,8 @@ int pbr_kernel_launch_batch(pbr_ctx* ctx, pbr_kernel k, int32_t n_frames, const 
 /* Scheduling knobs (never change a pixel): "node_phase_min", "refill_min" (traversal engine), "persist_t",
  * "persist_s" (blocks per SM of the two persistent kernels, persist_t 0 = what fits), "persist_fill",
  * "tail_steps_bulk", "tail_steps_flush", "flush_group" (carry-over wavefront), "batch_interleave",
- * "traverse_blocks" (cap on resident traverse blocks per SM, 0 = all that fit).
+ * "traverse_blocks" (cap on resident traverse blocks per SM, 0 = all that fit), "shadow_stage" (1: shadow rays are a
+ * wavefront stage of their own, walked by the traversal engine; 0: inside the shade kernel).
  * The environment variables PBR_NODE_PHASE_MIN, PBR_REFILL_MIN, PBR_PERSIST_T/_S/_FILL, PBR_PIPELINE set
  * the initial values.  Stands where opencl.localgroupsize stands in the reference's config.json. */
 int pbr_set_tuning(pbr_ctx* ctx, const char* key, int32_t value);

@@ -90,6 +90,12 @@ struct pbr_ctx {
 	float4* hitN = nullptr;                    /* allocated with the wave state, used when PHONGTESS */
 	QueueCtl qctl = {nullptr, {nullptr, nullptr}};
 	size_t waveCap = 0;
+	/* shadow rays as a wavefront stage (render.shadow_rays): ray per path, queue; qctl.ctrl[3] count, [4] cursor */
+	float4* shadowO = nullptr;
+	float4* shadowD = nullptr;
+	uint32_t* shadowQ = nullptr;
+	size_t shadowCap = 0;
+	int shadowStage = 1;                       /* tuning "shadow_stage": 0 = walk shadow rays inside the shade kernel */
 
 	/* carry-over wavefront (pipeline 3): resume nodes, hit queue, two carry queues, counters, host mailbox */
 	int* waveNode = nullptr;
@@ -322,6 +328,19 @@ int ensureWave(pbr_ctx* ctx, size_t nPaths) {
 	return PBR_OK;
 }
 
+int ensureShadow(pbr_ctx* ctx, size_t nPaths) {
+	if (nPaths <= ctx->shadowCap) return PBR_OK;
+	cudaFree(ctx->shadowO); cudaFree(ctx->shadowD); cudaFree(ctx->shadowQ);
+	ctx->shadowO = ctx->shadowD = nullptr;
+	ctx->shadowQ = nullptr;
+	ctx->shadowCap = 0;
+	CK(cudaMalloc(&ctx->shadowO, nPaths * 16));
+	CK(cudaMalloc(&ctx->shadowD, nPaths * 16));
+	CK(cudaMalloc(&ctx->shadowQ, nPaths * 4));
+	ctx->shadowCap = nPaths;
+	return PBR_OK;
+}
+
 int ensureRings(pbr_ctx* ctx, size_t nPaths) {
 	if (nPaths <= ctx->ringCap / 2 && ctx->pctl) return PBR_OK;
 	size_t cap = 1024;
@@ -530,6 +549,16 @@ int runWavefront(pbr_ctx* ctx, const FrameParams& P, WaveState W, int nPaths) {
 	const int gridT = ctx->smCount * (occT > 0 ? occT : 1);
 	const int gridS = ctx->smCount * (occS > 0 ? occS : 1);
 
+	/* shadow rays through the traversal engine instead of one thread per path inside the shade kernel */
+	const bool shadowStage = SHADOW && P.scene.numLights > 0 && ctx->shadowStage != 0;
+	int gridG = 0;
+	if (shadowStage) {
+		int rc = ensureShadow(ctx, (size_t) nPaths);
+		if (rc) return rc;
+		int occG = 0;
+		CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occG, shadowGenKernel<BRDF, PHONG>, 128, 0));
+		gridG = ctx->smCount * (occG > 0 ? occG : 1);
+	}
 	{
 		LaunchScope ls(ctx, K_RAYGEN);
 		raygenKernel<<<ctx->smCount * 8, 256, 0, ctx->stream>>>(P, W, Q, nPaths);
@@ -547,7 +576,24 @@ int runWavefront(pbr_ctx* ctx, const FrameParams& P, WaveState W, int nPaths) {
 			traverseKernel<PHONG><<<gridT, 128, 0, ctx->stream>>>(P.scene, W, qIn, Q.ctrl + in, Q.ctrl + 2, Q.ctrl + out, ctx->stats);
 		}
 		if (dump) cudaEventRecord(e1, ctx->stream);
-		{
+		if (shadowStage) {
+			{
+				LaunchScope ls(ctx, K_SHADE);
+				shadowGenKernel<BRDF, PHONG><<<gridG, 128, 0, ctx->stream>>>(
+					P, W, qIn, Q.ctrl + in, ctx->shadowO, ctx->shadowD, ctx->shadowQ, Q.ctrl + 3);
+			}
+			{
+				LaunchScope ls(ctx, K_TRAVERSE);
+				traverseShadowKernel<PHONG><<<gridT, 128, 0, ctx->stream>>>(
+					P.scene, W, ctx->shadowO, ctx->shadowD, ctx->shadowQ, Q.ctrl + 3, Q.ctrl + 4, ctx->stats);
+			}
+			{
+				LaunchScope ls(ctx, K_SHADE);
+				shadeKernel<BRDF, SHADOW, PHONG, true><<<gridS, 128, 0, ctx->stream>>>(
+					P, W, qIn, Q.ctrl + in, Q.queue[out], Q.ctrl + out, Q.ctrl + 2, Q.ctrl + 3, Q.ctrl + 4, ctx->shadowO);
+			}
+		}
+		else {
 			LaunchScope ls(ctx, K_SHADE);
 			shadeKernel<BRDF, SHADOW, PHONG><<<gridS, 128, 0, ctx->stream>>>(P, W, qIn, Q.ctrl + in, Q.queue[out], Q.ctrl + out, Q.ctrl + 2);
 		}
@@ -559,7 +605,7 @@ int runWavefront(pbr_ctx* ctx, const FrameParams& P, WaveState W, int nPaths) {
 			float tMs = 0.0f, sMs = 0.0f;
 			cudaEventElapsedTime(&tMs, e0, e1);
 			cudaEventElapsedTime(&sMs, e1, e2);
-			fprintf(stderr, "[wavefront] it %3d  traverse %7.3f ms  shade %7.3f ms  alive after %u\n", it, tMs, sMs, c[out]);
+			fprintf(stderr, "[wavefront] it %3d  traverse %7.3f ms  shade%s %7.3f ms  alive after %u\n", it, tMs, shadowStage ? " + shadow stage" : "", sMs, c[out]);
 		}
 	}
 	if (dump) { cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2); }
@@ -634,12 +680,12 @@ int pbr_create(int device, pbr_ctx** out) {
 	cudaEventCreate(&ctx->evStop);
 	if (cudaMalloc(&ctx->stats, 6 * sizeof(unsigned long long)) != cudaSuccess ||
 	    cudaMalloc(&ctx->cursor64, sizeof(unsigned long long)) != cudaSuccess ||
-	    cudaMalloc(&ctx->qctl.ctrl, 4 * sizeof(uint32_t)) != cudaSuccess) {
+	    cudaMalloc(&ctx->qctl.ctrl, 8 * sizeof(uint32_t)) != cudaSuccess) {
 		delete ctx;
 		return PBR_ERR_NO_DEVICE;
 	}
 	cudaMemset(ctx->stats, 0, 6 * sizeof(unsigned long long));
-	cudaMemset(ctx->qctl.ctrl, 0, 4 * sizeof(uint32_t));
+	cudaMemset(ctx->qctl.ctrl, 0, 8 * sizeof(uint32_t));
 	if (const char* e = getenv("PBR_NODE_PHASE_MIN")) {
 		const int v = atoi(e);
 		if (v >= 1 && v <= 32) ctx->nodePhaseMin = v;
@@ -669,6 +715,7 @@ int pbr_destroy(pbr_ctx* ctx) {
 	cudaFree(W.rayO); cudaFree(W.rayD); cudaFree(W.colS); cudaFree(W.finF); cudaFree(W.misc); cudaFree(W.dbg); cudaFree(ctx->hitN);
 	cudaFree(ctx->qctl.queue[0]); cudaFree(ctx->qctl.queue[1]); cudaFree(ctx->qctl.ctrl);
 	cudaFree(ctx->stats); cudaFree(ctx->cursor64);
+	cudaFree(ctx->shadowO); cudaFree(ctx->shadowD); cudaFree(ctx->shadowQ);
 	cudaFree(ctx->pctl); cudaFree(ctx->ring[0]); cudaFree(ctx->ring[1]);
 	cudaFree(ctx->waveNode); cudaFree(ctx->hitQ); cudaFree(ctx->carryQ[0]); cudaFree(ctx->carryQ[1]); cudaFree(ctx->cctl);
 	if (ctx->mailbox) cudaFreeHost(ctx->mailbox);
@@ -1124,6 +1171,7 @@ int pbr_set_tuning(pbr_ctx* ctx, const char* key, int32_t value) {
 	else if (k == "flush_group" && value >= 1 && value <= 64) ctx->flushGroup = value;
 	else if (k == "batch_interleave" && (value == 0 || value == 1)) ctx->batchInterleave = value;
 	else if (k == "traverse_blocks" && value >= 0 && value <= 32) ctx->traverseBlocks = value;
+	else if (k == "shadow_stage" && (value == 0 || value == 1)) ctx->shadowStage = value;
 	else return fail(ctx, PBR_ERR_INVALID, "pbr_set_tuning: unknown key or value out of range: " + k);
 	return PBR_OK;
 }

@@ -960,8 +960,16 @@ __device__ __forceinline__ void endSampleWithLight(PathState& s, const vec3 ligh
 /* The body of the depth loop after traverse() (pathtracing.cl:261-317).  On PATH_CONTINUE the
  * state holds the next ray (t = INFINITY, hitFace = 0) and depth has been advanced and checked
  * against MAX_DEPTH + depthAdded.  On PATH_SAMPLE_DONE the sample's light has been applied. */
-template <int BRDF, bool SHADOW, bool PHONG>
-__device__ __forceinline__ BounceResult bounce(const FrameParams& P, PathState& s, uint32_t& shadowNodes, uint32_t& shadowRays) {
+/* The part of the depth loop's body between traverse() and the shadow ray (pathtracing.cl:261-278): miss -> the
+ * sample ends with the sky or an orb light; otherwise material, extendDepth, the "last round" exit, seed += t.
+ * Shared by bounce() and by the kernel that generates the shadow rays of a wavefront (which runs it on a copy of
+ * the path state), so that both take exactly the same decisions. */
+enum PrefixResult { PREFIX_SAMPLE_DONE = 0, PREFIX_HIT = 1 };
+
+template <int BRDF, bool PHONG>
+__device__ __forceinline__ PrefixResult bouncePrefix(
+	const FrameParams& P, PathState& s, Material& mtl, vec3& normal, bool& addDepth, vec3& hitPoint
+) {
 	const SceneDev& S = P.scene;
 
 	s.focus = (s.sample + s.depth == 0) ? s.t : s.focus;
@@ -969,11 +977,10 @@ __device__ __forceinline__ BounceResult bounce(const FrameParams& P, PathState& 
 	if (s.t == PM_INF_F) {
 		const vec3 light = (s.hitFace < 0) ? p4xyz(S.lights[-(s.hitFace + 1)].rgb) : v3(P.skyLight.x, P.skyLight.y, P.skyLight.z);
 		endSampleWithLight(s, light);
-		return PATH_SAMPLE_DONE;
+		return PREFIX_SAMPLE_DONE;
 	}
 
 	uint32_t mtlIndex;
-	vec3 normal;
 	if (PHONG) {
 		mtlIndex = (uint32_t) __float_as_int(__ldg(S.tris + PT_TRI_STRIDE_PHONG * (size_t) s.hitFace).w);
 		normal = s.hitNormal;
@@ -984,36 +991,62 @@ __device__ __forceinline__ BounceResult bounce(const FrameParams& P, PathState& 
 		mtlIndex = (uint32_t) __float_as_int(A.w);
 		normal = pm::normalize(pm::cross(f4xyz(E1), f4xyz(E2)));
 	}
-	const Material mtl = fetchMaterial<BRDF>(P.materials, P.numMaterials, mtlIndex);
+	mtl = fetchMaterial<BRDF>(P.materials, P.numMaterials, mtlIndex);
 
 	/* extendDepth (pt_utils.cl:89-96) */
-	bool addDepth;
 	if (BRDF == 1) addDepth = (fmaxf(mtl.a2, mtl.a3) >= 50.0f);
 	else addDepth = (mtl.a3 < rnd(s.seed));
 
 	if (mtl.d == 1.0f && !addDepth && s.depth == (uint32_t) (P.maxDepth + s.depthAdded - 1)) {
-		return PATH_SAMPLE_DONE;
+		return PREFIX_SAMPLE_DONE;
 	}
 
 	s.seed += s.t;
 
-	const vec3 hitPoint = pm::fma3(s.d, s.t, s.o);
+	hitPoint = pm::fma3(s.d, s.t, s.o);
+	return PREFIX_HIT;
+}
+
+/* Does this hit send a shadow ray (pathtracing.cl:282-288), and which one (shadowRayTest, :188-192)? */
+__device__ __forceinline__ bool shadowRayOf(const SceneDev& S, const Material& mtl, const vec3 hitPoint, vec3& lightDir, float& tLight) {
+	if (!(S.numLights > 0 && mtl.d > 0.0f)) return false;
+	const vec3 toLight = p4xyz(S.lights[0].pos) - hitPoint;
+	lightDir = pm::normalize(toLight);
+	tLight = pm::length(toLight);
+	return true;
+}
+
+/* SHADOW_PRE: the shadow ray of this hit was walked by a separate launch; `shadowT` is its ray.t afterwards. */
+template <int BRDF, bool SHADOW, bool PHONG, bool SHADOW_PRE = false>
+__device__ __forceinline__ BounceResult bounce(
+	const FrameParams& P, PathState& s, uint32_t& shadowNodes, uint32_t& shadowRays, const float shadowT = 0.0f
+) {
+	const SceneDev& S = P.scene;
+	Material mtl;
+	vec3 normal, hitPoint;
+	bool addDepth;
+	if (bouncePrefix<BRDF, PHONG>(P, s, mtl, normal, addDepth, hitPoint) == PREFIX_SAMPLE_DONE) {
+		return PATH_SAMPLE_DONE;
+	}
 
 	/* shadowRayTest (pathtracing.cl:188-199) */
 	bool lit = false;
 	vec3 lightDir = v3(0.0f, 0.0f, 0.0f);
 	vec3 lightRgb = v3(-1.0f, -1.0f, -1.0f);
 	if (SHADOW) {
-		if (S.numLights > 0 && mtl.d > 0.0f) {
-			const vec3 toLight = p4xyz(S.lights[0].pos) - hitPoint;
-			lightDir = pm::normalize(toLight);
-			const float tLight = pm::length(toLight);
+		float tLight;
+		if (shadowRayOf(S, mtl, hitPoint, lightDir, tLight)) {
 			float lt = tLight;
-			int lf = 0, ll = -1;
-			uint32_t nn = 0;
-			traverseAny<PHONG>(S, hitPoint, lightDir, lt, lf, ll, nn, s.nTris);
-			shadowNodes += nn;
-			shadowRays++;
+			if (SHADOW_PRE) {
+				lt = shadowT;
+			}
+			else {
+				int lf = 0, ll = -1;
+				uint32_t nn = 0;
+				traverseAny<PHONG>(S, hitPoint, lightDir, lt, lf, ll, nn, s.nTris);
+				shadowNodes += nn;
+				shadowRays++;
+			}
 			if (lt >= tLight) {
 				lightRgb = p4xyz(S.lights[0].rgb);
 				lit = true;

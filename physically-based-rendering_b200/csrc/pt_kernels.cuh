@@ -484,11 +484,12 @@ __global__ void __launch_bounds__(256) raygenCarryKernel(const FrameParams P, co
 
 /* ------------------------------------------------------------------ shade */
 
-template <int BRDF, bool SHADOW, bool PHONG>
+/* SHADOW_PRE: the shadow rays of this wavefront were walked by traverseShadowKernel; shadowO[p].w is the result. */
+template <int BRDF, bool SHADOW, bool PHONG, bool SHADOW_PRE = false>
 __global__ void __launch_bounds__(128) shadeKernel(
 	const FrameParams P, const WaveState W, const uint32_t* __restrict__ queueIn, const uint32_t* __restrict__ countInPtr,
 	uint32_t* __restrict__ queueOut, uint32_t* countOutPtr, uint32_t* cursorToReset,
-	uint32_t* reset1 = nullptr, uint32_t* reset2 = nullptr
+	uint32_t* reset1 = nullptr, uint32_t* reset2 = nullptr, const float4* __restrict__ shadowO = nullptr
 ) {
 	const uint32_t count = *countInPtr;
 	const uint32_t stride = gridDim.x * blockDim.x;
@@ -509,7 +510,9 @@ __global__ void __launch_bounds__(128) shadeKernel(
 
 			if (s.t != PM_INF_F) shaded++;
 			const uint32_t nTrisIn = s.nTris;
-			const BounceResult r = bounce<BRDF, SHADOW, PHONG>(P, s, shadowNodes, shadowRays);
+			const BounceResult r = SHADOW_PRE
+				? bounce<BRDF, SHADOW, PHONG, true>(P, s, shadowNodes, shadowRays, shadowO[p].w)
+				: bounce<BRDF, SHADOW, PHONG, false>(P, s, shadowNodes, shadowRays);
 			trisAfter += s.nTris - nTrisIn;                /* shadow-ray triangle tests (advancePath may reset nTris) */
 			alive = advancePath(P, s, r, px, py);
 			if (alive) {
@@ -537,6 +540,81 @@ __global__ void __launch_bounds__(128) shadeKernel(
 		warpAddStat(P.stats + 5, shadowNodes);
 		warpAddStat(P.stats + 3, trisAfter);
 	}
+}
+
+/* ------------------------------------------------------------------ shadow rays as their own wavefront stage */
+
+/*
+ * With render.shadow_rays the reference shoots one shadow ray per hit from inside the bounce
+ * (pathtracing.cl:282-288).  Walked inside the shade kernel, one thread per path, those rays run at the lane
+ * utilisation of a plain per-thread loop (and double the frame time of the interior scene).  Instead:
+ *     shadowGenKernel       per hit path: the bounce's prefix on a COPY of the path state decides whether a shadow
+ *                           ray leaves this hit and which one (bouncePrefix + shadowRayOf: the same code bounce()
+ *                           runs); ray -> shadowO / shadowD, path -> shadow queue
+ *     traverseShadowKernel  the traversal engine in any-hit mode over that queue (traverseShadows, pt_bvh.cl:133-177);
+ *                           result ray.t -> shadowO[p].w, its triangle tests -> the path's debug counter
+ *     shadeKernel<.., SHADOW_PRE>  the bounce with the walked result plugged in
+ */
+template <int BRDF, bool PHONG>
+__global__ void __launch_bounds__(128) shadowGenKernel(
+	const FrameParams P, const WaveState W, const uint32_t* __restrict__ queueIn, const uint32_t* __restrict__ countInPtr,
+	float4* __restrict__ shadowO, float4* __restrict__ shadowD, uint32_t* __restrict__ shadowQ, uint32_t* shadowCount
+) {
+	const uint32_t count = *countInPtr;
+	const uint32_t stride = gridDim.x * blockDim.x;
+	const uint32_t countUp = (count + 31u) & ~31u;
+	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < countUp; i += stride) {
+		bool shoot = false;
+		uint32_t p = 0;
+		if (i < count) {
+			p = queueIn ? queueIn[i] : i;
+			PathState s;
+			loadPath(W, p, s);
+			Material mtl;
+			vec3 normal, hitPoint, lightDir;
+			bool addDepth;
+			float tLight;
+			if (bouncePrefix<BRDF, PHONG>(P, s, mtl, normal, addDepth, hitPoint) == PREFIX_HIT &&
+			    shadowRayOf(P.scene, mtl, hitPoint, lightDir, tLight)) {
+				shadowO[p] = make_float4(hitPoint.x, hitPoint.y, hitPoint.z, tLight);
+				shadowD[p] = make_float4(lightDir.x, lightDir.y, lightDir.z, 0.0f);
+				shoot = true;
+			}
+		}
+		queueAppend(shadowQ, shadowCount, shoot, p);
+	}
+}
+
+struct ShadowRaySource {
+	const WaveState& W;
+	float4* shadowO;
+	const float4* shadowD;
+	const uint32_t* queue;
+	uint32_t p;
+	__device__ __forceinline__ void fetch(uint32_t i, vec3& o, vec3& d, float& rt, int& hf) {
+		p = queue[i];
+		const float4 a = shadowO[p], b = shadowD[p];
+		o = v3(a.x, a.y, a.z); rt = a.w;
+		d = v3(b.x, b.y, b.z); hf = 0;
+	}
+	__device__ __forceinline__ void store(uint32_t, const LaneRay& L) {
+		shadowO[p].w = L.rt;
+		W.dbg[p].y += L.nt;                 /* shadow-ray face tests count into debugColor.x; node visits do not */
+	}
+};
+
+template <bool PHONG>
+__global__ void __launch_bounds__(128) traverseShadowKernel(
+	const SceneDev S, const WaveState W, float4* shadowO, const float4* __restrict__ shadowD,
+	const uint32_t* __restrict__ shadowQ, const uint32_t* __restrict__ countPtr, uint32_t* cursor, unsigned long long* stats
+) {
+	const uint32_t count = *countPtr;
+	uint32_t nodes = 0, tris = 0, rays = 0;
+	ShadowRaySource src = {W, shadowO, shadowD, shadowQ, 0u};
+	traverseEngine<true, PHONG>(S, src, count, cursor, nodes, tris, rays);
+	warpAddStat(stats + 1, rays);
+	warpAddStat(stats + 5, nodes);
+	warpAddStat(stats + 3, tris);
 }
 
 /* ------------------------------------------------------------------ megakernel (cross-check) */

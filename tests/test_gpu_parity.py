@@ -130,10 +130,17 @@ def test_render_parity_suzanne(device, suzanne, brdf, pipeline):
 
 
 @pytest.mark.parametrize("brdf", [1, 0])
-def test_render_parity_shadow_rays(device, suzanne, brdf):
+@pytest.mark.parametrize("shadow_stage", [1, 0])
+def test_render_parity_shadow_rays(device, suzanne, brdf, shadow_stage):
+    """Shadow rays walked by the traversal engine as their own wavefront stage (default) or inside the shade
+    kernel (shadow_stage 0): same pixels, same counters."""
     p = Hh.Prepared(suzanne, 96, 96, brdf=brdf, shadow_rays=1, max_depth=3)
     assert p.num_lights == 1
-    got, gdbg, gstats, want, wdbg, wstats = _render_both(device, p, 3)
+    device.setTuning("shadow_stage", shadow_stage)
+    try:
+        got, gdbg, gstats, want, wdbg, wstats = _render_both(device, p, 3)
+    finally:
+        device.setTuning("shadow_stage", 1)
     assert Hh.mean_relative_error(got, want) <= RADIANCE_MRE_TOLERANCE
     assert Hh.images_equal(got, want)
     assert Hh.images_equal(gdbg, wdbg)

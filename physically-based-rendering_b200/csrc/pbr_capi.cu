@@ -72,6 +72,14 @@ struct pbr_ctx {
 	int stripeRows = 0, stripeWorld = 1, stripeRank = 0;
 	pbr_mem scratchImage = 0;                  /* pbr_kernel_launch_batch with depth of field */
 	int pipeline = 0;
+	/* pipeline selection by measurement (pbr_set_pipeline(-1), the default): the first frame of a configuration
+	 * runs as a wavefront, the second as the megakernel, both timed with events; whichever was faster renders
+	 * the rest.  All pipelines write the same bits, so the switch is invisible in the image. */
+	bool pipelineAuto = true;
+	int autoState = 0;                          /* 0 time the wavefront, 1 time the megakernel, 2 decide, 3 decided */
+	int autoChoice = 0;
+	unsigned long long autoKey = 0;
+	cudaEvent_t evAuto[4] = {nullptr, nullptr, nullptr, nullptr};
 	bool debugImage = true;
 
 	/* repacked scene cache */
@@ -697,7 +705,7 @@ int pbr_create(int device, pbr_ctx** out) {
 	if (const char* e = getenv("PBR_PERSIST_T")) { const int v = atoi(e); if (v >= 0 && v <= 16) ctx->persistTBlocks = v; }
 	if (const char* e = getenv("PBR_PERSIST_S")) { const int v = atoi(e); if (v >= 1 && v <= 16) ctx->persistSBlocks = v; }
 	if (const char* e = getenv("PBR_PERSIST_FILL")) { const int v = atoi(e); if (v >= 0 && v <= 100000) ctx->persistFill = v; }
-	if (const char* e = getenv("PBR_PIPELINE")) { const int v = atoi(e); if (v >= 0 && v <= 3) ctx->pipeline = v; }
+	if (const char* e = getenv("PBR_PIPELINE")) { const int v = atoi(e); if (v >= 0 && v <= 3) { ctx->pipeline = v; ctx->pipelineAuto = false; } }
 	memset(&ctx->defines, 0, sizeof(ctx->defines));
 	memset(&ctx->args.cam, 0, sizeof(ctx->args.cam));
 	*out = ctx;
@@ -729,6 +737,7 @@ int pbr_destroy(pbr_ctx* ctx) {
 	for (cudaEvent_t e : ctx->eventPool) cudaEventDestroy(e);
 	if (ctx->copyStream) { cudaStreamSynchronize(ctx->copyStream); cudaStreamDestroy(ctx->copyStream); }
 	if (ctx->evCopy) cudaEventDestroy(ctx->evCopy);
+	for (int i = 0; i < 4; i++) if (ctx->evAuto[i]) cudaEventDestroy(ctx->evAuto[i]);
 	cudaStreamDestroy(ctx->ownStream);
 	delete ctx;
 	return PBR_OK;
@@ -1040,6 +1049,31 @@ static int launchFrames(pbr_ctx* ctx, int n, const float* seeds, const float* we
 	const bool shadow = (D.shadow_rays == 1);
 
 	const int variant = (D.brdf == 1 ? 4 : 0) | (shadow ? 2 : 0) | (phong ? 1 : 0);
+
+	/* which pipeline: the caller's, or the one that measured faster for this configuration */
+	const int callerPipeline = ctx->pipeline;
+	int timing = -1;
+	if (ctx->pipelineAuto && n == 1) {
+		const unsigned long long key = ctx->sceneEpoch * 0x9e3779b97f4a7c15ull ^ ((unsigned long long) nPaths << 20) ^
+			((unsigned long long) variant << 8) ^ ((unsigned long long) D.max_depth << 12) ^ (unsigned long long) D.samples;
+		if (key != ctx->autoKey) { ctx->autoKey = key; ctx->autoState = 0; }
+		if (!ctx->evAuto[0]) for (int i = 0; i < 4; i++) CK(cudaEventCreate(&ctx->evAuto[i]));
+		if (ctx->autoState == 2) {
+			float tWave = 0.0f, tMega = 0.0f;
+			CK(cudaEventSynchronize(ctx->evAuto[3]));
+			CK(cudaEventElapsedTime(&tWave, ctx->evAuto[0], ctx->evAuto[1]));
+			CK(cudaEventElapsedTime(&tMega, ctx->evAuto[2], ctx->evAuto[3]));
+			ctx->autoChoice = (tMega < 0.9f * tWave) ? 1 : 0;
+			ctx->autoState = 3;
+		}
+		if (ctx->autoState == 0) { ctx->pipeline = 0; timing = 0; }
+		else if (ctx->autoState == 1) { ctx->pipeline = 1; timing = 2; }
+		else ctx->pipeline = ctx->autoChoice;
+		if (timing >= 0) CK(cudaEventRecord(ctx->evAuto[timing], ctx->stream));
+	}
+	else if (ctx->pipelineAuto) {
+		ctx->pipeline = 0;                      /* interleaved batches: the wavefront */
+	}
 	switch (variant) {
 		case 0: rc = runFrame<0, false, false>(ctx, P, nPaths); break;
 		case 1: rc = runFrame<0, false, true>(ctx, P, nPaths); break;
@@ -1050,6 +1084,11 @@ static int launchFrames(pbr_ctx* ctx, int n, const float* seeds, const float* we
 		case 6: rc = runFrame<1, true, false>(ctx, P, nPaths); break;
 		default: rc = runFrame<1, true, true>(ctx, P, nPaths); break;
 	}
+	if (timing >= 0 && rc == PBR_OK) {
+		CK(cudaEventRecord(ctx->evAuto[timing + 1], ctx->stream));
+		ctx->autoState++;
+	}
+	ctx->pipeline = callerPipeline;
 	return rc;
 }
 
@@ -1153,8 +1192,11 @@ int pbr_set_tile_stripes(pbr_ctx* ctx, int32_t stripe_rows, int32_t world, int32
 }
 
 int pbr_set_pipeline(pbr_ctx* ctx, int32_t mode) {
-	if (!ctx || mode < 0 || mode > 3) return PBR_ERR_INVALID;
-	ctx->pipeline = mode;
+	if (!ctx || mode < -1 || mode > 3) return PBR_ERR_INVALID;
+	ctx->pipelineAuto = (mode == -1);
+	ctx->pipeline = mode < 0 ? 0 : mode;
+	ctx->autoState = 0;
+	ctx->autoKey = 0;
 	return PBR_OK;
 }
 

@@ -96,7 +96,7 @@ def test_device_frames_equal_reference_outputs(device, oracle, gold, name, pipel
             img = device.readImageOutput(ds.texOut, p.W, p.H)
         dbg = device.readImageOutput(ds.texDebug, p.W, p.H)
     finally:
-        device.setPipeline(0)
+        device.setPipeline(-1)
     assert Hh.images_equal(img, gold[name + "/image"])
     assert Hh.images_equal(dbg, gold[name + "/debug"])
 

@@ -57,7 +57,7 @@ def test_fullsize_pipelines_agree(device, c2dev):
         try:
             img, dbg = c2dev.frames(2, host_roundtrip=False)
         finally:
-            device.setPipeline(0)
+            device.setPipeline(-1)
         frames[pipeline] = (img, dbg, device.stats(reset=True))
     ref = frames[0]
     assert np.isfinite(ref[0][..., :3]).all() and 0.3 < ref[0][..., :3].mean() < 1.0

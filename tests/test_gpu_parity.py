@@ -111,7 +111,7 @@ def _render_both(device, prep, frames, pipeline=0):
         got, gdbg = ds.frames(frames)
         gstats = device.stats(reset=True)
     finally:
-        device.setPipeline(0)
+        device.setPipeline(-1)
     want, wdbg, wstats = prep.oracle_frames(frames)
     return got, gdbg, gstats, want, wdbg, wstats
 
@@ -202,7 +202,7 @@ def _batch_both(device, prep, frames, pipeline, interleave=1):
         got, gdbg = ds.frames_batch(frames)
         gstats = device.stats(reset=True)
     finally:
-        device.setPipeline(0)
+        device.setPipeline(-1)
         device.setTuning("batch_interleave", 0)
     want, wdbg, wstats = prep.oracle_frames(frames)
     return got, gdbg, gstats, want, wdbg, wstats
@@ -281,7 +281,7 @@ def test_non_multiple_image_size_and_tiles(device, suzanne):
                 stitched[mine] = part[mine]
         finally:
             device.setTileStripes(0)
-            device.setPipeline(0)
+            device.setPipeline(-1)
         assert Hh.images_equal(stitched, full), "stripes of %d rows, pipeline %d" % (stripe, pipeline)
     device.setTileStripes(5, 2, 0)
     with pytest.raises(Exception):

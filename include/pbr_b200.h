@@ -125,8 +125,8 @@ int pbr_set_tile(pbr_ctx* ctx, int32_t y0, int32_t y1);
  * (row / stripe_rows) % world == rank; IMG_HEIGHT must be a multiple of stripe_rows * world.  stripe_rows <= 0
  * switches back to pbr_set_tile's contiguous rows. */
 int pbr_set_tile_stripes(pbr_ctx* ctx, int32_t stripe_rows, int32_t world, int32_t rank);
-/* Choose the device pipeline.  -1 (default) = by measurement: the first frame of a configuration (scene, frame
- * size, kernel variant) runs as 0, the second as 1, both timed, and the faster of the two renders the rest -- the
+/* Choose the device pipeline.  -1 (default) = by measurement: after one warm-up frame of a configuration (scene, frame
+ * size, kernel variant) two frames run as 0 and two as 1, alternately, all timed, and the faster of the two renders the rest -- the
  * megakernel wins on small scenes and small frames (Suzanne at 512x512: 2.2x), the wavefront everywhere else.
  * 0 = wavefront, one traverse + one shade launch per bounce;
  * 1 = one-thread-per-pixel megakernel (the reference's launch structure; kept as an on-device cross-check);
@@ -136,6 +136,9 @@ int pbr_set_tile_stripes(pbr_ctx* ctx, int32_t stripe_rows, int32_t world, int32
  * for the next launch (the launch call then blocks until the frame is nearly done).
  * All four write identical pixels (DESIGN.md section 6 has the measurements). */
 int pbr_set_pipeline(pbr_ctx* ctx, int32_t mode);
+/* The pipeline frames are rendered with right now: the mode set explicitly, or with mode -1 the measured choice
+ * (0 or 1), -1 while the measurement is still running. */
+int pbr_pipeline_in_use(pbr_ctx* ctx, int32_t* mode);
 /* n_frames consecutive frames in one call.  Same pixels as the reference's frame loop
  *     for f in 0..n-1: setKernelArg(0, seeds[f]); setKernelArg(1, pixel_weights[f]); execute();
  *                      imageIn <- imageOut                     (PathTracer::generateImage, PathTracer.cpp:59-71)

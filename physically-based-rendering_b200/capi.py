@@ -21,7 +21,7 @@ SYMBOLS = [
     "pbr_free_buffers", "pbr_host_alloc", "pbr_host_free",
     "pbr_set_define", "pbr_program_load", "pbr_kernel_get", "pbr_kernel_set_arg", "pbr_kernel_launch",
     "pbr_finish", "pbr_kernel_time_ms",
-    "pbr_image_read_begin", "pbr_image_read_end", "pbr_set_tile", "pbr_set_tile_stripes", "pbr_set_pipeline", "pbr_set_tuning", "pbr_kernel_launch_batch", "pbr_set_debug_image", "pbr_stats",
+    "pbr_image_read_begin", "pbr_image_read_end", "pbr_set_tile", "pbr_set_tile_stripes", "pbr_set_pipeline", "pbr_pipeline_in_use", "pbr_set_tuning", "pbr_kernel_launch_batch", "pbr_set_debug_image", "pbr_stats",
     "pbr_trace", "pbr_trace_device", "pbr_pinned_math_eval",
     "pbr_set_stream", "pbr_profile_enable", "pbr_profile_read",
 ]
@@ -88,6 +88,7 @@ def load_library():
         "pbr_image_read_end": [vp],
         "pbr_set_tile_stripes": [vp, i32, i32, i32],
         "pbr_set_pipeline": [vp, i32],
+        "pbr_pipeline_in_use": [vp, C.POINTER(i32)],
         "pbr_set_tuning": [vp, C.c_char_p, i32],
         "pbr_kernel_launch_batch": [vp, u64, i32, vp, vp],
         "pbr_set_debug_image": [vp, i32],
@@ -245,6 +246,11 @@ class Device:
 
     def setPipeline(self, mode):
         self._ck(self.lib.pbr_set_pipeline(self.ctx, mode), "pbr_set_pipeline")
+
+    def pipelineInUse(self):
+        m = C.c_int32(-2)
+        self._ck(self.lib.pbr_pipeline_in_use(self.ctx, C.byref(m)), "pbr_pipeline_in_use")
+        return int(m.value)
 
     def executeBatch(self, kernel, seeds, pixel_weights):
         """pbr_kernel_launch_batch: len(seeds) consecutive frames, result in imageOut."""

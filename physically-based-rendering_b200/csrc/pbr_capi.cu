@@ -76,10 +76,11 @@ struct pbr_ctx {
 	 * runs as a wavefront, the second as the megakernel, both timed with events; whichever was faster renders
 	 * the rest.  All pipelines write the same bits, so the switch is invisible in the image. */
 	bool pipelineAuto = true;
-	int autoState = 0;                          /* 0 time the wavefront, 1 time the megakernel, 2 decide, 3 decided */
+	int autoState = 0;                          /* 0 warm-up frame (wavefront, untimed: allocations happen here); 1, 3 time
+	                                               the wavefront; 2, 4 time the megakernel; 5 decide; 6 decided */
 	int autoChoice = 0;
 	unsigned long long autoKey = 0;
-	cudaEvent_t evAuto[4] = {nullptr, nullptr, nullptr, nullptr};
+	cudaEvent_t evAuto[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 	bool debugImage = true;
 
 	/* repacked scene cache */
@@ -737,7 +738,7 @@ int pbr_destroy(pbr_ctx* ctx) {
 	for (cudaEvent_t e : ctx->eventPool) cudaEventDestroy(e);
 	if (ctx->copyStream) { cudaStreamSynchronize(ctx->copyStream); cudaStreamDestroy(ctx->copyStream); }
 	if (ctx->evCopy) cudaEventDestroy(ctx->evCopy);
-	for (int i = 0; i < 4; i++) if (ctx->evAuto[i]) cudaEventDestroy(ctx->evAuto[i]);
+	for (int i = 0; i < 8; i++) if (ctx->evAuto[i]) cudaEventDestroy(ctx->evAuto[i]);
 	cudaStreamDestroy(ctx->ownStream);
 	delete ctx;
 	return PBR_OK;
@@ -1057,17 +1058,21 @@ static int launchFrames(pbr_ctx* ctx, int n, const float* seeds, const float* we
 		const unsigned long long key = ctx->sceneEpoch * 0x9e3779b97f4a7c15ull ^ ((unsigned long long) nPaths << 20) ^
 			((unsigned long long) variant << 8) ^ ((unsigned long long) D.max_depth << 12) ^ (unsigned long long) D.samples;
 		if (key != ctx->autoKey) { ctx->autoKey = key; ctx->autoState = 0; }
-		if (!ctx->evAuto[0]) for (int i = 0; i < 4; i++) CK(cudaEventCreate(&ctx->evAuto[i]));
-		if (ctx->autoState == 2) {
-			float tWave = 0.0f, tMega = 0.0f;
-			CK(cudaEventSynchronize(ctx->evAuto[3]));
-			CK(cudaEventElapsedTime(&tWave, ctx->evAuto[0], ctx->evAuto[1]));
-			CK(cudaEventElapsedTime(&tMega, ctx->evAuto[2], ctx->evAuto[3]));
+		if (!ctx->evAuto[0]) for (int i = 0; i < 8; i++) CK(cudaEventCreate(&ctx->evAuto[i]));
+		if (ctx->autoState == 5) {
+			/* two rounds, the better time of each pipeline counts (clocks may still be ramping up in the first) */
+			float t[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+			CK(cudaEventSynchronize(ctx->evAuto[7]));
+			for (int i = 0; i < 4; i++) CK(cudaEventElapsedTime(&t[i], ctx->evAuto[2 * i], ctx->evAuto[2 * i + 1]));
+			const float tWave = fminf(t[0], t[2]), tMega = fminf(t[1], t[3]);
 			ctx->autoChoice = (tMega < 0.9f * tWave) ? 1 : 0;
-			ctx->autoState = 3;
+			ctx->autoState = 6;
 		}
-		if (ctx->autoState == 0) { ctx->pipeline = 0; timing = 0; }
-		else if (ctx->autoState == 1) { ctx->pipeline = 1; timing = 2; }
+		if (ctx->autoState == 0) { ctx->pipeline = 0; }
+		else if (ctx->autoState >= 1 && ctx->autoState <= 4) {
+			ctx->pipeline = (ctx->autoState & 1) ? 0 : 1;
+			timing = 2 * (ctx->autoState - 1);
+		}
 		else ctx->pipeline = ctx->autoChoice;
 		if (timing >= 0) CK(cudaEventRecord(ctx->evAuto[timing], ctx->stream));
 	}
@@ -1084,10 +1089,8 @@ static int launchFrames(pbr_ctx* ctx, int n, const float* seeds, const float* we
 		case 6: rc = runFrame<1, true, false>(ctx, P, nPaths); break;
 		default: rc = runFrame<1, true, true>(ctx, P, nPaths); break;
 	}
-	if (timing >= 0 && rc == PBR_OK) {
-		CK(cudaEventRecord(ctx->evAuto[timing + 1], ctx->stream));
-		ctx->autoState++;
-	}
+	if (timing >= 0 && rc == PBR_OK) CK(cudaEventRecord(ctx->evAuto[timing + 1], ctx->stream));
+	if (ctx->pipelineAuto && n == 1 && ctx->autoState < 5 && rc == PBR_OK) ctx->autoState++;
 	ctx->pipeline = callerPipeline;
 	return rc;
 }
@@ -1197,6 +1200,12 @@ int pbr_set_pipeline(pbr_ctx* ctx, int32_t mode) {
 	ctx->pipeline = mode < 0 ? 0 : mode;
 	ctx->autoState = 0;
 	ctx->autoKey = 0;
+	return PBR_OK;
+}
+
+int pbr_pipeline_in_use(pbr_ctx* ctx, int32_t* mode) {
+	if (!ctx || !mode) return PBR_ERR_INVALID;
+	*mode = !ctx->pipelineAuto ? ctx->pipeline : (ctx->autoState >= 6 ? ctx->autoChoice : -1);
 	return PBR_OK;
 }
 

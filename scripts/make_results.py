@@ -63,7 +63,7 @@ if os.path.isfile(n8path):
         out.append("| C5 %d M rays, primary / shadow | %.0f / %.0f Mrays/s | %.0f / %.0f Mrays/s, bit-exact %s / %s |" % (
             r1["requested_mrays"], r1["primary"]["mrays_per_s"], r1["shadow"]["mrays_per_s"], r8["primary"]["mrays_per_s"],
             r8["shadow"]["mrays_per_s"], r8["primary"]["hit_face_leaf_t_bit_exact"], r8["shadow"]["hit_face_leaf_t_bit_exact"]))
-out.append("Pipelines on C2, ms per 1080p frame: wavefront 4.58 (default) | persistent kernels 4.92 | carry-over 5.5 | wavefront with "
+out.append("Pipelines on C2, ms per 1080p frame: wavefront 4.58 (what the measured choice picks here) | megakernel 7.7 | persistent kernels 4.92 | carry-over 5.5 | wavefront with "
            "interleaved frame batches 5.2 -- all bit-identical (DESIGN.md section 6).")
 with open(os.path.join(P, "RESULTS_%s.md" % tag), "w") as f:
     f.write("\n".join(out) + "\n")

@@ -91,17 +91,23 @@ def renderer_program_values():
             r.close()
 
 
-def all_program_values():
+def static_program_values():
+    """Configurations whose program values are known without running the reference's host code."""
     from oracle import ref as R
-    from oracle import ref_host as RH
     for name in CASES:
         yield R.values_from_defines(prepared(name).defines)
+    if os.environ.get("PBR_REF_SKIP_BENCH") != "1":
+        yield bench_c2_values()
     import test_random_parity as T
     for brdf in (1, 0):
         for seed in range(T.TRIALS):
             yield R.values_from_defines(T._trial(seed, brdf).defines)
+
+
+def all_program_values():
+    from oracle import ref_host as RH
+    for v in static_program_values():
+        yield v
     if RH.available():
         for v in renderer_program_values():
             yield v
-    if os.environ.get("PBR_REF_SKIP_BENCH") != "1":
-        yield bench_c2_values()

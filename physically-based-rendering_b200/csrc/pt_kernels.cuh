@@ -8,17 +8,23 @@
  *     repeat (at most SAMPLES * (MAX_DEPTH + MAX_ADDED_DEPTH) times)
  *         traverse      persistent warps pull 32 live paths at a time from the queue and walk the
  *                       BVH (small register footprint -> many warps per SM to hide L2 latency)
+ *         [shadowGen, traverseShadow   with render.shadow_rays: the shadow ray of every hit as a stage of its own]
  *         shade         per live path: bounce(); paths that finish a sample start the next one
- *                       (seed carried over) or write their pixel (setColors) and leave; survivors
- *                       are appended to the next queue with one warp-aggregated atomic per warp
+ *                       (seed carried over) or write their pixel (setColors) and, in a batch, go on to
+ *                       their next frame, or leave; survivors are appended to the next queue with one
+ *                       warp-aggregated atomic per warp
  *
  * Per-pixel arithmetic and its order are those of the reference kernel, so every pixel gets the
- * same bits whatever the scheduling.  `megakernel` keeps the reference's launch structure (one
- * thread per pixel, everything inline) as an on-device cross-check of the wavefront.
+ * same bits whatever the scheduling.  `megaKernel` keeps the reference's launch structure (one
+ * thread per pixel, everything inline): the on-device cross-check of the wavefront and the faster of
+ * the two on small scenes (pbr_capi.cu chooses by measurement).  Also here: the carry-over variant of
+ * the traverse kernel, the explicit-ray kernels, the scene repack.  pt_persistent.cuh holds the
+ * two-resident-kernels pipeline.
  *
  * Path state lives in HBM as 16-byte SoA records (coalesced 128-bit accesses):
  *     rayO (o.xyz, t)   rayD (d.xyz, hitFace)   colS (color.xyz, seed)   finF (finalColor.xyz, focus)
- *     misc (depth | depthAdded << 16, sample, secondaryPaths, -)   dbg (nodes visited, triangle tests)
+ *     misc (depth | depthAdded << 16, sample, secondaryPaths, frame of the batch)
+ *     dbg (nodes visited, triangle tests)
  */
 #pragma once
 

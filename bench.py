@@ -449,7 +449,7 @@ def run_ours(args):
                 "pipeline": {0: "wavefront", 1: "megakernel", 2: "persistent", 3: "carry-over", -1: "undecided"}[dev.pipelineInUse()] +
                        " (chosen by measurement on the first frames)",
                        "l2_policy": "working set > L2: nodes+tris %.0f MB, path state %.0f MB, images %.0f MB" % (
-                    (info["emitted_nodes"] * 32 + info["faces"] * 40) / 1e6, W * H * 104 / 1e6, W * H * 48 / 1e6),
+                    (info["emitted_nodes"] * 32 + info["faces"] * 36) / 1e6, W * H * 104 / 1e6, W * H * 48 / 1e6),
             },
             "samples_per_s": round(samples_per_s), "rays_per_step": round(rays_all / args.steps),
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches_all), "verify": verify,

@@ -86,7 +86,8 @@ struct pbr_ctx {
 	/* repacked scene cache */
 	float4* nodes = nullptr;
 	float4* tris = nullptr;
-	const float2* trisB = nullptr;
+	const float* trisB = nullptr;
+	const uint32_t* triMat = nullptr;
 	size_t nodesCap = 0, trisCap = 0;
 	pbr_mem cacheBvh = 0, cacheFacesV = 0, cacheVertices = 0, cacheFacesN = 0, cacheNormals = 0;
 	bool cachePhong = false;
@@ -266,9 +267,11 @@ int ensureScene(pbr_ctx* ctx, pbr_mem hBvh, pbr_mem hFacesV, pbr_mem hVertices, 
 	Mem* normals = phong ? getMem(ctx, hNormals) : nullptr;
 	if (phong && (!facesN || !normals || facesN->bytes < facesV->bytes || normals->bytes < sizeof(pbr_float4)))
 		return fail(ctx, PBR_ERR_INVALID, "pathTracing: PHONGTESS needs facesN (one entry per face) and normals");
-	/* float4s: PHONGTESS 6 per face; otherwise 2 per face + half a float4 (edge2.yz) per face behind them */
+	/* float4s: PHONGTESS 6 per face; otherwise 2 per face, then a quarter float4 (edge2.z) per face behind them,
+	 * then a quarter float4 (material index) per face behind those */
 	const size_t facesAlloc = (size_t) (numFaces > 0 ? numFaces : 1);
-	const size_t wantTris = phong ? facesAlloc * PT_TRI_STRIDE_PHONG : facesAlloc * PT_TRI_STRIDE + (facesAlloc + 1) / 2;
+	const size_t quarter = (facesAlloc + 3) / 4;
+	const size_t wantTris = phong ? facesAlloc * PT_TRI_STRIDE_PHONG : facesAlloc * PT_TRI_STRIDE + 2 * quarter;
 	if (wantTris > ctx->trisCap || !ctx->tris) {
 		if (ctx->tris) cudaFree(ctx->tris);
 		ctx->tris = nullptr;
@@ -289,7 +292,7 @@ int ensureScene(pbr_ctx* ctx, pbr_mem hBvh, pbr_mem hFacesV, pbr_mem hVertices, 
 		else {
 			repackTrisKernel<<<gridFor(numFaces, 256), 256, 0, ctx->stream>>>(
 				(const uint4*) facesV->dptr, numFaces, (const float4*) vertices->dptr, numVertices, ctx->tris,
-				(float2*) (ctx->tris + PT_TRI_STRIDE * facesAlloc));
+				(float*) (ctx->tris + PT_TRI_STRIDE * facesAlloc), (uint32_t*) (ctx->tris + PT_TRI_STRIDE * facesAlloc + quarter));
 		}
 	}
 	CK(cudaGetLastError());
@@ -298,7 +301,8 @@ int ensureScene(pbr_ctx* ctx, pbr_mem hBvh, pbr_mem hFacesV, pbr_mem hVertices, 
 	ctx->cacheNumNodes = numNodes;
 	ctx->cacheEpoch = ctx->sceneEpoch;
 	ctx->numNodesDev = numNodes;
-	ctx->trisB = phong ? nullptr : (const float2*) (ctx->tris + PT_TRI_STRIDE * facesAlloc);
+	ctx->trisB = phong ? nullptr : (const float*) (ctx->tris + PT_TRI_STRIDE * facesAlloc);
+	ctx->triMat = phong ? nullptr : (const uint32_t*) (ctx->tris + PT_TRI_STRIDE * facesAlloc + quarter);
 	return PBR_OK;
 }
 
@@ -1011,6 +1015,7 @@ static int launchFrames(pbr_ctx* ctx, int n, const float* seeds, const float* we
 	P.scene.nodes = ctx->nodes;
 	P.scene.tris = ctx->tris;
 	P.scene.trisB = ctx->trisB;
+	P.scene.triMat = ctx->triMat;
 	P.scene.lights = (const pbr_light*) lights->dptr;
 	P.scene.numNodes = ctx->numNodesDev;
 	P.scene.numLights = D.num_lights;
@@ -1277,6 +1282,7 @@ static int traceImpl(pbr_ctx* ctx, pbr_mem bvh, pbr_mem facesV, pbr_mem vertices
 	S.nodes = ctx->nodes;
 	S.tris = ctx->tris;
 	S.trisB = ctx->trisB;
+	S.triMat = ctx->triMat;
 	S.numNodes = ctx->numNodesDev;
 	S.numLights = 0;
 	S.lights = nullptr;

@@ -44,7 +44,8 @@ using pm::v3;
 struct SceneDev {
 	const float4* nodes;          /* 2 x float4 per node */
 	const float4* tris;           /* 2 x float4 (32 B) per face; PHONGTESS: 6 x float4 (a b c an bn cn) */
-	const float2* trisB;          /* + 8 B per face (edge2.y, edge2.z); unused with PHONGTESS */
+	const float* trisB;           /* + 4 B per face (edge2.z); unused with PHONGTESS */
+	const uint32_t* triMat;       /* material index per face, read once per shaded hit; unused with PHONGTESS */
 	const pbr_light* lights;
 	float phongAlpha;             /* PHONGTESS_ALPHA */
 	int numNodes;
@@ -98,16 +99,20 @@ __device__ __forceinline__ void loadNode(const float4* nodes, int index, float4&
 
 #define PT_TRI_STRIDE 2           /* float4s per triangle record in `tris` */
 
-/* 40 bytes per face in two arrays, so that the randomly accessed part of the scene stays as small as it can
+/* 36 bytes per face in two arrays, so that the randomly accessed part of the scene stays as small as it can
  * (the walk is served from L2, and its hit rate falls off beyond ~60 MB, scripts/micro/chase.cu):
- * (a.xyz, material bits, edge1.xyz, edge2.x) with one 256-bit load, (edge2.y, edge2.z) with one 64-bit load. */
+ * (a.xyz, edge1.xyz, edge2.xy) with one 256-bit load, edge2.z with one 32-bit load.  The material index is not
+ * needed by the walk and lives in SceneDev::triMat. */
 __device__ __forceinline__ void loadTri(const SceneDev& S, int face, float4& A, float4& E1, float4& E2) {
 	const float4* p = S.tris + PT_TRI_STRIDE * (size_t) face;
+	float e1y, e1z, e2x, e2y;
 	asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-		: "=f"(A.x), "=f"(A.y), "=f"(A.z), "=f"(A.w), "=f"(E1.x), "=f"(E1.y), "=f"(E1.z), "=f"(E1.w)
+		: "=f"(A.x), "=f"(A.y), "=f"(A.z), "=f"(E1.x), "=f"(e1y), "=f"(e1z), "=f"(e2x), "=f"(e2y)
 		: "l"(p));
-	const float2 yz = __ldg(S.trisB + face);
-	E2 = make_float4(E1.w, yz.x, yz.y, 0.0f);
+	const float e2z = __ldg(S.trisB + face);
+	A.w = 0.0f;
+	E1.y = e1y; E1.z = e1z; E1.w = 0.0f;
+	E2 = make_float4(e2x, e2y, e2z, 0.0f);
 }
 
 __device__ __forceinline__ vec3 f4xyz(const float4& f) { return v3(f.x, f.y, f.z); }
@@ -988,7 +993,7 @@ __device__ __forceinline__ PrefixResult bouncePrefix(
 	else {
 		float4 A, E1, E2;
 		loadTri(S, s.hitFace, A, E1, E2);
-		mtlIndex = (uint32_t) __float_as_int(A.w);
+		mtlIndex = __ldg(S.triMat + s.hitFace);
 		normal = pm::normalize(pm::cross(f4xyz(E1), f4xyz(E2)));
 	}
 	mtl = fetchMaterial<BRDF>(P.materials, P.numMaterials, mtlIndex);

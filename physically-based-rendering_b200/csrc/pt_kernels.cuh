@@ -720,19 +720,20 @@ __global__ void repackNodesKernel(const float4* __restrict__ src, const int numS
 	dst[2 * (size_t) i + 1] = hi;
 }
 
-/* facesV[f] + vertices[] -> (a, material), b - a, c - a   (pt_intersect.cl:146-149, :98-99) */
+/* facesV[f] + vertices[] -> a, b - a, c - a; material index   (pt_intersect.cl:146-149, :98-99) */
 __global__ void repackTrisKernel(
 	const uint4* __restrict__ facesV, const int numFaces, const float4* __restrict__ vertices, const int numVertices,
-	float4* __restrict__ tris, float2* __restrict__ trisB
+	float4* __restrict__ tris, float* __restrict__ trisB, uint32_t* __restrict__ triMat
 ) {
 	const int f = blockIdx.x * blockDim.x + threadIdx.x;
 	if (f >= numFaces) return;
 	const uint4 fv = facesV[f];
 	const uint32_t last = (uint32_t) (numVertices - 1);
 	const float4 a = vertices[min(fv.x, last)], b = vertices[min(fv.y, last)], c = vertices[min(fv.z, last)];
-	tris[PT_TRI_STRIDE * (size_t) f] = make_float4(a.x, a.y, a.z, __int_as_float((int) fv.w));
-	tris[PT_TRI_STRIDE * (size_t) f + 1] = make_float4(b.x - a.x, b.y - a.y, b.z - a.z, c.x - a.x);
-	trisB[f] = make_float2(c.y - a.y, c.z - a.z);
+	tris[PT_TRI_STRIDE * (size_t) f] = make_float4(a.x, a.y, a.z, b.x - a.x);
+	tris[PT_TRI_STRIDE * (size_t) f + 1] = make_float4(b.y - a.y, b.z - a.z, c.x - a.x, c.y - a.y);
+	trisB[f] = c.z - a.z;
+	triMat[f] = fv.w;
 }
 
 /* PHONGTESS: facesV[f], facesN[f] + vertices[], normals[] -> (a, material), (b, allNormalsEqual), (c, 0),

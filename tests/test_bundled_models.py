@@ -82,3 +82,33 @@ def test_bundled_model_frames_equal_reference_kernel(name, brdf):
         assert Hh.images_equal(img_o, img_r), "frame %d: radiance" % k
         assert Hh.images_equal(dbg_o, dbg_r), "frame %d: visit counters" % k
     assert dbg_r[..., 0].max() > 0, "no triangle was ever tested: the camera does not see the model"
+
+
+def test_shipped_config_json_is_read_as_is(cfg):
+    """The reference's own config.json (// comments, tabs, a path with spaces) through the product's Cfg: every
+    key of Cfg.cpp:4-39 with the value the file states -- and those are also the product's built-in defaults."""
+    shipped = {
+        "camera.eye.x": 0.0, "camera.eye.y": 1.0, "camera.eye.z": 3.0,
+        "camera.center.x": 0.0, "camera.center.y": 0.0, "camera.center.z": 1.0,
+        "camera.perspective.fov": 45.0, "camera.perspective.zfar": 1000.0, "camera.perspective.znear": 0.1,
+        "camera.thin_lense.aperture": 1.8, "camera.thin_lense.focal_length": 0.035, "camera.speed": 0.2,
+        "info.kernel_times": 250.0, "accel_struct": 0, "bvh.max_faces": 2, "bvh.sah_faces_limit": 100000,
+        "bvh.skip_ahead": "true", "bvh.skip_ahead_compare": 0.7, "logging.level": 4,
+        "opencl.build_options": "", "opencl.check_errors": "true", "opencl.program": "source/opencl/pathtracing.cl",
+        "opencl.localgroupsize": 8, "render.antialiasing": 0.7, "render.brdf": 1, "render.interval": 33.3,
+        "render.max_added_depth": 5, "render.max_depth": 3, "render.phong_tessellation": 0.0, "render.samples": 1,
+        "render.shadow_rays": 0, "shader.name": "pathtracing", "shader.path": "source/shader/",
+        "window.height": 600, "window.width": 800,
+        "import_path": "/home/seba/programming/Physically-based Rendering/resources/models/",
+    }
+    defaults = {k: cfg.get(k) for k in shipped if k not in ("logging.level", "import_path")}
+    cfg.load_file("/root/reference/config.json")
+    for key, want in shipped.items():
+        got = cfg.get(key)
+        if isinstance(want, str):
+            assert got == want, key
+        else:
+            assert float(got) == float(want), key
+    for key, was in defaults.items():
+        got = cfg.get(key)
+        assert got == was or float(got) == float(was), "built-in default of %s differs from the shipped file" % key

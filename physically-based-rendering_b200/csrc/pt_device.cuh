@@ -124,14 +124,11 @@ __device__ __forceinline__ vec3 p4xyz(const pbr_float4& f) { return v3(f.x, f.y,
 
 /* flatTriAndRayIntersect (pt_intersect.cl:92-129) + intersectFace (pt_bvh.cl:10-24) on a
  * pre-gathered triangle record.  Updates (rt, hitFace, hitLeaf) when the face is closer. */
-__device__ __forceinline__ void intersectFace(
-	const SceneDev& S, const int face, const int leaf,
+__device__ __forceinline__ void intersectFaceLoaded(
+	const float4 A, const float4 E1, const float4 E2, const int face, const int leaf,
 	const vec3 o, const vec3 d, const float tNear,
 	float& rt, int& hitFace, int& hitLeaf
 ) {
-	float4 A, E1, E2;
-	loadTri(S, face, A, E1, E2);
-
 	const float f = fmaxf(0.0f, tNear - 0.001f);
 	const vec3 closeOrigin = pm::fma3(d, f, o);
 	const vec3 edge1 = f4xyz(E1);
@@ -161,6 +158,16 @@ __device__ __forceinline__ void intersectFace(
 		hitFace = face;
 		hitLeaf = leaf;
 	}
+}
+
+__device__ __forceinline__ void intersectFace(
+	const SceneDev& S, const int face, const int leaf,
+	const vec3 o, const vec3 d, const float tNear,
+	float& rt, int& hitFace, int& hitLeaf
+) {
+	float4 A, E1, E2;
+	loadTri(S, face, A, E1, E2);
+	intersectFaceLoaded(A, E1, E2, face, leaf, o, d, tNear, rt, hitFace, hitLeaf);
 }
 
 /* ------------------------------------------------------------ Phong tessellation (pt_phongtess.cl) */

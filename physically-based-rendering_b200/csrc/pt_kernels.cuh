@@ -185,8 +185,33 @@ __device__ __forceinline__ bool nodeStep(const SceneDev& S, LaneRay& L) {
 }
 
 /* intersectFaces (pt_bvh.cl:35-46) for the pending leaf. */
+#ifndef PT_LEAF_HOIST
+#define PT_LEAF_HOIST 1
+#endif
+#ifndef PT_TRAVERSE_MIN_BLOCKS
+#define PT_TRAVERSE_MIN_BLOCKS 9           /* resident blocks of 128 threads per SM the traversal kernels are compiled for */
+#endif
 template <bool ANY_HIT, bool PHONG>
 __device__ __forceinline__ void leafStep(const SceneDev& S, LaneRay& L) {
+#if PT_LEAF_HOIST
+	if (!PHONG) {
+		/* both records are requested before the first test, so a two-face leaf costs one trip to L2 instead of
+		 * two; the tests themselves run in the reference's order */
+		const bool two = L.leafF1 != -1;
+		float4 A0, E10, E20;
+		float4 A1 = make_float4(0.0f, 0.0f, 0.0f, 0.0f), E11 = A1, E21 = A1;
+		loadTri(S, L.leafF0, A0, E10, E20);
+		if (two) loadTri(S, L.leafF1, A1, E11, E21);
+		intersectFaceLoaded(A0, E10, E20, L.leafF0, L.leafCur, L.o, L.d, L.leafTNear, L.rt, L.hitFace, L.hitLeaf);
+		L.nt++;
+		if (two) {
+			intersectFaceLoaded(A1, E11, E21, L.leafF1, L.leafCur, L.o, L.d, L.leafTNear, L.rt, L.hitFace, L.hitLeaf);
+			L.nt++;
+		}
+		if (ANY_HIT && L.rt < L.tLight) L.index = -1;     /* `break` of traverseShadows (pt_bvh.cl:170-172) */
+		return;
+	}
+#endif
 	if (PHONG) intersectFacePhong(S, L.leafF0, L.leafCur, L.o, L.d, L.leafTNear, L.leafTFar, L.rt, L.hitFace, L.hitLeaf, L.normal);
 	else intersectFace(S, L.leafF0, L.leafCur, L.o, L.d, L.leafTNear, L.rt, L.hitFace, L.hitLeaf);
 	L.nt++;
@@ -288,7 +313,7 @@ struct WaveRaySource {
 
 /* Closest-hit traversal of every live path.  queue pointer NULL = identity (first bounce). */
 template <bool PHONG>
-__global__ void __launch_bounds__(128) traverseKernel(
+__global__ void __launch_bounds__(128, PHONG ? 1 : PT_TRAVERSE_MIN_BLOCKS) traverseKernel(
 	const SceneDev S, const WaveState W, const uint32_t* __restrict__ queue, const uint32_t* __restrict__ countPtr,
 	uint32_t* cursor, uint32_t* countToReset, unsigned long long* stats
 ) {
@@ -610,7 +635,7 @@ struct ShadowRaySource {
 };
 
 template <bool PHONG>
-__global__ void __launch_bounds__(128) traverseShadowKernel(
+__global__ void __launch_bounds__(128, PHONG ? 1 : PT_TRAVERSE_MIN_BLOCKS) traverseShadowKernel(
 	const SceneDev S, const WaveState W, float4* shadowO, const float4* __restrict__ shadowD,
 	const uint32_t* __restrict__ shadowQ, const uint32_t* __restrict__ countPtr, uint32_t* cursor, unsigned long long* stats
 ) {
@@ -683,7 +708,7 @@ struct ExplicitRaySource {
 };
 
 template <bool ANY_HIT>
-__global__ void __launch_bounds__(128) traceRaysKernel(
+__global__ void __launch_bounds__(128, PT_TRAVERSE_MIN_BLOCKS) traceRaysKernel(
 	const SceneDev S, const pbr_ray* __restrict__ rays, const long long n, pbr_hit* __restrict__ hits,
 	unsigned long long* cursor, unsigned long long* stats
 ) {

@@ -65,6 +65,13 @@ if os.path.isfile(n8path):
             r8["shadow"]["mrays_per_s"], r8["primary"]["hit_face_leaf_t_bit_exact"], r8["shadow"]["hit_face_leaf_t_bit_exact"]))
 out.append("Pipelines on C2, ms per 1080p frame: wavefront 4.58 (what the measured choice picks here) | megakernel 7.7 | persistent kernels 4.92 | carry-over 5.5 | wavefront with "
            "interleaved frame batches 5.2 -- all bit-identical (DESIGN.md section 6).")
+fin = os.path.join(P, "bench_%s_n1_final.json" % tag)
+if os.path.isfile(fin):
+    f1 = load("bench_%s_n1_final.json" % tag)
+    out.append("\nLast single-GPU run of the round (36-byte triangle records, both records of a two-face leaf loaded before the first test; "
+               "the tables above predate these two changes): %.0f Mrays/s resident, %.0f end to end, %.2f ms/frame, roofline fraction %.2f "
+               "(`bench_%s_n1_final.json`); compute-sanitizer memcheck / racecheck clean (`%s_sanitizer_and_tri36.md`)." % (
+               f1["value"], f1["e2e"]["value"], f1["ms_per_step"] / 16, f1["roofline"]["frac"], tag, tag))
 with open(os.path.join(P, "RESULTS_%s.md" % tag), "w") as f:
     f.write("\n".join(out) + "\n")
 print("\n".join(out))

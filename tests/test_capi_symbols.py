@@ -30,6 +30,47 @@ def test_library_exports_every_declared_symbol():
     assert sorted(pbr_b200.capi.SYMBOLS) == _declared()
 
 
+def test_host_library_exports_every_declared_symbol():
+    """include/pbr_host.h (the flat C view of the host mirror: Cfg, loaders, BVH, PathTracer, Camera) <-> libpbr_host.so."""
+    import pbr_b200
+    text = open(os.path.join(ROOT, "include", "pbr_host.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    declared = sorted(set(re.findall(r"\b(pbrh_[a-z0-9_]+)\s*\(", text)))
+    assert len(declared) >= 40
+    assert os.path.exists(pbr_b200.host.LIB_PATH), "libpbr_host.so not built: run __graft_entry__.build()"
+    lib = ctypes.CDLL(pbr_b200.host.LIB_PATH)
+    missing = [n for n in declared if not hasattr(lib, n)]
+    assert not missing, missing
+
+
+def test_headers_are_plain_c_and_link(tmp_path):
+    """The boundary is a C ABI: both public headers compile as strict C99 and a C program links against the
+    library and gets an error code -- not a crash, not a CPU path -- from pbr_create when there is no device."""
+    import shutil
+    import subprocess
+    import pbr_b200
+    if not shutil.which("gcc"):
+        return
+    src = tmp_path / "abi.c"
+    src.write_text('#include "pbr_b200.h"\n#include "pbr_host.h"\n#include <stdio.h>\n'
+                   'int main(void) { pbr_ctx* c = 0; int rc = pbr_create(0, &c);\n'
+                   '  printf("%d %d\\n", rc, (int) (sizeof(pbr_camera) + sizeof(pbr_ray) + sizeof(pbr_hit)));\n'
+                   '  if (rc == PBR_OK) pbr_destroy(c);\n  return 0; }\n')
+    inc = os.path.join(ROOT, "include")
+    libdir = os.path.dirname(pbr_b200.capi.LIB_PATH)
+    subprocess.check_call(["gcc", "-std=c99", "-pedantic", "-Wall", "-Wextra", "-Werror", "-I", inc, "-fsyntax-only", str(src)])
+    exe = str(tmp_path / "abi")
+    subprocess.check_call(["gcc", "-std=c99", "-I", inc, str(src), "-o", exe, "-L", libdir, "-lpbr_b200", "-Wl,-rpath," + libdir])
+    out = subprocess.check_output([exe]).decode().split()
+    assert int(out[1]) == 80 + 32 + 16                      # camera_cl (PathTracer.h:25-32), ray, hit record
+    try:
+        import torch
+        has_gpu = torch.cuda.is_available()
+    except Exception:
+        has_gpu = False
+    assert (int(out[0]) == 0) == has_gpu
+
+
 def test_no_cpu_fallback_without_device():
     """Without a CUDA device pbr_create must fail (the product never routes to the CPU)."""
     import pbr_b200

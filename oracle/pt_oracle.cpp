@@ -1453,6 +1453,42 @@ void oracle_visit_histogram(
 	}
 }
 
+/* Analysis helper: the same histogram for the walk traverse() really does (t pruning and face tests included).
+ * counts[0] receives the number of leaf visits whose box was hit. */
+void oracle_visit_histogram_pruned(
+	const pbr_defines* D, const pbr_bvh_node* bvh, const pbr_uint4* facesV, const pbr_uint4* facesN,
+	const pbr_float4* vertices, const pbr_float4* normals, const pbr_ray* rays, int64_t n, uint32_t* counts
+) {
+	const int N = D->bvh_num_nodes;
+	Stats st;
+	memset(&st, 0, sizeof(st));
+	for (int64_t i = 0; i < n; i++) {
+		Scene scene = { D, bvh, nullptr, facesV, facesN, vertices, normals, v4s(0.0f), &st };
+		ray4 ray;
+		ray.origin = xyz(rays[i].origin);
+		ray.dir = xyz(rays[i].dir);
+		ray.normal = v3(0.0f, 0.0f, 0.0f);
+		ray.t = rays[i].dir.w;
+		ray.hitFace = 0;
+		ray.hitLeaf = -1;
+		const vec3 invDir = v3(pm::rcp(ray.dir.x), pm::rcp(ray.dir.y), pm::rcp(ray.dir.z));
+		int index = 1;
+		do {
+			counts[index]++;
+			const pbr_bvh_node node = bvh[index];
+			const int cur = index;
+			index = (node.bbMin.w <= -1.0f) ? (int) node.bbMax.w : cur + 1;
+			float tNear = 0.0f, tFar = INF_F;
+			if (!(intersectBox(&ray, &invDir, node.bbMin, node.bbMax, &tNear, &tFar) && tFar > EPSILON5 && ray.t > tNear)) continue;
+			index = cur + 1;
+			if (node.bbMin.w >= 0.0f) {
+				counts[0]++;
+				intersectFaces(&scene, &ray, &node, tNear, tFar, cur);
+			}
+		} while (index > 0 && index < N);
+	}
+}
+
 /* Scalar entry points of the pinned math, for tests/test_pinned_math.py. */
 float oracle_pm_sin(float x) { return pm::sin_(x); }
 float oracle_pm_cos(float x) { return pm::cos_(x); }

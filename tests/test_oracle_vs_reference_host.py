@@ -163,3 +163,25 @@ def test_reference_renderer_equals_oracle_pipeline(name):
             assert np.array_equal(r.kernel_arg(10, np.float32), p.lights.ravel())
     finally:
         r.close()
+
+
+def test_number_spellings_parse_like_the_reference(cfg, tmp_path):
+    """The reference reads coordinates with atof(); the product takes a shortcut (std::from_chars) for tokens that are
+    one plain decimal number and keeps atof for the rest.  Every spelling below must give the reference's bits."""
+    from pbr_b200 import host
+    spellings = ["1", "-1", "0.1", "-0.3333333333333333333333", "1e-3", "1E+2", "+0.5", ".5", "-.5", "1.", "1e", "1e+",
+                 "0x10", "-0x1p-2", "1e999", "-1e999", "1e-999", "4.9e-324", "1.17549435e-38", "3.4028235e38", "3.5e38",
+                 "-", "+", ".", "e5", "1.5abc", "12,5", "nan", "inf", "-infinity", "0", "-0", "00012.5000", "1_000",
+                 "0.1234567890123456789012345678901234567890123456789012345678901234567890", "16777217", "1e23", "8.5e-46"]
+    lines = ["o numbers", "usemtl none"]
+    for k in range(0, len(spellings) - 2):
+        lines.append("v %s %s %s" % (spellings[k], spellings[k + 1], spellings[k + 2]))
+        lines.append("vn %s %s %s" % (spellings[k + 2], spellings[k], spellings[k + 1]))
+    lines += ["f 1//1 2//2 3//3", "f 2//2 3//3 4//4"]
+    (tmp_path / "numbers.obj").write_text("\n".join(lines) + "\n")
+    (tmp_path / "numbers.mtl").write_text("newmtl none\nKd 1e-1 +0.5 .25\nd 0x1p-1\nNi 1.5abc\n")
+    path = str(tmp_path / "numbers.obj")
+    ref_scene, _ = RH.load(path, build_bvh=False, shadow_rays=0)
+    assert ref_scene["vertices"].size == 3 * (len(spellings) - 2)
+    _same_scene(O.load_obj(path, 0), ref_scene)
+    _same_scene(host.Scene.load(str(tmp_path) + "/", "numbers.obj").to_dict(), ref_scene)

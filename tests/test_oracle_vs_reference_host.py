@@ -185,3 +185,42 @@ def test_number_spellings_parse_like_the_reference(cfg, tmp_path):
     assert ref_scene["vertices"].size == 3 * (len(spellings) - 2)
     _same_scene(O.load_obj(path, 0), ref_scene)
     _same_scene(host.Scene.load(str(tmp_path) + "/", "numbers.obj").to_dict(), ref_scene)
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_random_obj_text_parses_like_the_reference(cfg, tmp_path, seed):
+    """tests/obj_fuzz.py: reference classes == restatement == product on random OBJ text (parsers only)."""
+    import obj_fuzz
+    from pbr_b200 import host
+    rng = np.random.default_rng(seed)
+    with open(tmp_path / "f.obj", "w", newline="") as f:
+        f.write(obj_fuzz.gen(rng, int(rng.integers(20, 400))))
+    (tmp_path / "f.mtl").write_text("newmtl red\nKd 1 0 0\nnewmtl glass\nd 0.5\nNi 1.5\nnewmtl sky_light\nKd 0.9 0.9 1\n")
+    path = str(tmp_path / "f.obj")
+    ref_scene, _ = RH.load(path, build_bvh=False, shadow_rays=0)
+    _same_scene(O.load_obj(path, 0), ref_scene)
+    _same_scene(host.Scene.load(str(tmp_path) + "/", "f.obj").to_dict(), ref_scene)
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_random_mtl_and_lights_text_parse_like_the_reference(cfg, tmp_path, seed):
+    """Random .mtl and .lights next to a fixed .obj; with render.shadow_rays = 1 the .lights file is read, and an
+    empty one switches shadow rays off (LightParser.cpp:119-121)."""
+    import obj_fuzz
+    from pbr_b200 import host
+    rng = np.random.default_rng(1000 + seed)
+    (tmp_path / "f.obj").write_text("o a\nv 0 0 0\nv 1 0 0\nv 0 1 0\nvn 0 0 1\nusemtl red\nf 1//1 2//1 3//1\n"
+                                    "usemtl glass\nf 3//1 2//1 1//1\nusemtl m3\nf 1//1 3//1 2//1\n")
+    with open(tmp_path / "f.mtl", "w", newline="") as f:
+        f.write(obj_fuzz.gen_mtl(rng, int(rng.integers(5, 120))))
+    with open(tmp_path / "f.lights", "w", newline="") as f:
+        f.write(obj_fuzz.gen_lights(rng, int(rng.integers(0, 40))))
+    path = str(tmp_path / "f.obj")
+    for shadow_rays in (1, 0):
+        ref_scene, _ = RH.load(path, build_bvh=False, shadow_rays=shadow_rays)
+        ora = O.load_obj(path, shadow_rays)
+        _same_scene(ora, ref_scene)
+        cfg.set("render.shadow_rays", shadow_rays)
+        _same_scene(host.Scene.load(str(tmp_path) + "/", "f.obj").to_dict(), ref_scene)
+        forced_off = int(cfg.get("render.shadow_rays")) == 0 and shadow_rays == 1
+        assert forced_off == ora["shadowRaysForcedOff"] == (shadow_rays == 1 and ref_scene["lights"].shape[0] == 0)

@@ -1,6 +1,7 @@
 """Random, plausible OBJ text for the parser comparison: every number spelling, blank and tab runs, CR line ends,
 all four face styles, objects, usemtl in odd places, unknown statements.  Lines on which the reference indexes past
 its token vector (a bare `o`, `usemtl`, `v 1 2`) are not generated: undefined upstream."""
+import numpy as np
 
 
 def num(rng):
@@ -100,3 +101,24 @@ def gen_lights(rng, nlines):
             line += "\r"
         out.append(line)
     return "\n".join(out) + ("\n" if rng.integers(0, 2) else "")
+
+
+def gen_bvh_scene(rng):
+    """Random small scene for the builder comparison: 1-4 objects of 1-200 triangles, coordinates optionally snapped to
+    a grid (tied centres, flat boxes), some degenerate triangles, and a random builder configuration.
+    Returns (obj text, BVH keyword arguments, number of faces)."""
+    nobj = int(rng.integers(1, 5)); lines = ["vn 0 0 1"]; nv = 0
+    snap = [None, 0.5, 0.25, 0.1][rng.integers(0, 4)]
+    for o in range(nobj):
+        lines += ["o obj%d" % o, "usemtl m"]
+        nf = int(rng.integers(1, [4, 30, 200][rng.integers(0, 3)]))
+        for f in range(nf):
+            tri = rng.uniform(-1, 1, 3) + rng.uniform(-0.3, 0.3, (3, 3))
+            if snap: tri = np.round(tri / snap) * snap
+            if rng.integers(0, 15) == 0: tri[2] = tri[1]
+            for v in tri: lines.append("v %.6f %.6f %.6f" % tuple(v))
+            lines.append("f %d//1 %d//1 %d//1" % (nv + 1, nv + 2, nv + 3)); nv += 3
+    kw = dict(max_faces=int(rng.integers(1, 3)), skip_ahead=bool(rng.integers(0, 2)), skip_ahead_compare=float(np.round(rng.uniform(0.05, 1.0), 3)),
+              sah_faces_limit=int([100000, 50, 8, 3][rng.integers(0, 4)]))
+    if rng.integers(0, 4) == 0: kw["phong_tess"] = float(np.round(rng.uniform(0.1, 1.0), 2))
+    return "\n".join(lines) + "\n", kw, nv // 3

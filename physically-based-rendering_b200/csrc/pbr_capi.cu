@@ -13,6 +13,8 @@
 #include <string.h>
 #include <string>
 #include <vector>
+#include <algorithm>
+#include <numeric>
 
 #include "../../include/pbr_b200.h"
 #include "pt_kernels.cuh"
@@ -88,6 +90,10 @@ struct pbr_ctx {
 	float4* tris = nullptr;
 	const float* trisB = nullptr;
 	const uint32_t* triMat = nullptr;
+#if PT_NODE_ORDER
+	int* nodeOrig = nullptr;                   /* permuted position -> index in the reference's array */
+	size_t nodeOrigCap = 0;
+#endif
 	size_t nodesCap = 0, trisCap = 0;
 	pbr_mem cacheBvh = 0, cacheFacesV = 0, cacheVertices = 0, cacheFacesN = 0, cacheNormals = 0;
 	bool cachePhong = false;
@@ -282,6 +288,49 @@ int ensureScene(pbr_ctx* ctx, pbr_mem hBvh, pbr_mem hFacesV, pbr_mem hVertices, 
 		LaunchScope ls(ctx, K_OTHER);
 		repackNodesKernel<<<gridFor(numDst, 256), 256, 0, ctx->stream>>>((const float4*) bvh->dptr, numNodes, ctx->nodes, numDst);
 	}
+#if PT_NODE_ORDER
+	{
+		/* Experiment (scripts/node_permutation_proto.py): hot nodes dense, explicit links.  Done on the host, once per
+		 * scene: positions 0 and 1 stay, the rest is ordered by surface area, ties in the reference's order. */
+		const int N = numDst;
+		std::vector<float> h((size_t) N * 8), out((size_t) N * 8);
+		CK(cudaStreamSynchronize(ctx->stream));
+		CK(cudaMemcpy(h.data(), ctx->nodes, (size_t) N * 32, cudaMemcpyDeviceToHost));
+		std::vector<double> key((size_t) N);
+		for (int i = 0; i < N; i++) {
+			const float* r = &h[(size_t) i * 8];
+			const float ex = fmaxf(r[4] - r[0], 0.0f), ey = fmaxf(r[5] - r[1], 0.0f), ez = fmaxf(r[6] - r[2], 0.0f);
+			key[(size_t) i] = (double) ex * ey + (double) ey * ez + (double) ex * ez;
+		}
+		std::vector<int> orig((size_t) N), pos((size_t) N);
+		std::iota(orig.begin(), orig.end(), 0);
+		std::stable_sort(orig.begin() + (N > 2 ? 2 : N), orig.end(), [&](int a, int b) { return key[(size_t) a] > key[(size_t) b]; });
+		for (int j = 0; j < N; j++) pos[(size_t) orig[(size_t) j]] = j;
+		const auto link = [&](long long t) -> int { return (t > 0 && t < (long long) numNodes) ? pos[(size_t) t] : 0; };
+		for (int j = 0; j < N; j++) {
+			const int i = orig[(size_t) j];
+			const float* r = &h[(size_t) i * 8];
+			float* o = &out[(size_t) j * 8];
+			memcpy(o, r, 32);
+			int loW, hiW;
+			memcpy(&loW, r + 3, 4);
+			memcpy(&hiW, r + 7, 4);
+			int nlo, nhi;
+			if (loW < 0) { nlo = link((long long) i + 1); nhi = link(hiW); }
+			else { nlo = loW; nhi = (int) ((unsigned) link((long long) i + 1) | 0x80000000u | (hiW != -1 ? 0x40000000u : 0u)); }
+			memcpy(o + 3, &nlo, 4);
+			memcpy(o + 7, &nhi, 4);
+		}
+		CK(cudaMemcpy(ctx->nodes, out.data(), (size_t) N * 32, cudaMemcpyHostToDevice));
+		if ((size_t) N > ctx->nodeOrigCap) {
+			if (ctx->nodeOrig) cudaFree(ctx->nodeOrig);
+			ctx->nodeOrig = nullptr;
+			CK(cudaMalloc(&ctx->nodeOrig, (size_t) N * sizeof(int)));
+			ctx->nodeOrigCap = (size_t) N;
+		}
+		CK(cudaMemcpy(ctx->nodeOrig, orig.data(), (size_t) N * sizeof(int), cudaMemcpyHostToDevice));
+	}
+#endif
 	if (numFaces > 0 && numVertices > 0) {
 		LaunchScope ls(ctx, K_OTHER);
 		if (phong) {
@@ -724,6 +773,9 @@ int pbr_destroy(pbr_ctx* ctx) {
 	for (Mem& m : ctx->mems) if (m.alive && m.dptr) cudaFree(m.dptr);
 	for (void* p : ctx->pinned) cudaFreeHost(p);
 	cudaFree(ctx->nodes); cudaFree(ctx->tris);
+#if PT_NODE_ORDER
+	cudaFree(ctx->nodeOrig);
+#endif
 	WaveState& W = ctx->wave;
 	cudaFree(W.rayO); cudaFree(W.rayD); cudaFree(W.colS); cudaFree(W.finF); cudaFree(W.misc); cudaFree(W.dbg); cudaFree(ctx->hitN);
 	cudaFree(ctx->qctl.queue[0]); cudaFree(ctx->qctl.queue[1]); cudaFree(ctx->qctl.ctrl);
@@ -1016,6 +1068,9 @@ static int launchFrames(pbr_ctx* ctx, int n, const float* seeds, const float* we
 	P.scene.tris = ctx->tris;
 	P.scene.trisB = ctx->trisB;
 	P.scene.triMat = ctx->triMat;
+#if PT_NODE_ORDER
+	P.scene.nodeOrig = ctx->nodeOrig;
+#endif
 	P.scene.lights = (const pbr_light*) lights->dptr;
 	P.scene.numNodes = ctx->numNodesDev;
 	P.scene.numLights = D.num_lights;
@@ -1283,6 +1338,9 @@ static int traceImpl(pbr_ctx* ctx, pbr_mem bvh, pbr_mem facesV, pbr_mem vertices
 	S.tris = ctx->tris;
 	S.trisB = ctx->trisB;
 	S.triMat = ctx->triMat;
+#if PT_NODE_ORDER
+	S.nodeOrig = ctx->nodeOrig;
+#endif
 	S.numNodes = ctx->numNodesDev;
 	S.numLights = 0;
 	S.lights = nullptr;

@@ -41,11 +41,18 @@ using pm::v3;
 #define PT_M_PI_2 1.57079632679489661923
 #define PT_M_1_PI 0.31830988618379067154
 
+#ifndef PT_NODE_ORDER
+#define PT_NODE_ORDER 0            /* 1: permuted node array with explicit links (experiment, see decodeNode) */
+#endif
+
 struct SceneDev {
 	const float4* nodes;          /* 2 x float4 per node */
 	const float4* tris;           /* 2 x float4 (32 B) per face; PHONGTESS: 6 x float4 (a b c an bn cn) */
 	const float* trisB;           /* + 4 B per face (edge2.z); unused with PHONGTESS */
 	const uint32_t* triMat;       /* material index per face, read once per shaded hit; unused with PHONGTESS */
+#if PT_NODE_ORDER
+	const int* nodeOrig;          /* permuted position -> index in the reference's array (for the `leaf` output) */
+#endif
 	const pbr_light* lights;
 	float phongAlpha;             /* PHONGTESS_ALPHA */
 	int numNodes;
@@ -95,6 +102,40 @@ __device__ __forceinline__ void loadNode(const float4* nodes, int index, float4&
 	asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
 		: "=f"(lo.x), "=f"(lo.y), "=f"(lo.z), "=f"(lo.w), "=f"(hi.x), "=f"(hi.y), "=f"(hi.z), "=f"(hi.w)
 		: "l"(nodes + 2 * (size_t) index));
+}
+
+/*
+ * The two index words of a node record.
+ * PT_NODE_ORDER == 0: the reference's array order (pre-order).  lo.w = first face or -1 (inner node), hi.w = second
+ *   face or -1 (leaf) / miss link (inner node); the node after a box hit, and after a leaf, is cur + 1.
+ * PT_NODE_ORDER == 1 (experiment, scripts/node_permutation_proto.py): the array is permuted so that the nodes with
+ *   the largest surface area -- the most visited ones -- are dense, and every link is explicit: inner node lo.w =
+ *   where to go after a box hit, hi.w = miss link; leaf lo.w = first face, hi.w = successor | LEAF | (TWO: a second
+ *   face, always first + 1).  Link 0 ends the walk.  Every ray visits the same nodes in the same order.
+ */
+struct NodeWords {
+	bool leaf;
+	int afterMiss;     /* next node when the box is missed -- and after a leaf, hit or not */
+	int afterHit;      /* next node when the box of an inner node is hit */
+	int face0, face1;  /* leaf: its faces (face1 = -1: only one) */
+};
+
+__device__ __forceinline__ NodeWords decodeNode(const int cur, const int loW, const int hiW) {
+	NodeWords w;
+#if PT_NODE_ORDER
+	w.leaf = hiW < 0;
+	w.afterMiss = hiW & 0x3fffffff;
+	w.afterHit = w.leaf ? w.afterMiss : loW;
+	w.face0 = loW;
+	w.face1 = (hiW & 0x40000000) ? loW + 1 : -1;
+#else
+	w.leaf = loW >= 0;
+	w.afterMiss = w.leaf ? cur + 1 : hiW;
+	w.afterHit = cur + 1;
+	w.face0 = loW;
+	w.face1 = hiW;
+#endif
+	return w;
 }
 
 #define PT_TRI_STRIDE 2           /* float4s per triangle record in `tris` */
@@ -512,24 +553,24 @@ __device__ __forceinline__ void traverseClosest(
 		float4 lo, hi;
 		loadNode(S.nodes, index, lo, hi);
 		const int cur = index;
-		const int loW = __float_as_int(lo.w), hiW = __float_as_int(hi.w);
+		const NodeWords w = decodeNode(cur, __float_as_int(lo.w), __float_as_int(hi.w));
 
-		index = (loW < 0) ? hiW : cur + 1;
+		index = w.afterMiss;
 
 		float tNear, tFar;
 		const bool isNodeHit = intersectBox(o, invDir, lo, hi, tNear, tFar) && tFar > PT_EPSILON5 && rt > tNear;
 
 		if (!isNodeHit) continue;
 
-		index = cur + 1;
+		index = w.afterHit;
 
-		if (loW >= 0) {
-			if (PHONG) intersectFacePhong(S, loW, cur, o, d, tNear, tFar, rt, hitFace, hitLeaf, hitNormal);
-			else intersectFace(S, loW, cur, o, d, tNear, rt, hitFace, hitLeaf);
+		if (w.leaf) {
+			if (PHONG) intersectFacePhong(S, w.face0, cur, o, d, tNear, tFar, rt, hitFace, hitLeaf, hitNormal);
+			else intersectFace(S, w.face0, cur, o, d, tNear, rt, hitFace, hitLeaf);
 			nTris++;
-			if (hiW != -1) {
-				if (PHONG) intersectFacePhong(S, hiW, cur, o, d, tNear, tFar, rt, hitFace, hitLeaf, hitNormal);
-				else intersectFace(S, hiW, cur, o, d, tNear, rt, hitFace, hitLeaf);
+			if (w.face1 != -1) {
+				if (PHONG) intersectFacePhong(S, w.face1, cur, o, d, tNear, tFar, rt, hitFace, hitLeaf, hitNormal);
+				else intersectFace(S, w.face1, cur, o, d, tNear, rt, hitFace, hitLeaf);
 				nTris++;
 			}
 		}
@@ -555,24 +596,24 @@ __device__ __forceinline__ void traverseAny(
 		float4 lo, hi;
 		loadNode(S.nodes, index, lo, hi);
 		const int cur = index;
-		const int loW = __float_as_int(lo.w), hiW = __float_as_int(hi.w);
+		const NodeWords w = decodeNode(cur, __float_as_int(lo.w), __float_as_int(hi.w));
 
-		index = (loW < 0) ? hiW : cur + 1;
+		index = w.afterMiss;
 
 		float tNear, tFar;
 		const bool isNodeHit = intersectBox(o, invDir, lo, hi, tNear, tFar) && tFar > PT_EPSILON5;
 
 		if (!isNodeHit) continue;
 
-		index = cur + 1;
+		index = w.afterHit;
 
-		if (loW >= 0) {
-			if (PHONG) intersectFacePhong(S, loW, cur, o, d, tNear, tFar, rt, hitFace, hitLeaf, hitNormal);
-			else intersectFace(S, loW, cur, o, d, tNear, rt, hitFace, hitLeaf);
+		if (w.leaf) {
+			if (PHONG) intersectFacePhong(S, w.face0, cur, o, d, tNear, tFar, rt, hitFace, hitLeaf, hitNormal);
+			else intersectFace(S, w.face0, cur, o, d, tNear, rt, hitFace, hitLeaf);
 			nTris++;
-			if (hiW != -1) {
-				if (PHONG) intersectFacePhong(S, hiW, cur, o, d, tNear, tFar, rt, hitFace, hitLeaf, hitNormal);
-				else intersectFace(S, hiW, cur, o, d, tNear, rt, hitFace, hitLeaf);
+			if (w.face1 != -1) {
+				if (PHONG) intersectFacePhong(S, w.face1, cur, o, d, tNear, tFar, rt, hitFace, hitLeaf, hitNormal);
+				else intersectFace(S, w.face1, cur, o, d, tNear, rt, hitFace, hitLeaf);
 				nTris++;
 			}
 			if (rt < tLight) break;

@@ -158,20 +158,20 @@ template <bool ANY_HIT>
 __device__ __forceinline__ bool nodeVisit(LaneRay& L, const float4 lo, const float4 hi) {
 	L.nn++;
 	const int cur = L.index;
-	const int loW = __float_as_int(lo.w), hiW = __float_as_int(hi.w);
+	const NodeWords w = decodeNode(cur, __float_as_int(lo.w), __float_as_int(hi.w));
 
-	L.index = (loW < 0) ? hiW : cur + 1;
+	L.index = w.afterMiss;
 
 	float tNear, tFar;
 	bool isNodeHit = intersectBox(L.o, L.invDir, lo, hi, tNear, tFar) && tFar > PT_EPSILON5;
 	if (!ANY_HIT) isNodeHit = isNodeHit && (L.rt > tNear);
 	if (!isNodeHit) return false;
 
-	L.index = cur + 1;
-	if (loW < 0) return false;
+	L.index = w.afterHit;
+	if (!w.leaf) return false;
 	L.leafCur = cur;
-	L.leafF0 = loW;
-	L.leafF1 = hiW;
+	L.leafF0 = w.face0;
+	L.leafF1 = w.face1;
 	L.leafTNear = tNear;
 	L.leafTFar = tFar;
 	return true;
@@ -689,6 +689,9 @@ __global__ void __launch_bounds__(128) megaKernel(const FrameParams P, const int
 struct ExplicitRaySource {
 	const pbr_ray* __restrict__ rays;
 	pbr_hit* __restrict__ hits;
+#if PT_NODE_ORDER
+	const int* __restrict__ nodeOrig;
+#endif
 	__device__ __forceinline__ void fetch(unsigned long long i, vec3& o, vec3& d, float& rt, int& hf) {
 		const float4 a = __ldg((const float4*) &rays[i].origin);
 		const float4 b = __ldg((const float4*) &rays[i].dir);
@@ -701,7 +704,11 @@ struct ExplicitRaySource {
 		int4 out;
 		out.x = __float_as_int(L.rt);
 		out.y = L.hitFace;
+#if PT_NODE_ORDER
+		out.z = (L.hitLeaf > 0) ? __ldg(nodeOrig + L.hitLeaf) : L.hitLeaf;      /* back to the reference's numbering */
+#else
 		out.z = L.hitLeaf;
+#endif
 		out.w = (int) (min(L.nn, 0xfffffu) | (min(L.nt, 0xfffu) << 20));
 		*((int4*) &hits[i]) = out;
 	}
@@ -713,7 +720,11 @@ __global__ void __launch_bounds__(128, PT_TRAVERSE_MIN_BLOCKS) traceRaysKernel(
 	unsigned long long* cursor, unsigned long long* stats
 ) {
 	uint32_t nodes = 0, tris = 0, cnt = 0;
+#if PT_NODE_ORDER
+	ExplicitRaySource src = {rays, hits, S.nodeOrig};
+#else
 	ExplicitRaySource src = {rays, hits};
+#endif
 	traverseEngine<ANY_HIT, false>(S, src, (unsigned long long) n, cursor, nodes, tris, cnt);
 	warpAddStat(stats + (ANY_HIT ? 1 : 0), cnt);
 	warpAddStat(stats + (ANY_HIT ? 5 : 2), nodes);

@@ -65,6 +65,29 @@ if os.path.isfile(n8path):
             r8["shadow"]["mrays_per_s"], r8["primary"]["hit_face_leaf_t_bit_exact"], r8["shadow"]["hit_face_leaf_t_bit_exact"]))
 out.append("Pipelines on C2, ms per 1080p frame: wavefront 4.58 (what the measured choice picks here) | megakernel 7.7 | persistent kernels 4.92 | carry-over 5.5 | wavefront with "
            "interleaved frame batches 5.2 -- all bit-identical (DESIGN.md section 6).")
+PEAK = n[1]["roofline"]["peak"]
+
+
+def nodefetch(mrays, nodes_per_ray):
+    gbs = mrays * 1e6 * 32.0 * nodes_per_ray / 1e9
+    return "%.0f GB/s = %.0f %%" % (gbs, 100.0 * gbs / PEAK)
+
+
+out.append("\nNode-fetch bandwidth (algorithmic: 32 B x nodes visited, SURVEY 8d; triangle records not counted except on the bench line) "
+           "against the measured HBM peak of %.0f GB/s -- served by L1 / L2, DRAM traffic is ~2 %% of it:\n" % PEAK)
+out.append("| Config | nodes per ray | node-fetch GB/s, % of the HBM roofline |")
+out.append("|---|---|---|")
+out.append("| C1 suzanne | %.1f | %s |" % (c["c1"]["nodes_per_ray"], nodefetch(c["c1"]["gpu_mrays_per_s"], c["c1"]["nodes_per_ray"])))
+out.append("| C2 soup (bench.py; nodes + triangle tests: %.0f GB/s = %.0f %%) | %.1f | %s |" % (
+    n[1]["roofline"]["achieved"], 100 * n[1]["roofline"]["frac"], n[1]["roofline"]["nodes_per_ray"],
+    nodefetch(n[1]["value"], n[1]["roofline"]["nodes_per_ray"])))
+out.append("| C3 interior BRDF 1 / BRDF 0 | %.1f / %.1f | %s / %s |" % (b3["nodes_per_ray"], s3["nodes_per_ray"],
+           nodefetch(b3["gpu_mrays_per_s"], b3["nodes_per_ray"]), nodefetch(s3["gpu_mrays_per_s"], s3["nodes_per_ray"])))
+out.append("| C4 10M-triangle grid | %.1f | %s |" % (c["c4"]["nodes_per_ray"], nodefetch(c["c4"]["gpu_mrays_per_s"], c["c4"]["nodes_per_ray"])))
+r50 = c["c5"]["sweep"][-1]
+out.append("| C5 %d M explicit rays, primary / shadow | %.1f / %.1f | %s / %s |" % (r50["requested_mrays"], r50["primary"]["nodes_per_ray"],
+           r50["shadow"]["nodes_per_ray"], nodefetch(r50["primary"]["mrays_per_s"], r50["primary"]["nodes_per_ray"]),
+           nodefetch(r50["shadow"]["mrays_per_s"], r50["shadow"]["nodes_per_ray"])))
 fin = os.path.join(P, "bench_%s_n1_final.json" % tag)
 if os.path.isfile(fin):
     f1 = load("bench_%s_n1_final.json" % tag)

@@ -1489,6 +1489,43 @@ void oracle_visit_histogram_pruned(
 	}
 }
 
+/* Analysis helper: the node indices ray i visits, in order, into trace[i * cap ...] (at most cap; lengths[i] = how
+ * many there were).  Same walk as oracle_visit_histogram_pruned. */
+void oracle_visit_trace(
+	const pbr_defines* D, const pbr_bvh_node* bvh, const pbr_uint4* facesV, const pbr_uint4* facesN,
+	const pbr_float4* vertices, const pbr_float4* normals, const pbr_ray* rays, int64_t n, int32_t cap,
+	int32_t* trace, int32_t* lengths
+) {
+	const int N = D->bvh_num_nodes;
+	Stats st;
+	memset(&st, 0, sizeof(st));
+	for (int64_t i = 0; i < n; i++) {
+		Scene scene = { D, bvh, nullptr, facesV, facesN, vertices, normals, v4s(0.0f), &st };
+		ray4 ray;
+		ray.origin = xyz(rays[i].origin);
+		ray.dir = xyz(rays[i].dir);
+		ray.normal = v3(0.0f, 0.0f, 0.0f);
+		ray.t = rays[i].dir.w;
+		ray.hitFace = 0;
+		ray.hitLeaf = -1;
+		const vec3 invDir = v3(pm::rcp(ray.dir.x), pm::rcp(ray.dir.y), pm::rcp(ray.dir.z));
+		int index = 1;
+		int32_t len = 0;
+		do {
+			if (len < cap) trace[i * cap + len] = index;
+			len++;
+			const pbr_bvh_node node = bvh[index];
+			const int cur = index;
+			index = (node.bbMin.w <= -1.0f) ? (int) node.bbMax.w : cur + 1;
+			float tNear = 0.0f, tFar = INF_F;
+			if (!(intersectBox(&ray, &invDir, node.bbMin, node.bbMax, &tNear, &tFar) && tFar > EPSILON5 && ray.t > tNear)) continue;
+			index = cur + 1;
+			if (node.bbMin.w >= 0.0f) intersectFaces(&scene, &ray, &node, tNear, tFar, cur);
+		} while (index > 0 && index < N);
+		lengths[i] = len;
+	}
+}
+
 /* Scalar entry points of the pinned math, for tests/test_pinned_math.py. */
 float oracle_pm_sin(float x) { return pm::sin_(x); }
 float oracle_pm_cos(float x) { return pm::cos_(x); }

@@ -41,6 +41,9 @@ using pm::v3;
 #define PT_M_PI_2 1.57079632679489661923
 #define PT_M_1_PI 0.31830988618379067154
 
+#ifndef PT_TRI_NO_L1
+#define PT_TRI_NO_L1 0             /* 1: triangle records are loaded with L1::no_allocate (experiment) */
+#endif
 #ifndef PT_NODE_ORDER
 #define PT_NODE_ORDER 0            /* 1: permuted node array with explicit links (experiment, see decodeNode) */
 #endif
@@ -147,10 +150,19 @@ __device__ __forceinline__ NodeWords decodeNode(const int cur, const int loW, co
 __device__ __forceinline__ void loadTri(const SceneDev& S, int face, float4& A, float4& E1, float4& E2) {
 	const float4* p = S.tris + PT_TRI_STRIDE * (size_t) face;
 	float e1y, e1z, e2x, e2y;
+#if PT_TRI_NO_L1
+	/* experiment: triangle records bypass L1, so that they do not evict the node lines the rays are walking in */
+	asm volatile("ld.global.nc.L1::no_allocate.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+		: "=f"(A.x), "=f"(A.y), "=f"(A.z), "=f"(E1.x), "=f"(e1y), "=f"(e1z), "=f"(e2x), "=f"(e2y)
+		: "l"(p));
+	float e2z;
+	asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(e2z) : "l"(S.trisB + face));
+#else
 	asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
 		: "=f"(A.x), "=f"(A.y), "=f"(A.z), "=f"(E1.x), "=f"(e1y), "=f"(e1z), "=f"(e2x), "=f"(e2y)
 		: "l"(p));
 	const float e2z = __ldg(S.trisB + face);
+#endif
 	A.w = 0.0f;
 	E1.y = e1y; E1.z = e1z; E1.w = 0.0f;
 	E2 = make_float4(e2x, e2y, e2z, 0.0f);

@@ -1490,7 +1490,8 @@ void oracle_visit_histogram_pruned(
 }
 
 /* Analysis helper: the node indices ray i visits, in order, into trace[i * cap ...] (at most cap; lengths[i] = how
- * many there were).  Same walk as oracle_visit_histogram_pruned. */
+ * many there were).  Same walk as oracle_visit_histogram_pruned; a face handed to the triangle test appears as
+ * -(face + 1) behind its leaf. */
 void oracle_visit_trace(
 	const pbr_defines* D, const pbr_bvh_node* bvh, const pbr_uint4* facesV, const pbr_uint4* facesN,
 	const pbr_float4* vertices, const pbr_float4* normals, const pbr_ray* rays, int64_t n, int32_t cap,
@@ -1520,7 +1521,16 @@ void oracle_visit_trace(
 			float tNear = 0.0f, tFar = INF_F;
 			if (!(intersectBox(&ray, &invDir, node.bbMin, node.bbMax, &tNear, &tFar) && tFar > EPSILON5 && ray.t > tNear)) continue;
 			index = cur + 1;
-			if (node.bbMin.w >= 0.0f) intersectFaces(&scene, &ray, &node, tNear, tFar, cur);
+			if (node.bbMin.w >= 0.0f) {
+				/* the faces this leaf hands to the triangle test, as -(face + 1) */
+				if (len < cap) trace[i * cap + len] = -((int) node.bbMin.w + 1);
+				len++;
+				if (node.bbMax.w >= 0.0f) {
+					if (len < cap) trace[i * cap + len] = -((int) node.bbMax.w + 1);
+					len++;
+				}
+				intersectFaces(&scene, &ray, &node, tNear, tFar, cur);
+			}
 		} while (index > 0 && index < N);
 		lengths[i] = len;
 	}

@@ -1,8 +1,8 @@
 """CPU estimate for the node-permutation experiment: an LRU cache of 128-byte lines the size of
-an SM's L1 in front of the node fetches of as many rays as an SM has in flight, stepped round-robin -- hit rate with
-the node array in the reference's pre-order against the array permuted by surface area (scripts/node_permutation_proto.py).
-Only node fetches are simulated (triangle records and the path-state stream compete for the same L1 on the device), so
-the absolute numbers are optimistic; the difference between the two layouts is the point.
+an SM's L1 in front of the node and triangle fetches of as many rays as an SM has in flight, stepped round-robin.
+The cache is modelled the way the hardware fills it -- a miss brings in the one 32-byte sector that was asked for, the
+other three sectors of the line stay invalid -- and, for comparison, as if a miss filled the whole line.  Layouts: the
+reference's pre-order against the array permuted by surface area (scripts/node_permutation_proto.py).
     python scripts/l1_sim.py [tris]"""
 import ctypes as C
 import os
@@ -59,7 +59,10 @@ def traces(rays):
     return tr, np.minimum(ln, CAP)
 
 
-def hit_rate(tr, ln, index_of, lines):
+TRI_TAG, TRIB_TAG = 1 << 40, 1 << 41
+
+
+def hit_rate(tr, ln, index_of, lines, with_tris=False, sectored=True):
     """Rays enter in order, IN_FLIGHT at a time, one node step per ray per round; a finished ray is replaced by the next."""
     cache = OrderedDict()
     hits = total = 0
@@ -72,15 +75,28 @@ def hit_rate(tr, ln, index_of, lines):
             r = slot_ray[s]
             if r < 0:
                 continue
-            line = int(index_of[tr[r, slot_step[s]]]) >> 2          # four 32-byte nodes per 128-byte line
-            total += 1
-            if line in cache:
-                hits += 1
-                cache.move_to_end(line)
+            e = int(tr[r, slot_step[s]])
+            if e >= 0:
+                k = int(index_of[e])
+                touched = ((k >> 2, 1 << (k & 3)),)                 # four 32-byte nodes (sectors) per 128-byte line
+                total += 1
+            elif not with_tris:
+                touched = ()
             else:
-                cache[line] = True
-                if len(cache) > lines:
-                    cache.popitem(last=False)
+                f = -e - 1                                          # 32-byte record + 4-byte word of a face: two more lines
+                touched = ((TRI_TAG + (f >> 2), 1 << (f & 3)), (TRIB_TAG + (f >> 5), 1 << ((f >> 3) & 3)))
+            for line, sector in touched:
+                valid = cache.get(line)
+                if valid is not None:
+                    cache.move_to_end(line)
+                    if sectored and not (valid & sector):
+                        cache[line] = valid | sector                # tag hit, sector miss: only this sector is fetched
+                    else:
+                        hits += e >= 0
+                else:
+                    cache[line] = sector if sectored else 15
+                    if len(cache) > lines:
+                        cache.popitem(last=False)
             slot_step[s] += 1
             if slot_step[s] >= ln[r]:
                 if nxt < len(ln):
@@ -97,12 +113,15 @@ ident = np.arange(N, dtype=np.int64)
 sets = (("primary", Hh.primary_rays(P, 320, 180)[:4 * IN_FLIGHT]), ("random", Hh.random_rays(4 * IN_FLIGHT, 1, -1.0, 1.0)))
 for name, rays in sets:
     tr, ln = traces(rays)
-    for kb in ([] if os.environ.get('L1_SIM_SKIP_CACHE') else [128, 192, 256]):
+    for kb in ([] if os.environ.get('L1_SIM_SKIP_CACHE') else [128, 224]):
         lines = kb * 1024 // 128
-        a = hit_rate(tr, ln, ident, lines)
-        b = hit_rate(tr, ln, pos, lines)
-        print("%-8s L1 %3d KB: node fetches hitting, pre-order %.1f %%  ->  by surface area %.1f %%   (%.1f visits/ray)" % (
-            name, kb, 100 * a, 100 * b, ln.mean()), flush=True)
+        a = hit_rate(tr, ln, ident, lines, with_tris=True)
+        b = hit_rate(tr, ln, pos, lines, with_tris=True)
+        c = hit_rate(tr, ln, ident, lines, with_tris=True, sectored=False)
+        d = hit_rate(tr, ln, ident, lines, with_tris=False)
+        print("%-8s L1 %3d KB: node fetches hitting (triangle records go through the same cache), sector fills: pre-order %.1f %%, "
+              "by surface area %.1f %%, pre-order with the triangle records kept out of L1 %.1f %%;  whole-line fills, pre-order: %.1f %%" % (
+                  name, kb, 100 * a, 100 * b, 100 * d, 100 * c), flush=True)
 
 # What a private line buffer per ray would catch (no cache at all): visits that stay in the 128-byte line of the
 # previous visit of the same ray, or in one of the last two lines; the same for 64-byte pairs.
@@ -110,12 +129,13 @@ for name, rays in sets:
     tr, ln = traces(rays)
     same = two = pair = total = 0
     for r in range(len(ln)):
-        li = tr[r, :ln[r]] >> 2
+        nodes_only = tr[r, :ln[r]][tr[r, :ln[r]] >= 0]
+        li = nodes_only >> 2
         total += len(li) - 1
         s1 = li[1:] == li[:-1]
         same += int(s1.sum())
         two += int((s1[1:] | (li[2:] == li[:-2])).sum()) + int(s1[:1].sum())
-        pi = tr[r, :ln[r]] >> 1
+        pi = nodes_only >> 1
         pair += int((pi[1:] == pi[:-1]).sum())
     print("%-8s private buffer per ray: next node in the same 128-byte line %.1f %% of the visits, in one of the last two lines "
           "%.1f %%, in the same 64-byte pair %.1f %%" % (name, 100 * same / total, 100 * two / total, 100 * pair / total), flush=True)

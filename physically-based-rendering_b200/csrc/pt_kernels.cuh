@@ -188,6 +188,9 @@ __device__ __forceinline__ bool nodeStep(const SceneDev& S, LaneRay& L) {
 #ifndef PT_LEAF_HOIST
 #define PT_LEAF_HOIST 1
 #endif
+#ifndef PT_HELPER_PREFETCH
+#define PT_HELPER_PREFETCH 0               /* 1, 2: resting lanes fetch the neighbour sector for stepping lanes (experiment) */
+#endif
 #ifndef PT_TRAVERSE_MIN_BLOCKS
 #define PT_TRAVERSE_MIN_BLOCKS 9           /* resident blocks of 128 threads per SM the traversal kernels are compiled for */
 #endif
@@ -274,6 +277,39 @@ __device__ __forceinline__ void traverseEngine(
 		if (__ballot_sync(FULL, state != LANE_IDLE) == 0u) break;
 
 		/* node phase: index stays inside [1, numNodes) while a lane is stepping */
+#if PT_HELPER_PREFETCH
+		/* Experiment: L1 fills one 32-byte sector per miss, so the node behind the one a ray
+		 * visits -- its left child, 47 % of all successors are in the same 128-byte line -- is not in L1 when the
+		 * ray gets there.  Lanes that are not stepping in this round ride along in the same load instruction and
+		 * ask for that neighbour sector on behalf of a stepping lane: same line, so the same L1 request, and the
+		 * stepping lane's next fetch finds it.  The value is discarded; no ray's walk changes.
+		 * 1: a lane helps its neighbour (lane ^ 1);  2: the r-th resting lane helps the r-th stepping lane. */
+		unsigned stepMask = __ballot_sync(FULL, state == LANE_STEPPING);
+		while (true) {
+			int helpFor = lane;
+			if (PT_HELPER_PREFETCH == 1) {
+				if (state != LANE_STEPPING && ((stepMask >> (lane ^ 1)) & 1u)) helpFor = lane ^ 1;
+			}
+			else {
+				const int r = __popc(~stepMask & ltMask);
+				if (state != LANE_STEPPING && r < __popc(stepMask)) helpFor = (int) __fns(stepMask, 0u, r + 1);
+			}
+			const int theirs = __shfl_sync(FULL, L.index, helpFor);
+			const int succ = theirs + 1;
+			const bool helper = (helpFor != lane) && ((succ & 3) != 0) && ((unsigned) (succ - 1) < lastNode);
+			if (state == LANE_STEPPING || helper) {
+				float4 lo, hi;
+				loadNode(S.nodes, (state == LANE_STEPPING) ? L.index : succ, lo, hi);
+				if (state == LANE_STEPPING) {
+					const bool leaf = nodeVisit<ANY_HIT>(L, lo, hi);
+					const bool inside = (unsigned) (L.index - 1) < lastNode;
+					state = leaf ? LANE_PENDING : (inside ? LANE_STEPPING : LANE_FINISHED);
+				}
+			}
+			stepMask = __ballot_sync(FULL, state == LANE_STEPPING);
+			if (__popc(stepMask) < S.nodePhaseMin) break;
+		}
+#else
 		while (true) {
 			if (state == LANE_STEPPING) {
 				const bool leaf = nodeStep<ANY_HIT>(S, L);
@@ -282,6 +318,7 @@ __device__ __forceinline__ void traverseEngine(
 			}
 			if (__popc(__ballot_sync(FULL, state == LANE_STEPPING)) < S.nodePhaseMin) break;
 		}
+#endif
 
 		/* triangle phase */
 		if (state == LANE_PENDING) {

@@ -62,9 +62,11 @@ def traces(rays):
 TRI_TAG, TRIB_TAG = 1 << 40, 1 << 41
 
 
-def hit_rate(tr, ln, index_of, lines, with_tris=False, sectored=True):
+def hit_rate(tr, ln, index_of, lines, with_tris=False, sectored=True, neighbour=0.0):
     """Rays enter in order, IN_FLIGHT at a time, one node step per ray per round; a finished ray is replaced by the next."""
     cache = OrderedDict()
+    rng = np.random.default_rng(0)
+    helped = None
     hits = total = 0
     nxt = min(IN_FLIGHT, len(ln))
     slot_ray = list(range(nxt))
@@ -80,18 +82,25 @@ def hit_rate(tr, ln, index_of, lines, with_tris=False, sectored=True):
                 k = int(index_of[e])
                 touched = ((k >> 2, 1 << (k & 3)),)                 # four 32-byte nodes (sectors) per 128-byte line
                 total += 1
+                if neighbour > 0.0 and (k & 3) != 3 and rng.random() < neighbour:
+                    helped = (k >> 2, 1 << ((k & 3) + 1))           # a resting lane asks for the next sector of the line
             elif not with_tris:
                 touched = ()
             else:
                 f = -e - 1                                          # 32-byte record + 4-byte word of a face: two more lines
                 touched = ((TRI_TAG + (f >> 2), 1 << (f & 3)), (TRIB_TAG + (f >> 5), 1 << ((f >> 3) & 3)))
-            for line, sector in touched:
+            if e >= 0 and helped is not None:
+                touched = touched + (helped + (True,),)
+                helped = None
+            for entry in touched:
+                line, sector = entry[0], entry[1]
+                silent = len(entry) > 2
                 valid = cache.get(line)
                 if valid is not None:
                     cache.move_to_end(line)
                     if sectored and not (valid & sector):
                         cache[line] = valid | sector                # tag hit, sector miss: only this sector is fetched
-                    else:
+                    elif not silent:
                         hits += e >= 0
                 else:
                     cache[line] = sector if sectored else 15
@@ -113,15 +122,18 @@ ident = np.arange(N, dtype=np.int64)
 sets = (("primary", Hh.primary_rays(P, 320, 180)[:4 * IN_FLIGHT]), ("random", Hh.random_rays(4 * IN_FLIGHT, 1, -1.0, 1.0)))
 for name, rays in sets:
     tr, ln = traces(rays)
-    for kb in ([] if os.environ.get('L1_SIM_SKIP_CACHE') else [128, 224]):
+    for kb in ([] if os.environ.get('L1_SIM_SKIP_CACHE') else [224]):
         lines = kb * 1024 // 128
         a = hit_rate(tr, ln, ident, lines, with_tris=True)
         b = hit_rate(tr, ln, pos, lines, with_tris=True)
         c = hit_rate(tr, ln, ident, lines, with_tris=True, sectored=False)
         d = hit_rate(tr, ln, ident, lines, with_tris=False)
+        h1 = hit_rate(tr, ln, ident, lines, with_tris=True, neighbour=0.45)
+        h2 = hit_rate(tr, ln, ident, lines, with_tris=True, neighbour=0.7)
         print("%-8s L1 %3d KB: node fetches hitting (triangle records go through the same cache), sector fills: pre-order %.1f %%, "
-              "by surface area %.1f %%, pre-order with the triangle records kept out of L1 %.1f %%;  whole-line fills, pre-order: %.1f %%" % (
-                  name, kb, 100 * a, 100 * b, 100 * d, 100 * c), flush=True)
+              "by surface area %.1f %%, pre-order with the triangle records kept out of L1 %.1f %%, pre-order with the neighbour sector "
+              "fetched along on 45 %% / 70 %% of the fetches %.1f %% / %.1f %%;  whole-line fills, pre-order: %.1f %%" % (
+                  name, kb, 100 * a, 100 * b, 100 * d, 100 * h1, 100 * h2, 100 * c), flush=True)
 
 # What a private line buffer per ray would catch (no cache at all): visits that stay in the 128-byte line of the
 # previous visit of the same ray, or in one of the last two lines; the same for 64-byte pairs.

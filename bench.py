@@ -433,7 +433,22 @@ def run_ours(args):
     # ---- CPU baseline (rank 0, N = 1 only) ---------------------------------------------------------
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu_baseline = cpu_baseline_sample(w, r.flat(), scene)
+        cpu_baseline, cpu_frames, cpu_image = cpu_baseline_sample(w, r.flat(), scene)
+        # parity at the bench configuration itself: the frames the CPU arm has just rendered with the reference
+        # kernel (same seeds, same accumulation from a black image) against the same frames on the GPU, bit for bit
+        r.set_render_ahead(False)
+        r.reset_sample_count()
+        r.render_frames(cpu_frames)
+        gpu_image = r.read_image()
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import helpers as Hh
+        verify = {
+            "frames": cpu_frames, "pixels": W * H,
+            "bit_identical_pixels": Hh.count_identical_pixels(gpu_image, cpu_image),
+            "mre": Hh.mean_relative_error(gpu_image, cpu_image),
+            "what": "accumulated image after %d frame(s): GPU (%s) vs the CPU arm's %s kernel, all four channels" % (
+                cpu_frames, "reference-order walk", cpu_baseline["kind"]),
+        }
 
     if rank == 0:
         line = {
@@ -530,7 +545,8 @@ def cpu_baseline_sample(w, flat, scene, budget_s=12.0):
     sec = time.perf_counter() - t0
     rays = sum(count_rays(k, inputs[k]) for k in range(frames))
     return {"value": round(rays / sec / 1e6, 3), "unit": "Mrays/s", "cores": threads, "kind": kind,
-            "sample": "%d frame(s) of the full %dx%d image at 1 spp (%d rays) in %.1f s" % (frames, W, H, rays, sec)}
+            "sample": "%d frame(s) of the full %dx%d image at 1 spp (%d rays) in %.1f s" % (frames, W, H, rays, sec)}, \
+        frames, img
 
 
 # ------------------------------------------------------------------------------------------- reference

@@ -126,15 +126,12 @@ int pbr_set_tile(pbr_ctx* ctx, int32_t y0, int32_t y1);
  * switches back to pbr_set_tile's contiguous rows. */
 int pbr_set_tile_stripes(pbr_ctx* ctx, int32_t stripe_rows, int32_t world, int32_t rank);
 /* Choose the device pipeline.  -1 (default) = by measurement: after one warm-up frame of a configuration (scene, frame
- * size, kernel variant) two frames run as 0 and two as 1, alternately, all timed, and the faster of the two renders the rest -- the
- * megakernel wins on small scenes and small frames (Suzanne at 512x512: 2.2x), the wavefront everywhere else.
+ * size, kernel variant, walk) two frames run as 0 and two as 1, alternately, all timed, and the faster of the two renders
+ * the rest -- the megakernel wins on small scenes and small frames, the wavefront everywhere else.
  * 0 = wavefront, one traverse + one shade launch per bounce;
- * 1 = one-thread-per-pixel megakernel (the reference's launch structure; kept as an on-device cross-check);
- * 2 = persistent: one traversal and one shading kernel resident for the whole frame, exchanging paths
- * through rings in device memory (no per-bounce launch boundaries);
- * 3 = wavefront with carry-over: a traverse launch ends when its queue runs dry and parks unfinished rays
- * for the next launch (the launch call then blocks until the frame is nearly done).
- * All four write identical pixels (DESIGN.md section 6 has the measurements). */
+ * 1 = one-thread-per-pixel megakernel (the reference's launch structure; kept as an on-device cross-check).
+ * Both write identical pixels.  (Round 1 also had 2 = persistent kernels and 3 = carry-over wavefront; both measured
+ * slower on every scene and were removed: PBR_ERR_UNSUPPORTED.) */
 int pbr_set_pipeline(pbr_ctx* ctx, int32_t mode);
 /* The pipeline frames are rendered with right now: the mode set explicitly, or with mode -1 the measured choice
  * (0 or 1), -1 while the measurement is still running. */
@@ -144,22 +141,45 @@ int pbr_pipeline_in_use(pbr_ctx* ctx, int32_t* mode);
  *                      imageIn <- imageOut                     (PathTracer::generateImage, PathTracer.cpp:59-71)
  * with the camera and every other argument as currently set; the result is in imageOut (slot 12), imageIn
  * (slot 11) is only read.  One call instead of 4 n, no host round trip between frames.  Without depth of field a
- * pixel's frames depend only on that pixel: the frames accumulate in place in imageOut, and with
- * pbr_set_tuning("batch_interleave", 1) every pixel starts its next frame the moment it has finished one
- * (up to 32 frames in flight; measured slower than frame-after-frame on the C2 scene).  With a
+ * pixel's frames depend only on that pixel: the frames accumulate in place in imageOut, one after the other.  With a
  * focus point set (camera.focusPoint >= 0) a frame reads another pixel of the previous one, so the frames
  * ping-pong between imageOut and a scratch image. */
 int pbr_kernel_launch_batch(pbr_ctx* ctx, pbr_kernel k, int32_t n_frames, const float* seeds, const float* pixel_weights);
-/* Scheduling knobs (never change a pixel): "node_phase_min", "refill_min" (traversal engine), "persist_t",
- * "persist_s" (blocks per SM of the two persistent kernels, persist_t 0 = what fits), "persist_fill",
- * "tail_steps_bulk", "tail_steps_flush", "flush_group" (carry-over wavefront), "batch_interleave",
- * "traverse_blocks" (cap on resident traverse blocks per SM, 0 = all that fit), "shadow_stage" (1: shadow rays are a
- * wavefront stage of their own, walked by the traversal engine; 0: inside the shade kernel).
- * The environment variables PBR_NODE_PHASE_MIN, PBR_REFILL_MIN, PBR_PERSIST_T/_S/_FILL, PBR_PIPELINE set
- * the initial values.  Stands where opencl.localgroupsize stands in the reference's config.json. */
+/* Scheduling knobs (never change a pixel): "node_phase_min", "refill_min" (reference-order traversal engine),
+ * "traverse_blocks" / "wide_blocks" (cap on resident blocks per SM of the reference-order / ordered traversal kernels,
+ * 0 = all that fit), "wide_top" (how many nodes of the top of the 4-wide BVH the ordered walk stages in shared memory;
+ * the tree is renumbered at the next launch), "shadow_stage" (1: shadow rays are a wavefront stage of their own, walked
+ * by the traversal engine; 0: inside the shade kernel).
+ * The environment variables PBR_NODE_PHASE_MIN, PBR_REFILL_MIN, PBR_PIPELINE, PBR_TRAVERSAL set the initial values.
+ * Stands where opencl.localgroupsize stands in the reference's config.json. */
 int pbr_set_tuning(pbr_ctx* ctx, const char* key, int32_t value);
-/* Skip the imageDebug write (the counters are still available through pbr_stats). */
+/* Skip the imageDebug write.  The debug image is the only place where the reference's visit counters
+ * (writeDebugImage, pathtracing.cl:73-78) can be observed; with it switched off the automatic traversal choice
+ * (pbr_set_traversal) is free to take the ordered walk. */
 int pbr_set_debug_image(pbr_ctx* ctx, int32_t enabled);
+/* Which walk finds the hits.
+ *   0  the reference's: stackless, fixed pre-order over the uploaded node array (traverse / traverseShadows,
+ *      pt_bvh.cl:82-177) -- hit, t, visit counters and debug image all bit-exact;
+ *   1  the ordered walk: a 4-wide BVH collapsed from the same array, nearest child first, four lanes per ray
+ *      (csrc/pt_wide.cuh) -- the same hit face, leaf and t bits, hence the same image bits; the visit counters
+ *      (pbr_stats [2] [3] [5], pbr_hit.visits, the debug image) then count wide nodes / the ordered walk's tests.
+ *      PBR_ERR_UNSUPPORTED at launch when the node array is not one the ordered walk can honour (PHONGTESS, links that
+ *      do not nest, a child box outside its parent's, ...: pbr_traversal_info().why_not);
+ *  -1  (default) automatic: 1 for frames whose debug image is switched off, 0 otherwise -- and 0 for explicit rays,
+ *      whose pbr_hit carries the counters.  Explicit any-hit rays always take 0 (WHICH face ends traverseShadows
+ *      depends on its visiting order; inside a frame only "occluded or not" is consumed, which does not). */
+int pbr_set_traversal(pbr_ctx* ctx, int32_t mode);
+typedef struct {
+	int32_t mode;                 /* as set */
+	int32_t last_used;            /* 0 / 1: what the last launch walked with */
+	int32_t wide_available;       /* the 4-wide BVH exists for the bound scene */
+	int32_t wide_nodes, wide_top, wide_depth;
+	double wide_build_ms;         /* read-back + host collapse + upload */
+	uint64_t ordered_rays;        /* rays walked by the ordered walk since the last reset */
+	uint64_t rewalked_rays;       /* of those: ambiguous (or stack overflow), walked again in reference order */
+	char why_not[96];             /* when wide_available == 0 after a build attempt */
+} pbr_traversal_info_t;
+int pbr_traversal_info(pbr_ctx* ctx, pbr_traversal_info_t* out, int32_t reset);
 /* Counters accumulated since the last call with reset != 0:
  *   [0] traverse() calls  [1] traverseShadows() calls  [2] BVH nodes visited by traverse()
  *   [3] triangle tests    [4] shaded hits              [5] BVH nodes visited by traverseShadows()

@@ -22,6 +22,7 @@ SYMBOLS = [
     "pbr_set_define", "pbr_program_load", "pbr_kernel_get", "pbr_kernel_set_arg", "pbr_kernel_launch",
     "pbr_finish", "pbr_kernel_time_ms",
     "pbr_image_read_begin", "pbr_image_read_end", "pbr_set_tile", "pbr_set_tile_stripes", "pbr_set_pipeline", "pbr_pipeline_in_use", "pbr_set_tuning", "pbr_kernel_launch_batch", "pbr_set_debug_image", "pbr_stats",
+    "pbr_set_traversal", "pbr_traversal_info",
     "pbr_trace", "pbr_trace_device", "pbr_pinned_math_eval",
     "pbr_set_stream", "pbr_profile_enable", "pbr_profile_read",
 ]
@@ -41,6 +42,10 @@ HIT_DTYPE = np.dtype([("t", "<f4"), ("hitFace", "<i4"), ("leaf", "<i4"), ("visit
 PROFILE_DTYPE = np.dtype([("launches", "<u8"), ("raygen_launches", "<u8"), ("traverse_launches", "<u8"),
                           ("shade_launches", "<u8"), ("other_launches", "<u8"), ("raygen_ms", "<f8"),
                           ("traverse_ms", "<f8"), ("shade_ms", "<f8"), ("other_ms", "<f8")])
+
+TRAVERSAL_INFO_DTYPE = np.dtype([("mode", "<i4"), ("last_used", "<i4"), ("wide_available", "<i4"), ("wide_nodes", "<i4"),
+                                 ("wide_top", "<i4"), ("wide_depth", "<i4"), ("wide_build_ms", "<f8"), ("ordered_rays", "<u8"),
+                                 ("rewalked_rays", "<u8"), ("why_not", "S96")])
 
 _lib = None
 
@@ -93,6 +98,8 @@ def load_library():
         "pbr_kernel_launch_batch": [vp, u64, i32, vp, vp],
         "pbr_set_debug_image": [vp, i32],
         "pbr_stats": [vp, vp, i32],
+        "pbr_set_traversal": [vp, i32],
+        "pbr_traversal_info": [vp, vp, i32],
         "pbr_trace": [vp, u64, u64, u64, u64, i32, vp, i64, i32, vp],
         "pbr_trace_device": [vp, u64, u64, u64, u64, i32, u64, i64, i32, u64],
         "pbr_pinned_math_eval": [vp, i32, vp, vp, i64, vp],
@@ -270,6 +277,17 @@ class Device:
         out = np.zeros(6, np.uint64)
         self._ck(self.lib.pbr_stats(self.ctx, _p(out), int(reset)), "pbr_stats")
         return out
+
+    def setTraversal(self, mode):
+        """-1 automatic (default), 0 the reference's visiting order, 1 the ordered walk over the 4-wide BVH."""
+        self._ck(self.lib.pbr_set_traversal(self.ctx, int(mode)), "pbr_set_traversal")
+
+    def traversalInfo(self, reset=False):
+        out = np.zeros(1, TRAVERSAL_INFO_DTYPE)
+        self._ck(self.lib.pbr_traversal_info(self.ctx, _p(out), int(reset)), "pbr_traversal_info")
+        d = {k: out[k][0].item() for k in TRAVERSAL_INFO_DTYPE.names}
+        d["why_not"] = d["why_not"].decode(errors="replace")
+        return d
 
     def deviceInfo(self):
         name = C.create_string_buffer(256)

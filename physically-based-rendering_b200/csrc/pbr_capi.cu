@@ -11,6 +11,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <deque>
 #include <string>
 #include <vector>
 #include <algorithm>
@@ -18,7 +19,8 @@
 
 #include "../../include/pbr_b200.h"
 #include "pt_kernels.cuh"
-#include "pt_persistent.cuh"
+#include "pt_wide.cuh"
+#include "wide_bvh.h"
 
 using namespace ptk;
 
@@ -30,6 +32,7 @@ struct Mem {
 	bool image = false;
 	size_t width = 0, height = 0;
 	bool alive = false;
+	uint64_t epoch = 0;               /* bumped whenever the contents may have changed (create, update, free) */
 };
 
 struct KernelArgs {
@@ -59,7 +62,8 @@ struct pbr_ctx {
 	pbr_profile prof = {};
 	bool timed = false;
 	std::string lastError;
-	std::vector<Mem> mems;
+	std::deque<Mem> mems;             /* a deque: Mem* stay valid when a handle is added */
+	uint64_t epochCounter = 0;
 	std::vector<void*> pinned;
 
 	/* program */
@@ -90,19 +94,30 @@ struct pbr_ctx {
 	float4* tris = nullptr;
 	const float* trisB = nullptr;
 	const uint32_t* triMat = nullptr;
-#if PT_NODE_ORDER
-	int* nodeOrig = nullptr;                   /* permuted position -> index in the reference's array */
-	size_t nodeOrigCap = 0;
-#endif
 	size_t nodesCap = 0, trisCap = 0;
 	pbr_mem cacheBvh = 0, cacheFacesV = 0, cacheVertices = 0, cacheFacesN = 0, cacheNormals = 0;
+	uint64_t cacheEpochBvh = ~0ull, cacheEpochFacesV = ~0ull, cacheEpochVertices = ~0ull, cacheEpochFacesN = ~0ull, cacheEpochNormals = ~0ull;
 	bool cachePhong = false;
 	int cacheNumNodes = -1;
-	uint64_t sceneEpoch = 0, cacheEpoch = ~0ull;
+	uint64_t geometryVersion = 0;              /* bumped by every repack: keys the pipeline choice */
 	int numNodesDev = 0;
 
+	/* the 4-wide BVH of the ordered walk (wide_bvh.h, pt_wide.cuh), built on demand from the uploaded node array */
+	int traversal = -1;                        /* pbr_set_traversal: -1 automatic, 0 reference order, 1 ordered */
+	int lastTraversal = 0;                     /* what the last launch used */
+	float4* wide = nullptr;
+	int* faceLeaf = nullptr;
+	size_t wideCap = 0, faceLeafCap = 0;       /* wide nodes / faces allocated */
+	int wideCount = 0, wideTop = 0, wideDepth = 0;
+	int wideTopBudget = 85;                    /* tuning "wide_top": nodes staged in shared memory (1 + 4 + 16 + 64) */
+	bool wideBuilt = false, wideOk = false;
+	std::string wideWhy;
+	uint64_t wideVersion = ~0ull;              /* geometryVersion the wide tree was built for */
+	int wideBudgetBuilt = -1;
+	double wideBuildMs = 0.0;
+
 	/* wavefront state */
-	WaveState wave = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+	WaveState wave = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 	float4* hitN = nullptr;                    /* allocated with the wave state, used when PHONGTESS */
 	QueueCtl qctl = {nullptr, {nullptr, nullptr}};
 	size_t waveCap = 0;
@@ -113,34 +128,17 @@ struct pbr_ctx {
 	size_t shadowCap = 0;
 	int shadowStage = 1;                       /* tuning "shadow_stage": 0 = walk shadow rays inside the shade kernel */
 
-	/* carry-over wavefront (pipeline 3): resume nodes, hit queue, two carry queues, counters, host mailbox */
-	int* waveNode = nullptr;
-	uint32_t* hitQ = nullptr;
-	uint32_t* carryQ[2] = {nullptr, nullptr};
-	uint32_t* cctl = nullptr;                  /* nNew[2], nCarry[2], nHit[2], cursor, - */
-	uint32_t* mailbox = nullptr;               /* pinned, MAILBOX_SLOTS words */
-	cudaEvent_t evGroup[2] = {nullptr, nullptr};
-	int tailStepsBulk = 64, tailStepsFlush = 256, flushGroup = 4;
-	int prevGroupBegin = 0;
 	int traverseBlocks = 0;                    /* tuning: cap on resident traverse blocks per SM (0 = all that fit) */
-	int batchInterleave = 0;                   /* pbr_kernel_launch_batch: let pixels run ahead into later frames */
+	int wideBlocks = 0;                        /* tuning "wide_blocks": the same for the ordered walk's kernels */
 
 	/* can any material extend a path beyond MAX_DEPTH? (decides how many wavefront iterations to launch) */
 	pbr_mem extendCacheMem = 0;
-	uint64_t extendCacheEpoch = ~0ull;
+	uint64_t extendCacheEpoch = ~0ull;         /* epoch of the materials buffer the answer was computed from */
 	int extendCacheBrdf = -1;
 	bool canExtendDepth = true;
 	int nodePhaseMin = 16;                     /* PBR_NODE_PHASE_MIN overrides (tuning) */
 	int refillMin = 4;                         /* PBR_REFILL_MIN overrides (tuning) */
-	/* persistent pipeline (pipeline 2): rings between the two resident kernels, second stream */
-	PersistCtl* pctl = nullptr;
-	uint32_t* ring[2] = {nullptr, nullptr};    /* rayRing, hitRing */
-	size_t ringCap = 0;                        /* entries, power of two */
-	cudaStream_t shadeStream = nullptr;
-	cudaEvent_t evFork = nullptr, evJoin = nullptr;
-	bool persistUsed = false;                  /* a pipeline-2 frame ran since the last abort check */
-	int persistTBlocks = 0, persistSBlocks = 2, persistFill = 4;   /* T: 0 = what fits;  PBR_PERSIST_T / _S / _FILL override */
-	unsigned long long* stats = nullptr;       /* 6 counters */
+	unsigned long long* stats = nullptr;       /* 8 counters: the six of pbr_stats, re-walked rays, rays of the ordered walk */
 	unsigned long long* cursor64 = nullptr;    /* work cursor of traceRaysKernel */
 };
 
@@ -172,14 +170,12 @@ int newMem(pbr_ctx* ctx, size_t bytes, pbr_mem* out, Mem** mp) {
 	m.alive = true;
 	cudaError_t e = cudaMalloc(&m.dptr, bytes > 0 ? bytes : 16);
 	if (e != cudaSuccess) return cudaFail(ctx, e, "cudaMalloc");
+	m.epoch = ++ctx->epochCounter;
 	ctx->mems.push_back(m);
 	*out = (pbr_mem) ctx->mems.size();
 	if (mp) *mp = &ctx->mems.back();
-	ctx->sceneEpoch++;
 	return PBR_OK;
 }
-
-enum { MAILBOX_SLOTS = 256 };
 
 int gridFor(long long n, int block) { return (int) ((n + block - 1) / block); }
 
@@ -243,18 +239,24 @@ void drainTimed(pbr_ctx* ctx) {
 	ctx->timedInFlight.clear();
 }
 
-/* Rebuild the repacked node / triangle arrays when the bound buffers or BVH_NUM_NODES changed. */
+/* Rebuild the repacked node / triangle arrays when the bound buffers, their contents or BVH_NUM_NODES changed. */
 int ensureScene(pbr_ctx* ctx, pbr_mem hBvh, pbr_mem hFacesV, pbr_mem hVertices, int numNodes,
                 bool phong = false, pbr_mem hFacesN = 0, pbr_mem hNormals = 0) {
-	if (ctx->cacheBvh == hBvh && ctx->cacheFacesV == hFacesV && ctx->cacheVertices == hVertices &&
-	    ctx->cacheNumNodes == numNodes && ctx->cacheEpoch == ctx->sceneEpoch && ctx->cachePhong == phong &&
-	    (!phong || (ctx->cacheFacesN == hFacesN && ctx->cacheNormals == hNormals))) {
-		return PBR_OK;
-	}
 	Mem* bvh = getMem(ctx, hBvh);
 	Mem* facesV = getMem(ctx, hFacesV);
 	Mem* vertices = getMem(ctx, hVertices);
 	if (!bvh || !facesV || !vertices) return fail(ctx, PBR_ERR_INVALID, "pathTracing: bvh / facesV / vertices argument is not a live buffer");
+	Mem* facesN = phong ? getMem(ctx, hFacesN) : nullptr;
+	Mem* normals = phong ? getMem(ctx, hNormals) : nullptr;
+	if (phong && (!facesN || !normals || facesN->bytes < facesV->bytes || normals->bytes < sizeof(pbr_float4)))
+		return fail(ctx, PBR_ERR_INVALID, "pathTracing: PHONGTESS needs facesN (one entry per face) and normals");
+	if (ctx->cacheBvh == hBvh && ctx->cacheFacesV == hFacesV && ctx->cacheVertices == hVertices &&
+	    ctx->cacheEpochBvh == bvh->epoch && ctx->cacheEpochFacesV == facesV->epoch && ctx->cacheEpochVertices == vertices->epoch &&
+	    ctx->cacheNumNodes == numNodes && ctx->cachePhong == phong &&
+	    (!phong || (ctx->cacheFacesN == hFacesN && ctx->cacheNormals == hNormals &&
+	                ctx->cacheEpochFacesN == facesN->epoch && ctx->cacheEpochNormals == normals->epoch))) {
+		return PBR_OK;
+	}
 
 	const int numSrcNodes = (int) (bvh->bytes / sizeof(pbr_bvh_node));
 	if (numNodes > numSrcNodes) return fail(ctx, PBR_ERR_INVALID, "BVH_NUM_NODES exceeds the size of the bvh buffer");
@@ -269,10 +271,6 @@ int ensureScene(pbr_ctx* ctx, pbr_mem hBvh, pbr_mem hFacesV, pbr_mem hVertices, 
 		CK(cudaMalloc(&ctx->nodes, (size_t) numDst * 32));
 		ctx->nodesCap = (size_t) numDst;
 	}
-	Mem* facesN = phong ? getMem(ctx, hFacesN) : nullptr;
-	Mem* normals = phong ? getMem(ctx, hNormals) : nullptr;
-	if (phong && (!facesN || !normals || facesN->bytes < facesV->bytes || normals->bytes < sizeof(pbr_float4)))
-		return fail(ctx, PBR_ERR_INVALID, "pathTracing: PHONGTESS needs facesN (one entry per face) and normals");
 	/* float4s: PHONGTESS 6 per face; otherwise 2 per face, then a quarter float4 (edge2.z) per face behind them,
 	 * then a quarter float4 (material index) per face behind those */
 	const size_t facesAlloc = (size_t) (numFaces > 0 ? numFaces : 1);
@@ -288,49 +286,6 @@ int ensureScene(pbr_ctx* ctx, pbr_mem hBvh, pbr_mem hFacesV, pbr_mem hVertices, 
 		LaunchScope ls(ctx, K_OTHER);
 		repackNodesKernel<<<gridFor(numDst, 256), 256, 0, ctx->stream>>>((const float4*) bvh->dptr, numNodes, ctx->nodes, numDst);
 	}
-#if PT_NODE_ORDER
-	{
-		/* Experiment (scripts/node_permutation_proto.py): hot nodes dense, explicit links.  Done on the host, once per
-		 * scene: positions 0 and 1 stay, the rest is ordered by surface area, ties in the reference's order. */
-		const int N = numDst;
-		std::vector<float> h((size_t) N * 8), out((size_t) N * 8);
-		CK(cudaStreamSynchronize(ctx->stream));
-		CK(cudaMemcpy(h.data(), ctx->nodes, (size_t) N * 32, cudaMemcpyDeviceToHost));
-		std::vector<double> key((size_t) N);
-		for (int i = 0; i < N; i++) {
-			const float* r = &h[(size_t) i * 8];
-			const float ex = fmaxf(r[4] - r[0], 0.0f), ey = fmaxf(r[5] - r[1], 0.0f), ez = fmaxf(r[6] - r[2], 0.0f);
-			key[(size_t) i] = (double) ex * ey + (double) ey * ez + (double) ex * ez;
-		}
-		std::vector<int> orig((size_t) N), pos((size_t) N);
-		std::iota(orig.begin(), orig.end(), 0);
-		std::stable_sort(orig.begin() + (N > 2 ? 2 : N), orig.end(), [&](int a, int b) { return key[(size_t) a] > key[(size_t) b]; });
-		for (int j = 0; j < N; j++) pos[(size_t) orig[(size_t) j]] = j;
-		const auto link = [&](long long t) -> int { return (t > 0 && t < (long long) numNodes) ? pos[(size_t) t] : 0; };
-		for (int j = 0; j < N; j++) {
-			const int i = orig[(size_t) j];
-			const float* r = &h[(size_t) i * 8];
-			float* o = &out[(size_t) j * 8];
-			memcpy(o, r, 32);
-			int loW, hiW;
-			memcpy(&loW, r + 3, 4);
-			memcpy(&hiW, r + 7, 4);
-			int nlo, nhi;
-			if (loW < 0) { nlo = link((long long) i + 1); nhi = link(hiW); }
-			else { nlo = loW; nhi = (int) ((unsigned) link((long long) i + 1) | 0x80000000u | (hiW != -1 ? 0x40000000u : 0u)); }
-			memcpy(o + 3, &nlo, 4);
-			memcpy(o + 7, &nhi, 4);
-		}
-		CK(cudaMemcpy(ctx->nodes, out.data(), (size_t) N * 32, cudaMemcpyHostToDevice));
-		if ((size_t) N > ctx->nodeOrigCap) {
-			if (ctx->nodeOrig) cudaFree(ctx->nodeOrig);
-			ctx->nodeOrig = nullptr;
-			CK(cudaMalloc(&ctx->nodeOrig, (size_t) N * sizeof(int)));
-			ctx->nodeOrigCap = (size_t) N;
-		}
-		CK(cudaMemcpy(ctx->nodeOrig, orig.data(), (size_t) N * sizeof(int), cudaMemcpyHostToDevice));
-	}
-#endif
 	if (numFaces > 0 && numVertices > 0) {
 		LaunchScope ls(ctx, K_OTHER);
 		if (phong) {
@@ -347,11 +302,108 @@ int ensureScene(pbr_ctx* ctx, pbr_mem hBvh, pbr_mem hFacesV, pbr_mem hVertices, 
 	CK(cudaGetLastError());
 	ctx->cacheBvh = hBvh; ctx->cacheFacesV = hFacesV; ctx->cacheVertices = hVertices;
 	ctx->cacheFacesN = hFacesN; ctx->cacheNormals = hNormals; ctx->cachePhong = phong;
+	ctx->cacheEpochBvh = bvh->epoch; ctx->cacheEpochFacesV = facesV->epoch; ctx->cacheEpochVertices = vertices->epoch;
+	ctx->cacheEpochFacesN = facesN ? facesN->epoch : 0; ctx->cacheEpochNormals = normals ? normals->epoch : 0;
 	ctx->cacheNumNodes = numNodes;
-	ctx->cacheEpoch = ctx->sceneEpoch;
+	ctx->geometryVersion++;
 	ctx->numNodesDev = numNodes;
 	ctx->trisB = phong ? nullptr : (const float*) (ctx->tris + PT_TRI_STRIDE * facesAlloc);
 	ctx->triMat = phong ? nullptr : (const uint32_t*) (ctx->tris + PT_TRI_STRIDE * facesAlloc + quarter);
+	return PBR_OK;
+}
+
+/* The 4-wide BVH for the scene ensureScene has just bound (wide_bvh.h): the node array is read back once, the tree is
+ * recovered, checked and collapsed on the host, and the wide nodes go up.  When the builder refuses the array, wideOk
+ * stays false and every launch keeps the reference-order walk; pbr_traversal_info tells why. */
+int ensureWide(pbr_ctx* ctx) {
+	if (ctx->wideBuilt && ctx->wideVersion == ctx->geometryVersion && ctx->wideBudgetBuilt == ctx->wideTopBudget) return PBR_OK;
+	ctx->wideBuilt = true;
+	ctx->wideVersion = ctx->geometryVersion;
+	ctx->wideBudgetBuilt = ctx->wideTopBudget;
+	ctx->wideOk = false;
+	ctx->wideWhy.clear();
+	ctx->wideCount = ctx->wideTop = ctx->wideDepth = 0;
+	if (ctx->cachePhong) { ctx->wideWhy = "PHONGTESS: the ordered walk handles flat triangles only"; return PBR_OK; }
+	Mem* bvh = getMem(ctx, ctx->cacheBvh);
+	Mem* facesV = getMem(ctx, ctx->cacheFacesV);
+	if (!bvh || !facesV) { ctx->wideWhy = "no scene bound"; return PBR_OK; }
+	const int numNodes = ctx->cacheNumNodes;
+	if (numNodes < 2) { ctx->wideWhy = "fewer than two nodes"; return PBR_OK; }
+	const int numFaces = (int) (facesV->bytes / sizeof(pbr_uint4));
+	std::vector<float> host((size_t) numNodes * 8);
+	cudaEvent_t e0 = takeEvent(ctx), e1 = takeEvent(ctx);
+	cudaEventRecord(e0, ctx->stream);
+	CK(cudaMemcpyAsync(host.data(), bvh->dptr, (size_t) numNodes * 32, cudaMemcpyDeviceToHost, ctx->stream));
+	CK(cudaStreamSynchronize(ctx->stream));
+	wbvh::Result R = wbvh::build(host.data(), numNodes, numFaces, ctx->wideTopBudget);
+	if (!R.ok) { ctx->wideWhy = R.why; ctx->eventPool.push_back(e0); ctx->eventPool.push_back(e1); return PBR_OK; }
+	if (R.nodes.size() > ctx->wideCap) {
+		if (ctx->wide) cudaFree(ctx->wide);
+		ctx->wide = nullptr;
+		ctx->wideCap = 0;
+		CK(cudaMalloc(&ctx->wide, R.nodes.size() * sizeof(wbvh::Node)));
+		ctx->wideCap = R.nodes.size();
+	}
+	if (R.faceLeaf.size() > ctx->faceLeafCap) {
+		if (ctx->faceLeaf) cudaFree(ctx->faceLeaf);
+		ctx->faceLeaf = nullptr;
+		ctx->faceLeafCap = 0;
+		CK(cudaMalloc(&ctx->faceLeaf, R.faceLeaf.size() * sizeof(int32_t)));
+		ctx->faceLeafCap = R.faceLeaf.size();
+	}
+	CK(cudaMemcpyAsync(ctx->wide, R.nodes.data(), R.nodes.size() * sizeof(wbvh::Node), cudaMemcpyHostToDevice, ctx->stream));
+	CK(cudaMemcpyAsync(ctx->faceLeaf, R.faceLeaf.data(), R.faceLeaf.size() * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+	cudaEventRecord(e1, ctx->stream);
+	CK(cudaStreamSynchronize(ctx->stream));
+	float ms = 0.0f;
+	cudaEventElapsedTime(&ms, e0, e1);
+	ctx->wideBuildMs = (double) ms;
+	ctx->eventPool.push_back(e0);
+	ctx->eventPool.push_back(e1);
+	ctx->wideCount = (int) R.nodes.size();
+	ctx->wideTop = R.topCount;
+	ctx->wideDepth = R.depth;
+	ctx->wideOk = true;
+	return PBR_OK;
+}
+
+/* Which walk does this launch take?  Automatic: the ordered walk whenever the reference's visit counters cannot be
+ * observed (no debug image) and the wide tree exists; the caller can force either. */
+int chooseTraversal(pbr_ctx* ctx, bool countersObservable, bool* useWide) {
+	*useWide = false;
+	if (ctx->traversal == 0 || (ctx->traversal < 0 && countersObservable)) return PBR_OK;
+	int rc = ensureWide(ctx);
+	if (rc) return rc;
+	if (!ctx->wideOk) {
+		if (ctx->traversal == 1) return fail(ctx, PBR_ERR_UNSUPPORTED, "pbr_set_traversal(1): the ordered walk is not available for this scene: " + ctx->wideWhy);
+		return PBR_OK;
+	}
+	*useWide = true;
+	return PBR_OK;
+}
+
+void fillScene(pbr_ctx* ctx, SceneDev& S, bool useWide) {
+	S.nodes = ctx->nodes;
+	S.tris = ctx->tris;
+	S.trisB = ctx->trisB;
+	S.triMat = ctx->triMat;
+	S.wide = useWide ? ctx->wide : nullptr;
+	S.wideTop = useWide ? ctx->wideTop : 0;
+	S.faceLeaf = useWide ? ctx->faceLeaf : nullptr;
+	S.numNodes = ctx->numNodesDev;
+	S.nodePhaseMin = ctx->nodePhaseMin;
+	S.refillMin = ctx->refillMin;
+}
+
+template <typename K>
+int wideLaunchShape(pbr_ctx* ctx, K kernel, int* grid, size_t* shared) {
+	const size_t bytes = wideSharedBytes(ctx->wideTop);
+	CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes));
+	int occ = 0;
+	CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, PT_WIDE_BLOCK, bytes));
+	if (occ < 1) return fail(ctx, PBR_ERR_INVALID, "the ordered walk does not fit on an SM (wide_top too large?)");
+	*grid = ctx->smCount * occ;
+	*shared = bytes;
 	return PBR_OK;
 }
 
@@ -360,9 +412,7 @@ int ensureWave(pbr_ctx* ctx, size_t nPaths) {
 	WaveState& W = ctx->wave;
 	cudaFree(W.rayO); cudaFree(W.rayD); cudaFree(W.colS); cudaFree(W.finF); cudaFree(W.misc); cudaFree(W.dbg); cudaFree(ctx->hitN);
 	cudaFree(ctx->qctl.queue[0]); cudaFree(ctx->qctl.queue[1]);
-	cudaFree(ctx->waveNode); cudaFree(ctx->hitQ); cudaFree(ctx->carryQ[0]); cudaFree(ctx->carryQ[1]);
-	ctx->waveNode = nullptr; ctx->hitQ = nullptr; ctx->carryQ[0] = ctx->carryQ[1] = nullptr;
-	W = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+	W = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 	ctx->hitN = nullptr;
 	ctx->qctl.queue[0] = ctx->qctl.queue[1] = nullptr;
 	ctx->waveCap = 0;
@@ -375,17 +425,6 @@ int ensureWave(pbr_ctx* ctx, size_t nPaths) {
 	CK(cudaMalloc(&ctx->hitN, nPaths * 16));
 	CK(cudaMalloc(&ctx->qctl.queue[0], nPaths * 4));
 	CK(cudaMalloc(&ctx->qctl.queue[1], nPaths * 4));
-	CK(cudaMalloc(&ctx->waveNode, nPaths * 4));
-	CK(cudaMalloc(&ctx->hitQ, nPaths * 4));
-	CK(cudaMalloc(&ctx->carryQ[0], nPaths * 4));
-	CK(cudaMalloc(&ctx->carryQ[1], nPaths * 4));
-	if (!ctx->cctl) {
-		CK(cudaMalloc(&ctx->cctl, 8 * sizeof(uint32_t)));
-		CK(cudaMemset(ctx->cctl, 0, 8 * sizeof(uint32_t)));
-		CK(cudaHostAlloc(&ctx->mailbox, MAILBOX_SLOTS * sizeof(uint32_t), cudaHostAllocMapped));
-		CK(cudaEventCreateWithFlags(&ctx->evGroup[0], cudaEventDisableTiming));
-		CK(cudaEventCreateWithFlags(&ctx->evGroup[1], cudaEventDisableTiming));
-	}
 	ctx->waveCap = nPaths;
 	return PBR_OK;
 }
@@ -403,56 +442,13 @@ int ensureShadow(pbr_ctx* ctx, size_t nPaths) {
 	return PBR_OK;
 }
 
-int ensureRings(pbr_ctx* ctx, size_t nPaths) {
-	if (nPaths <= ctx->ringCap / 2 && ctx->pctl) return PBR_OK;
-	size_t cap = 1024;
-	while (cap < 2 * nPaths) cap <<= 1;
-	cudaFree(ctx->ring[0]); cudaFree(ctx->ring[1]);
-	ctx->ring[0] = ctx->ring[1] = nullptr;
-	ctx->ringCap = 0;
-	if (!ctx->pctl) CK(cudaMalloc(&ctx->pctl, sizeof(PersistCtl)));
-	if (!ctx->shadeStream) CK(cudaStreamCreateWithFlags(&ctx->shadeStream, cudaStreamNonBlocking));
-	if (!ctx->evFork) CK(cudaEventCreateWithFlags(&ctx->evFork, cudaEventDisableTiming));
-	if (!ctx->evJoin) CK(cudaEventCreateWithFlags(&ctx->evJoin, cudaEventDisableTiming));
-	CK(cudaMalloc(&ctx->ring[0], cap * 4));
-	CK(cudaMalloc(&ctx->ring[1], cap * 4));
-	CK(cudaMemsetAsync(ctx->ring[0], 0, cap * 4, ctx->stream));
-	CK(cudaMemsetAsync(ctx->ring[1], 0, cap * 4, ctx->stream));
-	CK(cudaMemsetAsync(ctx->pctl, 0, sizeof(PersistCtl), ctx->stream));
-	ctx->ringCap = cap;
-	return PBR_OK;
-}
-
-/* After a pipeline-2 frame: did a watchdog fire?  (The stream must be idle.) */
-int checkPersistAbort(pbr_ctx* ctx) {
-	if (!ctx->persistUsed || !ctx->pctl) return PBR_OK;
-	ctx->persistUsed = false;
-	PersistCtl h;
-	CK(cudaMemcpyAsync(&h, ctx->pctl, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
-	CK(cudaStreamSynchronize(ctx->stream));
-	if (getenv("PBR_PERSIST_DEBUG")) {
-		fprintf(stderr, "[persist] idle polls: traverse %llu shade %llu\n", h.idleT, h.idleS);
-		cudaMemsetAsync(&ctx->pctl->idleT, 0, 16, ctx->stream);
-	}
-	if (h.abort != 0u || h.finished != h.total) {
-		cudaMemsetAsync(ctx->ring[0], 0, ctx->ringCap * 4, ctx->stream);
-		cudaMemsetAsync(ctx->ring[1], 0, ctx->ringCap * 4, ctx->stream);
-		cudaMemsetAsync(ctx->pctl, 0, sizeof(PersistCtl), ctx->stream);
-		cudaStreamSynchronize(ctx->stream);
-		char msg[160];
-		snprintf(msg, sizeof(msg), "pathTracing: persistent pipeline gave up (abort=%u, %u of %u pixels written)", h.abort, h.finished, h.total);
-		return fail(ctx, PBR_ERR_INVALID, msg);
-	}
-	return PBR_OK;
-}
-
 /* extendDepth (pt_utils.cl:89-96) and the transparency branch of getNewRay (pt_brdf.cl:352-354) are the
  * only places that set addDepth.  If no material can trigger either, depthAdded stays 0 and a path ends
  * after MAX_DEPTH bounces: the MAX_ADDED_DEPTH extra wavefront iterations would all be empty. */
 int updateCanExtendDepth(pbr_ctx* ctx, pbr_mem hMaterials, int brdf) {
-	if (ctx->extendCacheMem == hMaterials && ctx->extendCacheEpoch == ctx->sceneEpoch && ctx->extendCacheBrdf == brdf) return PBR_OK;
 	Mem* m = getMem(ctx, hMaterials);
 	if (!m) return fail(ctx, PBR_ERR_INVALID, "pathTracing: materials argument is not a live buffer");
+	if (ctx->extendCacheMem == hMaterials && ctx->extendCacheEpoch == m->epoch && ctx->extendCacheBrdf == brdf) return PBR_OK;
 	const size_t stride = brdf == 0 ? sizeof(pbr_material_schlick) : sizeof(pbr_material_sa);
 	const size_t n = m->bytes / stride;
 	std::vector<float> host(m->bytes / 4 + 1);
@@ -468,148 +464,31 @@ int updateCanExtendDepth(pbr_ctx* ctx, pbr_mem hMaterials, int brdf) {
 	}
 	ctx->canExtendDepth = can;
 	ctx->extendCacheMem = hMaterials;
-	ctx->extendCacheEpoch = ctx->sceneEpoch;
+	ctx->extendCacheEpoch = m->epoch;
 	ctx->extendCacheBrdf = brdf;
 	return PBR_OK;
 }
 
-/* pipeline 2: two kernels resident together for the whole frame (pt_persistent.cuh) */
-template <int BRDF, bool SHADOW, bool PHONG>
-int runPersistent(pbr_ctx* ctx, const FrameParams& P, WaveState W, int nPaths) {
-	int rc = ensureRings(ctx, (size_t) nPaths);
-	if (rc) return rc;
-	const uint32_t mask = (uint32_t) ctx->ringCap - 1u;
-	/* Both kernels must be resident at once: give the shading kernel its blocks per SM and the
-	 * traversal kernel what is left of the register file and the thread slots. */
-	static int regsT = 0, regsS = 0;
-	if (regsT == 0) {
-		cudaFuncAttributes aT, aS;
-		CK(cudaFuncGetAttributes(&aT, persistTraverseKernel<PHONG>));
-		CK(cudaFuncGetAttributes(&aS, persistShadeKernel<BRDF, SHADOW, PHONG>));
-		regsT = (aT.numRegs + 7) / 8 * 8 * 128;
-		regsS = (aS.numRegs + 7) / 8 * 8 * 128;
-	}
-	int sB = ctx->persistSBlocks, tB = ctx->persistTBlocks;
-	while (sB > 1 && sB * regsS + regsT > 65536) sB--;
-	const int room = (65536 - sB * regsS) / regsT;
-	if (tB <= 0 || tB > room) tB = room;
-	if (tB + sB > 16) tB = 16 - sB;
-	if (tB < 1) return fail(ctx, PBR_ERR_INVALID, "pathTracing: persistent pipeline does not fit on an SM");
-	{
-		LaunchScope ls(ctx, K_RAYGEN);
-		persistRaygenKernel<<<ctx->smCount * 8, 256, 0, ctx->stream>>>(P, W, ctx->pctl, ctx->ring[0], nPaths);
-	}
-	CK(cudaEventRecord(ctx->evFork, ctx->stream));
-	CK(cudaStreamWaitEvent(ctx->shadeStream, ctx->evFork, 0));
-	{
-		LaunchScope ls(ctx, K_SHADE, ctx->shadeStream);
-		persistShadeKernel<BRDF, SHADOW, PHONG><<<ctx->smCount * sB, 128, 0, ctx->shadeStream>>>(
-			P, W, ctx->pctl, ctx->ring[0], ctx->ring[1], mask, ctx->persistFill);
-	}
-	CK(cudaEventRecord(ctx->evJoin, ctx->shadeStream));
-	{
-		LaunchScope ls(ctx, K_TRAVERSE);
-		persistTraverseKernel<PHONG><<<ctx->smCount * tB, 128, 0, ctx->stream>>>(
-			P.scene, W, ctx->pctl, ctx->ring[0], ctx->ring[1], mask, ctx->stats);
-	}
-	CK(cudaStreamWaitEvent(ctx->stream, ctx->evJoin, 0));
-	CK(cudaGetLastError());
-	ctx->persistUsed = true;
-	return PBR_OK;
-}
-
-/* pipeline 3: wavefront with carry-over (traverseCarryKernel) */
-template <int BRDF, bool SHADOW, bool PHONG>
-int runCarryOver(pbr_ctx* ctx, const FrameParams& P, WaveState W, int nPaths) {
-	const QueueCtl& Q = ctx->qctl;
-	/* wavefront with carry-over (traverseCarryKernel): the number of iterations depends on the rays,
-	 * so launches go out in groups and the host looks at the mailbox of the group before the one it
-	 * has just enqueued -- the device never waits for the host */
-	W.node = ctx->waveNode;
-	int occT = 0, occS = 0;
-	CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occT, traverseCarryKernel<PHONG>, 128, 0));
-	CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occS, shadeKernel<BRDF, SHADOW, PHONG>, 128, 0));
-	const int gridT = ctx->smCount * (occT > 0 ? occT : 1);
-	const int gridS = ctx->smCount * (occS > 0 ? occS : 1);
-	uint32_t* c = ctx->cctl;
-	uint32_t* mailboxDev = nullptr;
-	CK(cudaHostGetDevicePointer((void**) &mailboxDev, ctx->mailbox, 0));
-	static const bool dump = getenv("PBR_PROFILE_DUMP") != nullptr;
-	{
-		LaunchScope ls(ctx, K_RAYGEN);
-		raygenCarryKernel<<<ctx->smCount * 8, 256, 0, ctx->stream>>>(P, W, c, nPaths);
-	}
-	const int firstGroup = P.frameCount * P.samples > 1 ? P.frameCount * P.samples : P.maxDepth;
-	int it = 0;
-	for (int group = 0; ; group++) {
-		const int n = group == 0 ? firstGroup : ctx->flushGroup;
-		const int itBegin = it;
-		for (int j = 0; j < n; j++, it++) {
-			const int a = it & 1, b = a ^ 1;
-			ctx->mailbox[it % MAILBOX_SLOTS] = 0xffffffffu;
-			CarryQueues Qc;
-			Qc.qCarryIn = ctx->carryQ[a]; Qc.nCarryIn = c + 2 + a;
-			Qc.qNew = (it == 0) ? nullptr : Q.queue[a]; Qc.nNew = c + 0 + a;
-			Qc.qHit = ctx->hitQ; Qc.nHit = c + 4 + a;
-			Qc.qCarryOut = ctx->carryQ[b]; Qc.nCarryOut = c + 2 + b;
-			Qc.cursor = c + 6;
-			Qc.zeroAtStart = c + 0 + b;
-			Qc.mailbox = mailboxDev + (it % MAILBOX_SLOTS);
-			cudaEvent_t d0 = nullptr, d1 = nullptr, d2 = nullptr;
-			if (dump) { d0 = takeEvent(ctx); d1 = takeEvent(ctx); d2 = takeEvent(ctx); cudaEventRecord(d0, ctx->stream); }
-			{
-				LaunchScope ls(ctx, K_TRAVERSE);
-				traverseCarryKernel<PHONG><<<gridT, 128, 0, ctx->stream>>>(P.scene, W, Qc, ctx->tailStepsBulk, ctx->tailStepsFlush, ctx->stats);
-			}
-			if (dump) cudaEventRecord(d1, ctx->stream);
-			{
-				LaunchScope ls(ctx, K_SHADE);
-				shadeKernel<BRDF, SHADOW, PHONG><<<gridS, 128, 0, ctx->stream>>>(
-					P, W, ctx->hitQ, c + 4 + a, Q.queue[b], c + 0 + b, c + 6, c + 2 + a, c + 4 + b);
-			}
-			if (dump) {
-				cudaEventRecord(d2, ctx->stream);
-				uint32_t h[8];
-				cudaMemcpyAsync(h, c, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream);
-				cudaStreamSynchronize(ctx->stream);
-				float tMs = 0.0f, sMs = 0.0f;
-				cudaEventElapsedTime(&tMs, d0, d1);
-				cudaEventElapsedTime(&sMs, d1, d2);
-				fprintf(stderr, "[carry] it %3d  start %8u  traverse %7.3f ms -> finished %8u parked %8u   shade %6.3f ms -> new %8u\n",
-					it, ((volatile uint32_t*) ctx->mailbox)[it % MAILBOX_SLOTS], tMs, h[4 + a], h[2 + b], sMs, h[0 + b]);
-				ctx->eventPool.push_back(d0); ctx->eventPool.push_back(d1); ctx->eventPool.push_back(d2);
-			}
-		}
-		CK(cudaEventRecord(ctx->evGroup[group & 1], ctx->stream));
-		CK(cudaGetLastError());
-		if (group >= 1 || dump) {
-			/* the group before this one: did one of its launches start with nothing to do? */
-			const int gPrev = dump ? group : group - 1;
-			CK(cudaEventSynchronize(ctx->evGroup[gPrev & 1]));
-			bool done = false;
-			const int pb = dump ? itBegin : ctx->prevGroupBegin, pe = dump ? it : itBegin;
-			for (int k = pb; k < pe; k++) {
-				const uint32_t live = ((volatile uint32_t*) ctx->mailbox)[k % MAILBOX_SLOTS];
-				if (live == 0u) done = true;
-			}
-			if (done) break;
-		}
-		ctx->prevGroupBegin = itBegin;
-		if (it > 1000000) return fail(ctx, PBR_ERR_INVALID, "pathTracing: carry-over wavefront does not terminate");
-	}
-	return PBR_OK;
-}
-
-/* pipeline 0: one traverse + one shade launch per bounce (what the measured choice picks on all but small scenes) */
+/* pipeline 0: one traverse + one shade launch per bounce (what the measured choice picks on all but small scenes).
+ * The traverse stage is the reference-order engine (traverseKernel) or, with P.scene.wide set, the ordered walk
+ * (traverseWideKernel): both leave the same t / hitFace in the path state. */
 template <int BRDF, bool SHADOW, bool PHONG>
 int runWavefront(pbr_ctx* ctx, const FrameParams& P, WaveState W, int nPaths) {
 	const QueueCtl& Q = ctx->qctl;
+	const bool useWide = !PHONG && P.scene.wide != nullptr;
 	int occT = 0, occS = 0;
 	CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occT, traverseKernel<PHONG>, 128, 0));
 	CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occS, shadeKernel<BRDF, SHADOW, PHONG>, 128, 0));
 	if (ctx->traverseBlocks > 0 && ctx->traverseBlocks < occT) occT = ctx->traverseBlocks;
 	const int gridT = ctx->smCount * (occT > 0 ? occT : 1);
 	const int gridS = ctx->smCount * (occS > 0 ? occS : 1);
+	int gridW = 0, gridWS = 0;
+	size_t sharedW = 0;
+	if (useWide) {
+		int rc = wideLaunchShape(ctx, traverseWideKernel, &gridW, &sharedW);
+		if (rc) return rc;
+		if (ctx->wideBlocks > 0 && ctx->wideBlocks * ctx->smCount < gridW) gridW = ctx->wideBlocks * ctx->smCount;
+	}
 
 	/* shadow rays through the traversal engine instead of one thread per path inside the shade kernel */
 	const bool shadowStage = SHADOW && P.scene.numLights > 0 && ctx->shadowStage != 0;
@@ -620,6 +499,10 @@ int runWavefront(pbr_ctx* ctx, const FrameParams& P, WaveState W, int nPaths) {
 		int occG = 0;
 		CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occG, shadowGenKernel<BRDF, PHONG>, 128, 0));
 		gridG = ctx->smCount * (occG > 0 ? occG : 1);
+		if (useWide) {
+			rc = wideLaunchShape(ctx, traverseWideShadowKernel, &gridWS, &sharedW);
+			if (rc) return rc;
+		}
 	}
 	{
 		LaunchScope ls(ctx, K_RAYGEN);
@@ -635,7 +518,8 @@ int runWavefront(pbr_ctx* ctx, const FrameParams& P, WaveState W, int nPaths) {
 		if (dump) cudaEventRecord(e0, ctx->stream);
 		{
 			LaunchScope ls(ctx, K_TRAVERSE);
-			traverseKernel<PHONG><<<gridT, 128, 0, ctx->stream>>>(P.scene, W, qIn, Q.ctrl + in, Q.ctrl + 2, Q.ctrl + out, ctx->stats);
+			if (useWide) traverseWideKernel<<<gridW, PT_WIDE_BLOCK, sharedW, ctx->stream>>>(P.scene, W, qIn, Q.ctrl + in, Q.ctrl + 2, Q.ctrl + out, ctx->stats);
+			else traverseKernel<PHONG><<<gridT, 128, 0, ctx->stream>>>(P.scene, W, qIn, Q.ctrl + in, Q.ctrl + 2, Q.ctrl + out, ctx->stats);
 		}
 		if (dump) cudaEventRecord(e1, ctx->stream);
 		if (shadowStage) {
@@ -646,7 +530,9 @@ int runWavefront(pbr_ctx* ctx, const FrameParams& P, WaveState W, int nPaths) {
 			}
 			{
 				LaunchScope ls(ctx, K_TRAVERSE);
-				traverseShadowKernel<PHONG><<<gridT, 128, 0, ctx->stream>>>(
+				if (useWide) traverseWideShadowKernel<<<gridWS, PT_WIDE_BLOCK, sharedW, ctx->stream>>>(
+					P.scene, W, ctx->shadowO, ctx->shadowD, ctx->shadowQ, Q.ctrl + 3, Q.ctrl + 4, ctx->stats);
+				else traverseShadowKernel<PHONG><<<gridT, 128, 0, ctx->stream>>>(
 					P.scene, W, ctx->shadowO, ctx->shadowD, ctx->shadowQ, Q.ctrl + 3, Q.ctrl + 4, ctx->stats);
 			}
 			{
@@ -667,7 +553,8 @@ int runWavefront(pbr_ctx* ctx, const FrameParams& P, WaveState W, int nPaths) {
 			float tMs = 0.0f, sMs = 0.0f;
 			cudaEventElapsedTime(&tMs, e0, e1);
 			cudaEventElapsedTime(&sMs, e1, e2);
-			fprintf(stderr, "[wavefront] it %3d  traverse %7.3f ms  shade%s %7.3f ms  alive after %u\n", it, tMs, shadowStage ? " + shadow stage" : "", sMs, c[out]);
+			fprintf(stderr, "[wavefront%s] it %3d  traverse %7.3f ms  shade%s %7.3f ms  alive after %u\n", useWide ? ", ordered walk" : "", it, tMs,
+				shadowStage ? " + shadow stage" : "", sMs, c[out]);
 		}
 	}
 	if (dump) { cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2); }
@@ -689,11 +576,7 @@ int runFrame(pbr_ctx* ctx, const FrameParams& P, int nPaths) {
 	if (rc) return rc;
 	WaveState W = ctx->wave;
 	W.hitN = PHONG ? ctx->hitN : nullptr;
-	switch (ctx->pipeline) {
-		case 2: return runPersistent<BRDF, SHADOW, PHONG>(ctx, P, W, nPaths);
-		case 3: return runCarryOver<BRDF, SHADOW, PHONG>(ctx, P, W, nPaths);
-		default: return runWavefront<BRDF, SHADOW, PHONG>(ctx, P, W, nPaths);
-	}
+	return runWavefront<BRDF, SHADOW, PHONG>(ctx, P, W, nPaths);
 }
 
 bool parseSky(const char* v, pbr_float4* out) {
@@ -740,13 +623,13 @@ int pbr_create(int device, pbr_ctx** out) {
 	ctx->stream = ctx->ownStream;
 	cudaEventCreate(&ctx->evStart);
 	cudaEventCreate(&ctx->evStop);
-	if (cudaMalloc(&ctx->stats, 6 * sizeof(unsigned long long)) != cudaSuccess ||
+	if (cudaMalloc(&ctx->stats, 8 * sizeof(unsigned long long)) != cudaSuccess ||
 	    cudaMalloc(&ctx->cursor64, sizeof(unsigned long long)) != cudaSuccess ||
 	    cudaMalloc(&ctx->qctl.ctrl, 8 * sizeof(uint32_t)) != cudaSuccess) {
 		delete ctx;
 		return PBR_ERR_NO_DEVICE;
 	}
-	cudaMemset(ctx->stats, 0, 6 * sizeof(unsigned long long));
+	cudaMemset(ctx->stats, 0, 8 * sizeof(unsigned long long));
 	cudaMemset(ctx->qctl.ctrl, 0, 8 * sizeof(uint32_t));
 	if (const char* e = getenv("PBR_NODE_PHASE_MIN")) {
 		const int v = atoi(e);
@@ -756,10 +639,8 @@ int pbr_create(int device, pbr_ctx** out) {
 		const int v = atoi(e);
 		if (v >= 1 && v <= 32) ctx->refillMin = v;
 	}
-	if (const char* e = getenv("PBR_PERSIST_T")) { const int v = atoi(e); if (v >= 0 && v <= 16) ctx->persistTBlocks = v; }
-	if (const char* e = getenv("PBR_PERSIST_S")) { const int v = atoi(e); if (v >= 1 && v <= 16) ctx->persistSBlocks = v; }
-	if (const char* e = getenv("PBR_PERSIST_FILL")) { const int v = atoi(e); if (v >= 0 && v <= 100000) ctx->persistFill = v; }
-	if (const char* e = getenv("PBR_PIPELINE")) { const int v = atoi(e); if (v >= 0 && v <= 3) { ctx->pipeline = v; ctx->pipelineAuto = false; } }
+	if (const char* e = getenv("PBR_PIPELINE")) { const int v = atoi(e); if (v >= 0 && v <= 1) { ctx->pipeline = v; ctx->pipelineAuto = false; } }
+	if (const char* e = getenv("PBR_TRAVERSAL")) { const int v = atoi(e); if (v >= -1 && v <= 1) ctx->traversal = v; }
 	memset(&ctx->defines, 0, sizeof(ctx->defines));
 	memset(&ctx->args.cam, 0, sizeof(ctx->args.cam));
 	*out = ctx;
@@ -772,23 +653,12 @@ int pbr_destroy(pbr_ctx* ctx) {
 	cudaStreamSynchronize(ctx->stream);
 	for (Mem& m : ctx->mems) if (m.alive && m.dptr) cudaFree(m.dptr);
 	for (void* p : ctx->pinned) cudaFreeHost(p);
-	cudaFree(ctx->nodes); cudaFree(ctx->tris);
-#if PT_NODE_ORDER
-	cudaFree(ctx->nodeOrig);
-#endif
+	cudaFree(ctx->nodes); cudaFree(ctx->tris); cudaFree(ctx->wide); cudaFree(ctx->faceLeaf);
 	WaveState& W = ctx->wave;
 	cudaFree(W.rayO); cudaFree(W.rayD); cudaFree(W.colS); cudaFree(W.finF); cudaFree(W.misc); cudaFree(W.dbg); cudaFree(ctx->hitN);
 	cudaFree(ctx->qctl.queue[0]); cudaFree(ctx->qctl.queue[1]); cudaFree(ctx->qctl.ctrl);
 	cudaFree(ctx->stats); cudaFree(ctx->cursor64);
 	cudaFree(ctx->shadowO); cudaFree(ctx->shadowD); cudaFree(ctx->shadowQ);
-	cudaFree(ctx->pctl); cudaFree(ctx->ring[0]); cudaFree(ctx->ring[1]);
-	cudaFree(ctx->waveNode); cudaFree(ctx->hitQ); cudaFree(ctx->carryQ[0]); cudaFree(ctx->carryQ[1]); cudaFree(ctx->cctl);
-	if (ctx->mailbox) cudaFreeHost(ctx->mailbox);
-	if (ctx->evGroup[0]) cudaEventDestroy(ctx->evGroup[0]);
-	if (ctx->evGroup[1]) cudaEventDestroy(ctx->evGroup[1]);
-	if (ctx->shadeStream) { cudaStreamSynchronize(ctx->shadeStream); cudaStreamDestroy(ctx->shadeStream); }
-	if (ctx->evFork) cudaEventDestroy(ctx->evFork);
-	if (ctx->evJoin) cudaEventDestroy(ctx->evJoin);
 	cudaEventDestroy(ctx->evStart); cudaEventDestroy(ctx->evStop);
 	for (const pbr_ctx::Timed& t : ctx->timedInFlight) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
 	for (cudaEvent_t e : ctx->eventPool) cudaEventDestroy(e);
@@ -842,7 +712,7 @@ int pbr_buffer_update(pbr_ctx* ctx, pbr_mem buf, size_t bytes, const void* host)
 	CK(cudaSetDevice(ctx->device));
 	CK(cudaMemcpyAsync(m->dptr, host, bytes, cudaMemcpyHostToDevice, ctx->stream));
 	CK(cudaStreamSynchronize(ctx->stream));
-	ctx->sceneEpoch++;
+	m->epoch = ++ctx->epochCounter;           /* only what was built from THIS buffer is rebuilt */
 	return PBR_OK;
 }
 
@@ -893,7 +763,7 @@ int pbr_image_read(pbr_ctx* ctx, pbr_mem image, size_t width, size_t height, flo
 	CK(cudaSetDevice(ctx->device));
 	CK(cudaMemcpyAsync(host, m->dptr, m->bytes, cudaMemcpyDeviceToHost, ctx->stream));
 	CK(cudaStreamSynchronize(ctx->stream));
-	return checkPersistAbort(ctx);
+	return PBR_OK;
 }
 
 int pbr_image_read_begin(pbr_ctx* ctx, pbr_mem image, size_t width, size_t height, float* host) {
@@ -950,8 +820,9 @@ int pbr_free_buffers(pbr_ctx* ctx) {
 		if (m.alive && m.dptr) cudaFree(m.dptr);
 		m.alive = false;
 		m.dptr = nullptr;
+		m.epoch = ++ctx->epochCounter;
 	}
-	ctx->sceneEpoch++;
+	ctx->cacheBvh = 0;                         /* the repacked scene belongs to buffers that are gone */
 	return PBR_OK;
 }
 
@@ -1002,8 +873,10 @@ int pbr_program_load(pbr_ctx* ctx, const pbr_defines* defines) {
 	if (ctx->haveSky) d.sky_light = ctx->defSky;
 	if (d.accel_struct != 0) return fail(ctx, PBR_ERR_UNSUPPORTED, "accel_struct: only 0 (BVH) exists");
 	if (d.brdf != 0 && d.brdf != 1) return fail(ctx, PBR_ERR_UNSUPPORTED, "render.brdf must be 0 (Schlick) or 1 (Shirley-Ashikhmin)");
-	if (d.img_width <= 0 || d.img_height <= 0 || d.samples <= 0 || d.max_depth < 0 || d.max_added_depth < 0)
-		return fail(ctx, PBR_ERR_INVALID, "invalid image size / samples / depth");
+	/* (MAX_DEPTH 0 would render nothing: the reference's depth loop does not run and every pixel becomes
+	 *  mix(0, imageIn, weight); rejected here rather than served by two pipelines that disagree about it) */
+	if (d.img_width <= 0 || d.img_height <= 0 || d.samples <= 0 || d.max_depth < 1 || d.max_added_depth < 0)
+		return fail(ctx, PBR_ERR_INVALID, "invalid image size / samples / depth (render.max_depth must be at least 1)");
 	if (d.max_depth + d.max_added_depth > 0xffff) return fail(ctx, PBR_ERR_INVALID, "max_depth + max_added_depth too large");
 	ctx->defines = d;
 	ctx->programLoaded = true;
@@ -1063,20 +936,17 @@ static int launchFrames(pbr_ctx* ctx, int n, const float* seeds, const float* we
 	if ((size_t) D.num_lights * sizeof(pbr_light) > lights->bytes)
 		return fail(ctx, PBR_ERR_INVALID, "NUM_LIGHTS exceeds the lights buffer");
 
+	/* the reference's visit counters are observable through the debug image only */
+	bool useWide = false;
+	rc = chooseTraversal(ctx, ctx->debugImage || phong, &useWide);
+	if (rc) return rc;
+	ctx->lastTraversal = useWide ? 1 : 0;
+
 	FrameParams P;
-	P.scene.nodes = ctx->nodes;
-	P.scene.tris = ctx->tris;
-	P.scene.trisB = ctx->trisB;
-	P.scene.triMat = ctx->triMat;
-#if PT_NODE_ORDER
-	P.scene.nodeOrig = ctx->nodeOrig;
-#endif
+	fillScene(ctx, P.scene, useWide);
 	P.scene.lights = (const pbr_light*) lights->dptr;
-	P.scene.numNodes = ctx->numNodesDev;
 	P.scene.numLights = D.num_lights;
 	P.scene.phongAlpha = D.phongtess_alpha;
-	P.scene.nodePhaseMin = ctx->nodePhaseMin;
-	P.scene.refillMin = ctx->refillMin;
 	P.materials = materials->dptr;
 	P.numMaterials = (int) (materials->bytes / (D.brdf == 0 ? sizeof(pbr_material_schlick) : sizeof(pbr_material_sa)));
 	P.cam = a.cam;
@@ -1115,8 +985,9 @@ static int launchFrames(pbr_ctx* ctx, int n, const float* seeds, const float* we
 	const int callerPipeline = ctx->pipeline;
 	int timing = -1;
 	if (ctx->pipelineAuto && n == 1) {
-		const unsigned long long key = ctx->sceneEpoch * 0x9e3779b97f4a7c15ull ^ ((unsigned long long) nPaths << 20) ^
-			((unsigned long long) variant << 8) ^ ((unsigned long long) D.max_depth << 12) ^ (unsigned long long) D.samples;
+		const unsigned long long key = ctx->geometryVersion * 0x9e3779b97f4a7c15ull ^ ((unsigned long long) nPaths << 20) ^
+			((unsigned long long) variant << 8) ^ ((unsigned long long) D.max_depth << 12) ^ (unsigned long long) D.samples ^
+			((unsigned long long) (useWide ? 1 : 0) << 40);
 		if (key != ctx->autoKey) { ctx->autoKey = key; ctx->autoState = 0; }
 		if (!ctx->evAuto[0]) for (int i = 0; i < 8; i++) CK(cudaEventCreate(&ctx->evAuto[i]));
 		if (ctx->autoState == 5) {
@@ -1137,8 +1008,9 @@ static int launchFrames(pbr_ctx* ctx, int n, const float* seeds, const float* we
 		if (timing >= 0) CK(cudaEventRecord(ctx->evAuto[timing], ctx->stream));
 	}
 	else if (ctx->pipelineAuto) {
-		ctx->pipeline = 0;                      /* interleaved batches: the wavefront */
+		ctx->pipeline = 0;
 	}
+	if (ctx->pipeline == 1) ctx->lastTraversal = 0;       /* the megakernel walks in the reference's order */
 	switch (variant) {
 		case 0: rc = runFrame<0, false, false>(ctx, P, nPaths); break;
 		case 1: rc = runFrame<0, false, true>(ctx, P, nPaths); break;
@@ -1185,13 +1057,10 @@ int pbr_kernel_launch_batch(pbr_ctx* ctx, pbr_kernel k, int32_t n_frames, const 
 	CK(cudaEventRecord(ctx->evStart, ctx->stream));
 	const bool depthOfField = a.cam.focusPoint.x >= 0 && a.cam.focusPoint.y >= 0;
 	if (!depthOfField) {
-		/* pixels are independent of each other, so everything after frame 0 can run in place in imageOut:
-		 * frame after frame (default: the rays of one bounce of one frame stay together, which the caches
-		 * like), or -- "batch_interleave" -- PT_MAX_BATCH frames per pass, pixels running ahead */
-		const int chunk = ctx->batchInterleave ? PT_MAX_BATCH : 1;
-		for (int f = 0; f < n_frames; f += chunk) {
-			const int n = n_frames - f < chunk ? n_frames - f : chunk;
-			rc = launchFrames(ctx, n, seeds + f, pixel_weights + f, f == 0 ? hIn : hOut, hOut);
+		/* pixels are independent of each other, so everything after frame 0 can run in place in imageOut, frame after
+		 * frame (the rays of one bounce of one frame stay together, which the caches like) */
+		for (int f = 0; f < n_frames; f++) {
+			rc = launchFrames(ctx, 1, seeds + f, pixel_weights + f, f == 0 ? hIn : hOut, hOut);
 			if (rc) return rc;
 		}
 	}
@@ -1200,13 +1069,13 @@ int pbr_kernel_launch_batch(pbr_ctx* ctx, pbr_kernel k, int32_t n_frames, const 
 		 * ping-pong between imageOut and a scratch image so that the last frame lands in imageOut */
 		Mem* out = getMem(ctx, hOut);
 		if (!out) return fail(ctx, PBR_ERR_INVALID, "pathTracing: imageOut is not live");
-		if (ctx->scratchImage == 0 || !getMem(ctx, ctx->scratchImage) || getMem(ctx, ctx->scratchImage)->bytes < out->bytes) {
-			const uint64_t epoch = ctx->sceneEpoch;
+		const size_t outBytes = out->bytes, outW = out->width, outH = out->height;
+		Mem* scratch = getMem(ctx, ctx->scratchImage);
+		if (ctx->scratchImage == 0 || !scratch || scratch->bytes < outBytes) {
 			Mem* m = nullptr;
-			rc = newMem(ctx, out->bytes, &ctx->scratchImage, &m);
+			rc = newMem(ctx, outBytes, &ctx->scratchImage, &m);
 			if (rc) return rc;
-			m->image = true; m->width = out->width; m->height = out->height;
-			ctx->sceneEpoch = epoch;                   /* not a scene buffer: keep the repacked scene */
+			m->image = true; m->width = outW; m->height = outH;
 		}
 		pbr_mem prev = hIn;
 		for (int f = 0; f < n_frames; f++) {
@@ -1225,7 +1094,7 @@ int pbr_finish(pbr_ctx* ctx) {
 	if (!ctx) return PBR_ERR_INVALID;
 	CK(cudaSetDevice(ctx->device));
 	CK(cudaStreamSynchronize(ctx->stream));
-	return checkPersistAbort(ctx);
+	return PBR_OK;
 }
 
 int pbr_kernel_time_ms(pbr_ctx* ctx, pbr_kernel k, double* ms) {
@@ -1255,7 +1124,9 @@ int pbr_set_tile_stripes(pbr_ctx* ctx, int32_t stripe_rows, int32_t world, int32
 }
 
 int pbr_set_pipeline(pbr_ctx* ctx, int32_t mode) {
-	if (!ctx || mode < -1 || mode > 3) return PBR_ERR_INVALID;
+	if (!ctx) return PBR_ERR_INVALID;
+	if (mode == 2 || mode == 3) return fail(ctx, PBR_ERR_UNSUPPORTED, "pipelines 2 (persistent) and 3 (carry-over) of round 1 measured slower on every scene and were removed");
+	if (mode < -1 || mode > 1) return PBR_ERR_INVALID;
 	ctx->pipelineAuto = (mode == -1);
 	ctx->pipeline = mode < 0 ? 0 : mode;
 	ctx->autoState = 0;
@@ -1274,14 +1145,9 @@ int pbr_set_tuning(pbr_ctx* ctx, const char* key, int32_t value) {
 	const std::string k(key);
 	if (k == "node_phase_min" && value >= 1 && value <= 32) ctx->nodePhaseMin = value;
 	else if (k == "refill_min" && value >= 1 && value <= 32) ctx->refillMin = value;
-	else if (k == "persist_t" && value >= 0 && value <= 16) ctx->persistTBlocks = value;
-	else if (k == "persist_s" && value >= 1 && value <= 16) ctx->persistSBlocks = value;
-	else if (k == "persist_fill" && value >= 0 && value <= 100000) ctx->persistFill = value;
-	else if (k == "tail_steps_bulk" && value >= 1 && value <= 1000000) ctx->tailStepsBulk = value;
-	else if (k == "tail_steps_flush" && value >= 1 && value <= 1000000) ctx->tailStepsFlush = value;
-	else if (k == "flush_group" && value >= 1 && value <= 64) ctx->flushGroup = value;
-	else if (k == "batch_interleave" && (value == 0 || value == 1)) ctx->batchInterleave = value;
 	else if (k == "traverse_blocks" && value >= 0 && value <= 32) ctx->traverseBlocks = value;
+	else if (k == "wide_blocks" && value >= 0 && value <= 32) ctx->wideBlocks = value;
+	else if (k == "wide_top" && value >= 1 && value <= 1365) ctx->wideTopBudget = value;      /* rebuilt at the next launch */
 	else if (k == "shadow_stage" && (value == 0 || value == 1)) ctx->shadowStage = value;
 	else return fail(ctx, PBR_ERR_INVALID, "pbr_set_tuning: unknown key or value out of range: " + k);
 	return PBR_OK;
@@ -1299,6 +1165,35 @@ int pbr_stats(pbr_ctx* ctx, uint64_t out[6], int32_t reset) {
 	CK(cudaMemcpyAsync(out, ctx->stats, 6 * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
 	if (reset) CK(cudaMemsetAsync(ctx->stats, 0, 6 * sizeof(uint64_t), ctx->stream));
 	CK(cudaStreamSynchronize(ctx->stream));
+	return PBR_OK;
+}
+
+int pbr_set_traversal(pbr_ctx* ctx, int32_t mode) {
+	if (!ctx || mode < -1 || mode > 1) return PBR_ERR_INVALID;
+	ctx->traversal = mode;
+	ctx->autoState = 0;                        /* the pipeline choice was measured with the other walk */
+	ctx->autoKey = 0;
+	return PBR_OK;
+}
+
+int pbr_traversal_info(pbr_ctx* ctx, pbr_traversal_info_t* out, int32_t reset) {
+	if (!ctx || !out) return PBR_ERR_INVALID;
+	CK(cudaSetDevice(ctx->device));
+	memset(out, 0, sizeof(*out));
+	unsigned long long c[2] = {0, 0};
+	CK(cudaMemcpyAsync(c, ctx->stats + 6, sizeof(c), cudaMemcpyDeviceToHost, ctx->stream));
+	if (reset) CK(cudaMemsetAsync(ctx->stats + 6, 0, sizeof(c), ctx->stream));
+	CK(cudaStreamSynchronize(ctx->stream));
+	out->mode = ctx->traversal;
+	out->last_used = ctx->lastTraversal;
+	out->wide_available = (ctx->wideBuilt && ctx->wideOk) ? 1 : 0;
+	out->wide_nodes = ctx->wideCount;
+	out->wide_top = ctx->wideTop;
+	out->wide_depth = ctx->wideDepth;
+	out->wide_build_ms = ctx->wideBuildMs;
+	out->rewalked_rays = c[0];
+	out->ordered_rays = c[1];
+	strncpy(out->why_not, ctx->wideWhy.c_str(), sizeof(out->why_not) - 1);
 	return PBR_OK;
 }
 
@@ -1333,20 +1228,19 @@ static int traceImpl(pbr_ctx* ctx, pbr_mem bvh, pbr_mem facesV, pbr_mem vertices
 	const int numNodes = ctx->haveNumNodes ? ctx->defNumNodes : (int) (b->bytes / sizeof(pbr_bvh_node));
 	int rc = ensureScene(ctx, bvh, facesV, vertices, numNodes);
 	if (rc) return rc;
+	/* pbr_hit carries the visit counters, so the automatic choice is the reference-order walk; the ordered walk on
+	 * request (closest hit only: WHICH face ends an any-hit walk depends on the visiting order, see pt_wide.cuh) */
+	bool useWide = false;
+	if (ctx->traversal == 1 && !any_hit) {
+		rc = chooseTraversal(ctx, false, &useWide);
+		if (rc) return rc;
+	}
+	ctx->lastTraversal = useWide ? 1 : 0;
 	SceneDev S;
-	S.nodes = ctx->nodes;
-	S.tris = ctx->tris;
-	S.trisB = ctx->trisB;
-	S.triMat = ctx->triMat;
-#if PT_NODE_ORDER
-	S.nodeOrig = ctx->nodeOrig;
-#endif
-	S.numNodes = ctx->numNodesDev;
+	fillScene(ctx, S, useWide);
 	S.numLights = 0;
 	S.lights = nullptr;
 	S.phongAlpha = 0.0f;
-	S.nodePhaseMin = ctx->nodePhaseMin;
-	S.refillMin = ctx->refillMin;
 	if (num_lights > 0) {
 		Mem* l = getMem(ctx, lights);
 		if (!l || (size_t) num_lights * sizeof(pbr_light) > l->bytes) return fail(ctx, PBR_ERR_INVALID, "pbr_trace: bad lights buffer");
@@ -1355,14 +1249,23 @@ static int traceImpl(pbr_ctx* ctx, pbr_mem bvh, pbr_mem facesV, pbr_mem vertices
 	}
 	if (n <= 0) return PBR_OK;
 	CK(cudaMemsetAsync(ctx->cursor64, 0, sizeof(unsigned long long), ctx->stream));
-	int occ = 0;
-	if (any_hit) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, traceRaysKernel<true>, 128, 0));
-	else CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, traceRaysKernel<false>, 128, 0));
-	const int grid = ctx->smCount * (occ > 0 ? occ : 1);
+	int occ = 0, grid = 0;
+	size_t shared = 0;
+	if (useWide) {
+		rc = wideLaunchShape(ctx, traceRaysWideKernel, &grid, &shared);
+		if (rc) return rc;
+		if (ctx->wideBlocks > 0 && ctx->wideBlocks * ctx->smCount < grid) grid = ctx->wideBlocks * ctx->smCount;
+	}
+	else {
+		if (any_hit) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, traceRaysKernel<true>, 128, 0));
+		else CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, traceRaysKernel<false>, 128, 0));
+		grid = ctx->smCount * (occ > 0 ? occ : 1);
+	}
 	CK(cudaEventRecord(ctx->evStart, ctx->stream));
 	{
 		LaunchScope ls(ctx, K_TRAVERSE);
-		if (any_hit) traceRaysKernel<true><<<grid, 128, 0, ctx->stream>>>(S, dRays, (long long) n, dHits, ctx->cursor64, ctx->stats);
+		if (useWide) traceRaysWideKernel<<<grid, PT_WIDE_BLOCK, shared, ctx->stream>>>(S, dRays, (long long) n, dHits, ctx->cursor64, ctx->stats);
+		else if (any_hit) traceRaysKernel<true><<<grid, 128, 0, ctx->stream>>>(S, dRays, (long long) n, dHits, ctx->cursor64, ctx->stats);
 		else traceRaysKernel<false><<<grid, 128, 0, ctx->stream>>>(S, dRays, (long long) n, dHits, ctx->cursor64, ctx->stats);
 	}
 	CK(cudaGetLastError());
@@ -1412,6 +1315,7 @@ int pbr_pinned_math_eval(pbr_ctx* ctx, int32_t op, const float* x, const float* 
 	if (n == 0) return PBR_OK;
 	CK(cudaSetDevice(ctx->device));
 	float *dx = nullptr, *dy = nullptr, *dout = nullptr;
+	struct Guard { float** p[3]; ~Guard() { for (float** q : p) if (*q) cudaFree(*q); } } guard = {{&dx, &dy, &dout}};
 	CK(cudaMalloc(&dx, (size_t) n * 4));
 	CK(cudaMalloc(&dy, (size_t) n * 4));
 	CK(cudaMalloc(&dout, (size_t) n * 4));
@@ -1425,7 +1329,6 @@ int pbr_pinned_math_eval(pbr_ctx* ctx, int32_t op, const float* x, const float* 
 	CK(cudaGetLastError());
 	CK(cudaMemcpyAsync(out, dout, (size_t) n * 4, cudaMemcpyDeviceToHost, ctx->stream));
 	CK(cudaStreamSynchronize(ctx->stream));
-	cudaFree(dx); cudaFree(dy); cudaFree(dout);
 	return PBR_OK;
 }
 

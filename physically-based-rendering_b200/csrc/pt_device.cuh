@@ -15,11 +15,12 @@
  *            INTEGER bit patterns instead of float-encoded indices:
  *              lo.w  >= 0: leaf, index of its first face;   < 0: inner node
  *              hi.w  leaf: index of its second face or -1;  inner: miss link or -1 (stop)
- *   tris   : 64 B per face in leaf order: one 256-bit load (a.xyz, material index bits, edge1.xyz, 0)
- *            and one 128-bit load (edge2.xyz, 0), with edge1 = b - a, edge2 = c - a -- the reference
- *            fetches facesV[f] and then three dependent vertices (pt_intersect.cl:146-149).  The L1
- *            data stage serves one 128-byte line per cycle and per load instruction of a divergent
- *            warp, so the number of load instructions per triangle (2 instead of 4) is what counts.
+ *   tris   : 36 B per face in leaf order, in two arrays: one 256-bit load (a.xyz, edge1.xyz, edge2.xy) and one
+ *            32-bit load (edge2.z), with edge1 = b - a, edge2 = c - a -- the reference fetches facesV[f] and
+ *            then three dependent vertices (pt_intersect.cl:146-149).  The material index, which the walk never
+ *            needs, is a third array read once per shaded hit.
+ *   wide   : the 4-wide BVH of the ordered walk (wide_bvh.h, pt_wide.cuh): 128 B per node = 4 children x
+ *            (box min, box max, ref, aux), four 256-bit loads per node visit.
  */
 #pragma once
 
@@ -41,21 +42,14 @@ using pm::v3;
 #define PT_M_PI_2 1.57079632679489661923
 #define PT_M_1_PI 0.31830988618379067154
 
-#ifndef PT_TRI_NO_L1
-#define PT_TRI_NO_L1 0             /* 1: triangle records are loaded with L1::no_allocate (experiment) */
-#endif
-#ifndef PT_NODE_ORDER
-#define PT_NODE_ORDER 0            /* 1: permuted node array with explicit links (experiment, see decodeNode) */
-#endif
-
 struct SceneDev {
 	const float4* nodes;          /* 2 x float4 per node */
 	const float4* tris;           /* 2 x float4 (32 B) per face; PHONGTESS: 6 x float4 (a b c an bn cn) */
 	const float* trisB;           /* + 4 B per face (edge2.z); unused with PHONGTESS */
 	const uint32_t* triMat;       /* material index per face, read once per shaded hit; unused with PHONGTESS */
-#if PT_NODE_ORDER
-	const int* nodeOrig;          /* permuted position -> index in the reference's array (for the `leaf` output) */
-#endif
+	const float4* wide;           /* ordered walk: 8 x float4 per wide node (NULL: not built) */
+	int wideTop;                  /* wide nodes [0, wideTop) are staged in shared memory by the wide kernels */
+	const int* faceLeaf;          /* ordered walk: face -> index of its leaf in the reference's node array */
 	const pbr_light* lights;
 	float phongAlpha;             /* PHONGTESS_ALPHA */
 	int numNodes;
@@ -69,7 +63,7 @@ struct Material {                 /* both reference layouts, widened */
 	vec3 rgbDiff, rgbSpec;
 };
 
-#define PT_MAX_BATCH 32           /* frames per batched launch */
+#define PT_MAX_BATCH 1            /* frames per launch (the in-kernel batch of round 1 measured slower and is gone) */
 
 struct FrameParams {
 	SceneDev scene;
@@ -108,13 +102,10 @@ __device__ __forceinline__ void loadNode(const float4* nodes, int index, float4&
 }
 
 /*
- * The two index words of a node record.
- * PT_NODE_ORDER == 0: the reference's array order (pre-order).  lo.w = first face or -1 (inner node), hi.w = second
- *   face or -1 (leaf) / miss link (inner node); the node after a box hit, and after a leaf, is cur + 1.
- * PT_NODE_ORDER == 1 (experiment, scripts/node_permutation_proto.py): the array is permuted so that the nodes with
- *   the largest surface area -- the most visited ones -- are dense, and every link is explicit: inner node lo.w =
- *   where to go after a box hit, hi.w = miss link; leaf lo.w = first face, hi.w = successor | LEAF | (TWO: a second
- *   face, always first + 1).  Link 0 ends the walk.  Every ray visits the same nodes in the same order.
+ * The two index words of a node record (the reference's array order, pre-order): lo.w = first face (leaf), -1
+ * (inner node) or -2 (inner node carrying traverseShadows' "skip the next left child" flag, pt_bvh.cl:157-159 --
+ * the reference's host never sets it, a foreign buffer may); hi.w = second face or -1 (leaf) / miss link (inner
+ * node).  The node after a box hit, and after a leaf, is cur + 1.
  */
 struct NodeWords {
 	bool leaf;
@@ -123,21 +114,14 @@ struct NodeWords {
 	int face0, face1;  /* leaf: its faces (face1 = -1: only one) */
 };
 
+template <bool ANY_HIT>
 __device__ __forceinline__ NodeWords decodeNode(const int cur, const int loW, const int hiW) {
 	NodeWords w;
-#if PT_NODE_ORDER
-	w.leaf = hiW < 0;
-	w.afterMiss = hiW & 0x3fffffff;
-	w.afterHit = w.leaf ? w.afterMiss : loW;
-	w.face0 = loW;
-	w.face1 = (hiW & 0x40000000) ? loW + 1 : -1;
-#else
 	w.leaf = loW >= 0;
 	w.afterMiss = w.leaf ? cur + 1 : hiW;
-	w.afterHit = cur + 1;
+	w.afterHit = cur + 1 + ((ANY_HIT && loW == -2) ? 1 : 0);
 	w.face0 = loW;
 	w.face1 = hiW;
-#endif
 	return w;
 }
 
@@ -150,19 +134,10 @@ __device__ __forceinline__ NodeWords decodeNode(const int cur, const int loW, co
 __device__ __forceinline__ void loadTri(const SceneDev& S, int face, float4& A, float4& E1, float4& E2) {
 	const float4* p = S.tris + PT_TRI_STRIDE * (size_t) face;
 	float e1y, e1z, e2x, e2y;
-#if PT_TRI_NO_L1
-	/* experiment: triangle records bypass L1, so that they do not evict the node lines the rays are walking in */
-	asm volatile("ld.global.nc.L1::no_allocate.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-		: "=f"(A.x), "=f"(A.y), "=f"(A.z), "=f"(E1.x), "=f"(e1y), "=f"(e1z), "=f"(e2x), "=f"(e2y)
-		: "l"(p));
-	float e2z;
-	asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(e2z) : "l"(S.trisB + face));
-#else
 	asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
 		: "=f"(A.x), "=f"(A.y), "=f"(A.z), "=f"(E1.x), "=f"(e1y), "=f"(e1z), "=f"(e2x), "=f"(e2y)
 		: "l"(p));
 	const float e2z = __ldg(S.trisB + face);
-#endif
 	A.w = 0.0f;
 	E1.y = e1y; E1.z = e1z; E1.w = 0.0f;
 	E2 = make_float4(e2x, e2y, e2z, 0.0f);
@@ -211,6 +186,34 @@ __device__ __forceinline__ void intersectFaceLoaded(
 		hitFace = face;
 		hitLeaf = leaf;
 	}
+}
+
+/* The same test as a function of the face alone (the ordered walk, pt_wide.cuh): the t flatTriAndRayIntersect
+ * leaves behind for a ray whose ray.t is still INFINITY, or INFINITY when it rejects the face.  With a finite
+ * ray.t the reference additionally rejects t' >= ray.t before the barycentric tests (pt_intersect.cl:107); such a
+ * face has t = t' + f >= ray.t and loses the `ray->t > t` comparison of intersectFace anyway (pt_bvh.cl:17), so
+ * "accepted" is exactly "returned t < ray.t". */
+__device__ __forceinline__ float faceTLoaded(
+	const float4 A, const float4 E1, const float4 E2, const vec3 o, const vec3 d, const float tNear
+) {
+	const float f = fmaxf(0.0f, tNear - 0.001f);
+	const vec3 closeOrigin = pm::fma3(d, f, o);
+	const vec3 edge1 = f4xyz(E1);
+	const vec3 edge2 = f4xyz(E2);
+	const vec3 tVec = closeOrigin - f4xyz(A);
+	const vec3 pVec = pm::cross(d, edge2);
+	const vec3 qVec = pm::cross(tVec, edge1);
+	const float invDet = pm::rcp(pm::dot(edge1, pVec));
+
+	float t = pm::dot(edge2, qVec) * invDet;
+	if (t >= PM_INF_F || t < PT_EPSILON5) return PM_INF_F;
+
+	const float u = pm::dot(tVec, pVec) * invDet;
+	const float v = pm::dot(d, qVec) * invDet;
+	if (u + v > 1.0f || fminf(u, v) < 0.0f) return PM_INF_F;
+
+	t += f;
+	return (t < PM_INF_F) ? t : PM_INF_F;          /* NaN can never be accepted (`ray->t > NaN` is false) */
 }
 
 __device__ __forceinline__ void intersectFace(
@@ -565,7 +568,7 @@ __device__ __forceinline__ void traverseClosest(
 		float4 lo, hi;
 		loadNode(S.nodes, index, lo, hi);
 		const int cur = index;
-		const NodeWords w = decodeNode(cur, __float_as_int(lo.w), __float_as_int(hi.w));
+		const NodeWords w = decodeNode<false>(cur, __float_as_int(lo.w), __float_as_int(hi.w));
 
 		index = w.afterMiss;
 
@@ -608,7 +611,7 @@ __device__ __forceinline__ void traverseAny(
 		float4 lo, hi;
 		loadNode(S.nodes, index, lo, hi);
 		const int cur = index;
-		const NodeWords w = decodeNode(cur, __float_as_int(lo.w), __float_as_int(hi.w));
+		const NodeWords w = decodeNode<true>(cur, __float_as_int(lo.w), __float_as_int(hi.w));
 
 		index = w.afterMiss;
 

@@ -17,9 +17,10 @@
  * Per-pixel arithmetic and its order are those of the reference kernel, so every pixel gets the
  * same bits whatever the scheduling.  `megaKernel` keeps the reference's launch structure (one
  * thread per pixel, everything inline): the on-device cross-check of the wavefront and the faster of
- * the two on small scenes (pbr_capi.cu chooses by measurement).  Also here: the carry-over variant of
- * the traverse kernel, the explicit-ray kernels, the scene repack.  pt_persistent.cuh holds the
- * two-resident-kernels pipeline.
+ * the two on small scenes (pbr_capi.cu chooses by measurement).  Also here: the explicit-ray kernels and the
+ * scene repack.  The traverse stage exists twice: here in the reference's visiting order (one lane per ray, the
+ * stackless pre-order walk: visit counters and debug image bit-exact), and in pt_wide.cuh as the ordered walk
+ * over a 4-wide BVH (four lanes per ray: same hits, same image, a fraction of the node fetches).
  *
  * Path state lives in HBM as 16-byte SoA records (coalesced 128-bit accesses):
  *     rayO (o.xyz, t)   rayD (d.xyz, hitFace)   colS (color.xyz, seed)   finF (finalColor.xyz, focus)
@@ -42,7 +43,6 @@ struct WaveState {
 	uint4* misc;
 	uint2* dbg;
 	float4* hitN;             /* PHONGTESS only: normal of the hit found by traverse */
-	int* node;                /* carry-over wavefront only: node at which the path's ray resumes (1 = new ray) */
 };
 
 /* ctrl[0], ctrl[1]: element counts of queue 0 / 1;  ctrl[2]: work cursor of the traverse kernel */
@@ -57,7 +57,6 @@ __device__ __forceinline__ void storePath(const WaveState& W, const uint32_t p, 
 	W.colS[p] = make_float4(s.color.x, s.color.y, s.color.z, s.seed);
 	W.finF[p] = make_float4(s.finalColor.x, s.finalColor.y, s.finalColor.z, s.focus);
 	W.misc[p] = make_uint4(s.depth | ((uint32_t) s.depthAdded << 16), s.sample, s.secondaryPaths, s.frame);
-	if (W.node) W.node[p] = 1;
 }
 
 __device__ __forceinline__ void loadPath(const WaveState& W, const uint32_t p, PathState& s) {
@@ -158,7 +157,7 @@ template <bool ANY_HIT>
 __device__ __forceinline__ bool nodeVisit(LaneRay& L, const float4 lo, const float4 hi) {
 	L.nn++;
 	const int cur = L.index;
-	const NodeWords w = decodeNode(cur, __float_as_int(lo.w), __float_as_int(hi.w));
+	const NodeWords w = decodeNode<ANY_HIT>(cur, __float_as_int(lo.w), __float_as_int(hi.w));
 
 	L.index = w.afterMiss;
 
@@ -185,18 +184,11 @@ __device__ __forceinline__ bool nodeStep(const SceneDev& S, LaneRay& L) {
 }
 
 /* intersectFaces (pt_bvh.cl:35-46) for the pending leaf. */
-#ifndef PT_LEAF_HOIST
-#define PT_LEAF_HOIST 1
-#endif
-#ifndef PT_HELPER_PREFETCH
-#define PT_HELPER_PREFETCH 0               /* 1, 2: resting lanes fetch the neighbour sector for stepping lanes (experiment) */
-#endif
 #ifndef PT_TRAVERSE_MIN_BLOCKS
 #define PT_TRAVERSE_MIN_BLOCKS 9           /* resident blocks of 128 threads per SM the traversal kernels are compiled for */
 #endif
 template <bool ANY_HIT, bool PHONG>
 __device__ __forceinline__ void leafStep(const SceneDev& S, LaneRay& L) {
-#if PT_LEAF_HOIST
 	if (!PHONG) {
 		/* both records are requested before the first test, so a two-face leaf costs one trip to L2 instead of
 		 * two; the tests themselves run in the reference's order */
@@ -211,17 +203,14 @@ __device__ __forceinline__ void leafStep(const SceneDev& S, LaneRay& L) {
 			intersectFaceLoaded(A1, E11, E21, L.leafF1, L.leafCur, L.o, L.d, L.leafTNear, L.rt, L.hitFace, L.hitLeaf);
 			L.nt++;
 		}
-		if (ANY_HIT && L.rt < L.tLight) L.index = -1;     /* `break` of traverseShadows (pt_bvh.cl:170-172) */
-		return;
 	}
-#endif
-	if (PHONG) intersectFacePhong(S, L.leafF0, L.leafCur, L.o, L.d, L.leafTNear, L.leafTFar, L.rt, L.hitFace, L.hitLeaf, L.normal);
-	else intersectFace(S, L.leafF0, L.leafCur, L.o, L.d, L.leafTNear, L.rt, L.hitFace, L.hitLeaf);
-	L.nt++;
-	if (L.leafF1 != -1) {
-		if (PHONG) intersectFacePhong(S, L.leafF1, L.leafCur, L.o, L.d, L.leafTNear, L.leafTFar, L.rt, L.hitFace, L.hitLeaf, L.normal);
-		else intersectFace(S, L.leafF1, L.leafCur, L.o, L.d, L.leafTNear, L.rt, L.hitFace, L.hitLeaf);
+	else {
+		intersectFacePhong(S, L.leafF0, L.leafCur, L.o, L.d, L.leafTNear, L.leafTFar, L.rt, L.hitFace, L.hitLeaf, L.normal);
 		L.nt++;
+		if (L.leafF1 != -1) {
+			intersectFacePhong(S, L.leafF1, L.leafCur, L.o, L.d, L.leafTNear, L.leafTFar, L.rt, L.hitFace, L.hitLeaf, L.normal);
+			L.nt++;
+		}
 	}
 	if (ANY_HIT && L.rt < L.tLight) L.index = -1;     /* `break` of traverseShadows (pt_bvh.cl:170-172) */
 }
@@ -277,39 +266,6 @@ __device__ __forceinline__ void traverseEngine(
 		if (__ballot_sync(FULL, state != LANE_IDLE) == 0u) break;
 
 		/* node phase: index stays inside [1, numNodes) while a lane is stepping */
-#if PT_HELPER_PREFETCH
-		/* Experiment: L1 fills one 32-byte sector per miss, so the node behind the one a ray
-		 * visits -- its left child, 47 % of all successors are in the same 128-byte line -- is not in L1 when the
-		 * ray gets there.  Lanes that are not stepping in this round ride along in the same load instruction and
-		 * ask for that neighbour sector on behalf of a stepping lane: same line, so the same L1 request, and the
-		 * stepping lane's next fetch finds it.  The value is discarded; no ray's walk changes.
-		 * 1: a lane helps its neighbour (lane ^ 1);  2: the r-th resting lane helps the r-th stepping lane. */
-		unsigned stepMask = __ballot_sync(FULL, state == LANE_STEPPING);
-		while (true) {
-			int helpFor = lane;
-			if (PT_HELPER_PREFETCH == 1) {
-				if (state != LANE_STEPPING && ((stepMask >> (lane ^ 1)) & 1u)) helpFor = lane ^ 1;
-			}
-			else {
-				const int r = __popc(~stepMask & ltMask);
-				if (state != LANE_STEPPING && r < __popc(stepMask)) helpFor = (int) __fns(stepMask, 0u, r + 1);
-			}
-			const int theirs = __shfl_sync(FULL, L.index, helpFor);
-			const int succ = theirs + 1;
-			const bool helper = (helpFor != lane) && ((succ & 3) != 0) && ((unsigned) (succ - 1) < lastNode);
-			if (state == LANE_STEPPING || helper) {
-				float4 lo, hi;
-				loadNode(S.nodes, (state == LANE_STEPPING) ? L.index : succ, lo, hi);
-				if (state == LANE_STEPPING) {
-					const bool leaf = nodeVisit<ANY_HIT>(L, lo, hi);
-					const bool inside = (unsigned) (L.index - 1) < lastNode;
-					state = leaf ? LANE_PENDING : (inside ? LANE_STEPPING : LANE_FINISHED);
-				}
-			}
-			stepMask = __ballot_sync(FULL, state == LANE_STEPPING);
-			if (__popc(stepMask) < S.nodePhaseMin) break;
-		}
-#else
 		while (true) {
 			if (state == LANE_STEPPING) {
 				const bool leaf = nodeStep<ANY_HIT>(S, L);
@@ -318,7 +274,6 @@ __device__ __forceinline__ void traverseEngine(
 			}
 			if (__popc(__ballot_sync(FULL, state == LANE_STEPPING)) < S.nodePhaseMin) break;
 		}
-#endif
 
 		/* triangle phase */
 		if (state == LANE_PENDING) {
@@ -338,6 +293,7 @@ struct WaveRaySource {
 		o = v3(a.x, a.y, a.z); rt = a.w;
 		d = v3(b.x, b.y, b.z); hf = __float_as_int(b.w);
 	}
+	__device__ __forceinline__ bool wantsLeaf() const { return false; }
 	__device__ __forceinline__ void store(uint32_t, const LaneRay& L) {
 		W.rayO[p].w = L.rt;
 		W.rayD[p].w = __int_as_float(L.hitFace);
@@ -368,32 +324,6 @@ __global__ void __launch_bounds__(128, PHONG ? 1 : PT_TRAVERSE_MIN_BLOCKS) trave
 }
 
 
-/* ------------------------------------------------------------------ traverse with carry-over */
-
-/*
- * The number of nodes a ray visits has a long tail (C2: mean 150, max > 1 400), a ray is one serial chain
- * of dependent loads (~0.5 us per node under load), and with persistent warps nearly every warp ends up
- * holding one of the long rays: a launch of traverseKernel lasts ~0.9 ms however few rays it has, and no
- * block retires early enough for another kernel to fill in.  Here a launch ends when its queue runs dry:
- * `tailSteps` node steps after a warp has seen the queue empty it tests the leaves it has pending, retires
- * the rays that are done and parks the others -- best hit so far in the path state, next node in
- * WaveState::node -- in the carry queue.  The next launch resumes them first, packed densely with the rays
- * of the next bounce, so the machine is always full and a long ray only delays its own path.  A resumed ray
- * continues at exactly the node where it stopped with exactly the state it had: same visits, same hits.
- *
- *   in:  carry queue (parked by the previous launch) ++ new queue (written by the previous shade launch)
- *   out: hit queue (finished rays, for the next shade launch) and the other carry queue
- */
-struct CarryQueues {
-	const uint32_t* qCarryIn; const uint32_t* nCarryIn;
-	const uint32_t* qNew; const uint32_t* nNew;       /* qNew == NULL: identity (first iteration) */
-	uint32_t* qHit; uint32_t* nHit;
-	uint32_t* qCarryOut; uint32_t* nCarryOut;
-	uint32_t* cursor;
-	uint32_t* zeroAtStart;                             /* a counter nobody uses during this launch */
-	volatile uint32_t* mailbox;                        /* host-visible: how many rays this launch started with */
-};
-
 /* Append path p to a queue for every lane with `push` set; all 32 lanes must call. */
 __device__ __forceinline__ void queueAppend(uint32_t* queue, uint32_t* count, const bool push, const uint32_t p) {
 	const unsigned FULL = 0xffffffffu;
@@ -405,149 +335,6 @@ __device__ __forceinline__ void queueAppend(uint32_t* queue, uint32_t* count, co
 	if (lane == leader) base = atomicAdd(count, (uint32_t) __popc(m));
 	base = __shfl_sync(FULL, base, leader);
 	if (push) queue[base + (uint32_t) __popc(m & ((1u << lane) - 1u))] = p;
-}
-
-template <bool PHONG>
-__global__ void __launch_bounds__(128) traverseCarryKernel(
-	const SceneDev S, const WaveState W, const CarryQueues Q, const int tailStepsBulk, const int tailStepsFlush,
-	unsigned long long* stats
-) {
-	const unsigned FULL = 0xffffffffu;
-	const int lane = threadIdx.x & 31;
-	const unsigned ltMask = (1u << lane) - 1u;
-	const unsigned lastNode = (unsigned) (S.numNodes - 1);
-	const uint32_t nCarry = *Q.nCarryIn, count = nCarry + *Q.nNew;
-	if (blockIdx.x == 0 && threadIdx.x == 0) {
-		*Q.zeroAtStart = 0u;
-		*Q.mailbox = count;
-		__threadfence_system();
-	}
-	/* fewer rays than lanes: nothing is waiting behind them, let them run longer before parking */
-	int budget = (count > gridDim.x * blockDim.x) ? tailStepsBulk : tailStepsFlush;
-
-	LaneRay L;
-	L.index = 0;
-	int state = LANE_IDLE;
-	bool exhausted = false;
-	uint32_t p = 0, nodes = 0, tris = 0, rays = 0, trips = 0;
-
-	while (true) {
-		/* retire finished rays */
-		const bool fin = (state == LANE_FINISHED);
-		if (fin) {
-			W.rayO[p].w = L.rt;
-			W.rayD[p].w = __int_as_float(L.hitFace);
-			uint2 g = W.dbg[p];
-			g.x += L.nn; g.y += L.nt;
-			W.dbg[p] = g;
-			if (PHONG) W.hitN[p] = make_float4(L.normal.x, L.normal.y, L.normal.z, 0.0f);
-			nodes += L.nn; tris += L.nt; rays++;
-			state = LANE_IDLE;
-		}
-		queueAppend(Q.qHit, Q.nHit, fin, p);
-
-		/* refill idle lanes: parked rays first, then the new ones */
-		const unsigned need = __ballot_sync(FULL, state == LANE_IDLE);
-		if (!exhausted && (__popc(need) >= S.refillMin || need == FULL)) {
-			const int leader = __ffs(need) - 1;
-			const int n = __popc(need);
-			uint32_t base = 0;
-			if (lane == leader) base = atomicAdd(Q.cursor, (uint32_t) n);
-			base = __shfl_sync(FULL, base, leader);
-			if (state == LANE_IDLE) {
-				const uint32_t i = base + (uint32_t) __popc(need & ltMask);
-				if (i < count) {
-					p = (i < nCarry) ? Q.qCarryIn[i] : (Q.qNew ? Q.qNew[i - nCarry] : i - nCarry);
-					const float4 a = W.rayO[p], b = W.rayD[p];
-					const int node = W.node[p];
-					L.o = v3(a.x, a.y, a.z);
-					L.d = v3(b.x, b.y, b.z);
-					L.invDir = v3(pm::rcp(b.x), pm::rcp(b.y), pm::rcp(b.z));
-					L.rt = a.w;
-					L.tLight = a.w;
-					L.hitFace = __float_as_int(b.w);
-					L.hitLeaf = -1;
-					L.index = node;
-					L.nn = 0;
-					L.nt = 0;
-					L.normal = v3(0.0f, 0.0f, 0.0f);
-					if (node == 1) {
-						if (S.numLights > 0) traverseLights(S, L.o, L.d, L.rt, L.hitFace);
-					}
-					else if (PHONG) {
-						const float4 hn = W.hitN[p];
-						L.normal = v3(hn.x, hn.y, hn.z);
-					}
-					state = ((unsigned) (L.index - 1) < lastNode) ? LANE_STEPPING : LANE_FINISHED;
-				}
-			}
-			if (base + (uint32_t) n >= count) exhausted = true;
-		}
-		if (__ballot_sync(FULL, state != LANE_IDLE) == 0u) break;
-
-		/* a warp that never needs a refill learns from the cursor that the queue is empty */
-		if (!exhausted && (++trips & 7u) == 0u) {
-			uint32_t c = 0;
-			if (lane == 0) c = *((volatile uint32_t*) Q.cursor);
-			exhausted = __shfl_sync(FULL, c, 0) >= count;
-		}
-
-		/* node phase */
-		while (true) {
-			if (state == LANE_STEPPING) {
-				const bool leaf = nodeStep<false>(S, L);
-				const bool inside = (unsigned) (L.index - 1) < lastNode;
-				state = leaf ? LANE_PENDING : (inside ? LANE_STEPPING : LANE_FINISHED);
-			}
-			if (exhausted) budget--;
-			if (__popc(__ballot_sync(FULL, state == LANE_STEPPING)) < S.nodePhaseMin || (exhausted && budget <= 0)) break;
-		}
-
-		/* triangle phase */
-		if (state == LANE_PENDING) {
-			leafStep<false, PHONG>(S, L);
-			state = ((unsigned) (L.index - 1) < lastNode) ? LANE_STEPPING : LANE_FINISHED;
-		}
-
-		/* queue empty and the grace period over: park what is still walking (finished rays retire above) */
-		if (exhausted && budget <= 0) {
-			const bool park = (state == LANE_STEPPING);
-			if (park) {
-				W.rayO[p].w = L.rt;
-				W.rayD[p].w = __int_as_float(L.hitFace);
-				uint2 g = W.dbg[p];
-				g.x += L.nn; g.y += L.nt;
-				W.dbg[p] = g;
-				if (PHONG) W.hitN[p] = make_float4(L.normal.x, L.normal.y, L.normal.z, 0.0f);
-				W.node[p] = L.index;
-				nodes += L.nn; tris += L.nt;
-				state = LANE_IDLE;
-			}
-			queueAppend(Q.qCarryOut, Q.nCarryOut, park, p);
-		}
-	}
-	warpAddStat(stats + 0, rays);
-	warpAddStat(stats + 2, nodes);
-	warpAddStat(stats + 3, tris);
-}
-
-/* raygen for the carry-over wavefront: ctl = nNew[2], nCarry[2], nHit[2], cursor */
-__global__ void __launch_bounds__(256) raygenCarryKernel(const FrameParams P, const WaveState W, uint32_t* ctl, const int nPaths) {
-	const int stride = gridDim.x * blockDim.x;
-	for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < nPaths; p += stride) {
-		int px, py;
-		pixelOf(P, p, px, py);
-		PathState s;
-		s.frame = 0u;
-		initPath(P, s);
-		beginSample(P, s, px, py);
-		storePath(W, (uint32_t) p, s);
-		W.dbg[p] = make_uint2(0u, 0u);
-	}
-	if (blockIdx.x == 0 && threadIdx.x == 0) {
-		ctl[0] = (uint32_t) nPaths;
-		for (int i = 1; i < 8; i++) ctl[i] = 0u;
-	}
 }
 
 /* ------------------------------------------------------------------ shade */
@@ -665,6 +452,7 @@ struct ShadowRaySource {
 		o = v3(a.x, a.y, a.z); rt = a.w;
 		d = v3(b.x, b.y, b.z); hf = 0;
 	}
+	__device__ __forceinline__ bool wantsLeaf() const { return false; }
 	__device__ __forceinline__ void store(uint32_t, const LaneRay& L) {
 		shadowO[p].w = L.rt;
 		W.dbg[p].y += L.nt;                 /* shadow-ray face tests count into debugColor.x; node visits do not */
@@ -726,9 +514,6 @@ __global__ void __launch_bounds__(128) megaKernel(const FrameParams P, const int
 struct ExplicitRaySource {
 	const pbr_ray* __restrict__ rays;
 	pbr_hit* __restrict__ hits;
-#if PT_NODE_ORDER
-	const int* __restrict__ nodeOrig;
-#endif
 	__device__ __forceinline__ void fetch(unsigned long long i, vec3& o, vec3& d, float& rt, int& hf) {
 		const float4 a = __ldg((const float4*) &rays[i].origin);
 		const float4 b = __ldg((const float4*) &rays[i].dir);
@@ -737,15 +522,12 @@ struct ExplicitRaySource {
 		rt = b.w;
 		hf = 0;
 	}
+	__device__ __forceinline__ bool wantsLeaf() const { return true; }
 	__device__ __forceinline__ void store(unsigned long long i, const LaneRay& L) {
 		int4 out;
 		out.x = __float_as_int(L.rt);
 		out.y = L.hitFace;
-#if PT_NODE_ORDER
-		out.z = (L.hitLeaf > 0) ? __ldg(nodeOrig + L.hitLeaf) : L.hitLeaf;      /* back to the reference's numbering */
-#else
 		out.z = L.hitLeaf;
-#endif
 		out.w = (int) (min(L.nn, 0xfffffu) | (min(L.nt, 0xfffu) << 20));
 		*((int4*) &hits[i]) = out;
 	}
@@ -757,11 +539,7 @@ __global__ void __launch_bounds__(128, PT_TRAVERSE_MIN_BLOCKS) traceRaysKernel(
 	unsigned long long* cursor, unsigned long long* stats
 ) {
 	uint32_t nodes = 0, tris = 0, cnt = 0;
-#if PT_NODE_ORDER
-	ExplicitRaySource src = {rays, hits, S.nodeOrig};
-#else
 	ExplicitRaySource src = {rays, hits};
-#endif
 	traverseEngine<ANY_HIT, false>(S, src, (unsigned long long) n, cursor, nodes, tris, cnt);
 	warpAddStat(stats + (ANY_HIT ? 1 : 0), cnt);
 	warpAddStat(stats + (ANY_HIT ? 5 : 2), nodes);
@@ -779,9 +557,11 @@ __global__ void repackNodesKernel(const float4* __restrict__ src, const int numS
 	if (i < numSrc) {
 		lo = src[2 * (size_t) i];
 		hi = src[2 * (size_t) i + 1];
-		const bool inner = (lo.w <= -1.0f);
-		const int loW = inner ? -1 : (int) lo.w;
-		const int hiW = (int) hi.w;
+		/* pt_bvh.cl:100,117: `bbMin.w <= -1` takes the miss link, `bbMin.w >= 0` tests faces; anything in between
+		 * (or NaN) does neither -- the walk steps over such a node to cur + 1 whether its box is hit or not */
+		const bool inner = (lo.w <= -1.0f), leaf = (lo.w >= 0.0f);
+		const int loW = inner ? ((lo.w == -2.0f) ? -2 : -1) : (leaf ? (int) lo.w : -1);
+		const int hiW = (inner || leaf) ? (int) hi.w : i + 1;
 		lo.w = __int_as_float(loW);
 		hi.w = __int_as_float(hiW);
 	}

@@ -112,7 +112,8 @@ class PathTracer {
 		cl_mem getBufVertices() const { return mBufVertices; }
 		cl_mem getBufLights() const { return mBufLights; }
 		cl_uint getNumLights() const { return (cl_uint) mLights.size(); }
-		const camera_cl& getCameraStruct() const { return mStructCam; }
+		/** The camera as the next frame will see it (additive accessor). */
+		const camera_cl& getCameraStruct() { this->updateEyeBuffer(); return mStructCam; }
 		cl_float getPxDim() const { return mPxDim; }
 
 	protected:

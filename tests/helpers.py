@@ -175,9 +175,18 @@ def shadow_rays_from_hits(rays, hits, light_pos):
 
 
 def images_equal(a, b):
-    """Bit-level equality with NaN == NaN (the two sides may carry different NaN payloads)."""
-    a, b = np.asarray(a, f32), np.asarray(b, f32)
-    return bool(np.all((a == b) | (np.isnan(a) & np.isnan(b))))
+    """Bit-level equality (+0 and -0 differ) with NaN == NaN (the two sides may carry different NaN payloads)."""
+    a, b = np.ascontiguousarray(a, f32), np.ascontiguousarray(b, f32)
+    if a.shape != b.shape:
+        return False
+    return bool(np.all((a.view(np.uint32) == b.view(np.uint32)) | (np.isnan(a) & np.isnan(b))))
+
+
+def count_identical_pixels(a, b):
+    """Number of pixels whose four channels are bit-identical (NaN == NaN)."""
+    a, b = np.ascontiguousarray(a, f32), np.ascontiguousarray(b, f32)
+    same = (a.view(np.uint32) == b.view(np.uint32)) | (np.isnan(a) & np.isnan(b))
+    return int(same.reshape(-1, a.shape[-1]).all(axis=1).sum())
 
 
 def mean_relative_error(a, b):

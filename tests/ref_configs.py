@@ -102,6 +102,9 @@ def static_program_values():
     for brdf in (1, 0):
         for seed in range(T.TRIALS):
             yield R.values_from_defines(T._trial(seed, brdf).defines)
+    import config_cases                                            # C1 at 512x512, C3 at 1920x1080 (both BRDFs)
+    for v in config_cases.program_values():
+        yield v
 
 
 def all_program_values():

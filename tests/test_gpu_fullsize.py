@@ -1,7 +1,7 @@
 """GPU, BASELINE.json's full C2 size (1 M-triangle soup, 1920x1080): what cannot be compared pixel by pixel with
 a CPU run in test time is pinned by size-independent properties --
   * explicit closest-hit and shadow rays: a 200 k sample against the oracle, bit for bit (face, leaf, t, visits);
-  * every pipeline (wavefront, megakernel, persistent, carry-over) writes the same 1080p frame and counters;
+  * both pipelines (wavefront, megakernel) write the same 1080p frame and counters, and the ordered walk the same frame;
   * sharding is idempotent: the frame rendered in three row blocks equals the frame rendered whole;
   * a batch of frames equals the same frames one by one; accumulation is linear in the sense of setColors:
     frame k of the running average is (k * previous + new) / (k + 1) of the same per-frame radiance."""
@@ -51,7 +51,7 @@ def test_fullsize_explicit_rays_bit_exact(c2, c2dev):
 
 def test_fullsize_pipelines_agree(device, c2dev):
     frames = {}
-    for pipeline in (0, 1, 2, 3):
+    for pipeline in (0, 1):
         device.setPipeline(pipeline)
         device.stats(reset=True)
         try:
@@ -61,7 +61,7 @@ def test_fullsize_pipelines_agree(device, c2dev):
         frames[pipeline] = (img, dbg, device.stats(reset=True))
     ref = frames[0]
     assert np.isfinite(ref[0][..., :3]).all() and 0.3 < ref[0][..., :3].mean() < 1.0
-    for pipeline in (1, 2, 3):
+    for pipeline in (1,):
         assert Hh.images_equal(frames[pipeline][0], ref[0]), "pipeline %d: frame" % pipeline
         assert Hh.images_equal(frames[pipeline][1], ref[1]), "pipeline %d: debug image" % pipeline
         assert np.array_equal(frames[pipeline][2], ref[2]), "pipeline %d: counters" % pipeline

@@ -117,7 +117,7 @@ def _render_both(device, prep, frames, pipeline=0):
 
 
 @pytest.mark.parametrize("brdf", [1, 0])
-@pytest.mark.parametrize("pipeline", [0, 1, 2, 3])
+@pytest.mark.parametrize("pipeline", [0, 1])
 def test_render_parity_suzanne(device, suzanne, brdf, pipeline):
     p = Hh.Prepared(suzanne, 128, 96, brdf=brdf, max_depth=4)
     got, gdbg, gstats, want, wdbg, wstats = _render_both(device, p, 4, pipeline)
@@ -155,7 +155,7 @@ def test_render_parity_multisample_and_dof(device, suzanne):
     assert np.array_equal(gstats, wstats)
 
 
-@pytest.mark.parametrize("pipeline", [0, 1, 2, 3])
+@pytest.mark.parametrize("pipeline", [0, 1])
 @pytest.mark.parametrize("brdf,shadow", [(1, 0), (0, 1)])
 def test_render_parity_phong_tessellation(device, suzanne, pipeline, brdf, shadow):
     """render.phong_tessellation > 0: Ogaki-Tokuyoshi direct ray tracing of Phong tessellation
@@ -193,29 +193,25 @@ def test_device_equals_reference_kernel(device, name):
     assert Hh.images_equal(gdbg, dbg)
 
 
-def _batch_both(device, prep, frames, pipeline, interleave=1):
+def _batch_both(device, prep, frames, pipeline):
     ds = Hh.DeviceScene(device, prep)
     device.setPipeline(pipeline)
-    device.setTuning("batch_interleave", interleave)
     device.stats(reset=True)
     try:
         got, gdbg = ds.frames_batch(frames)
         gstats = device.stats(reset=True)
     finally:
         device.setPipeline(-1)
-        device.setTuning("batch_interleave", 0)
     want, wdbg, wstats = prep.oracle_frames(frames)
     return got, gdbg, gstats, want, wdbg, wstats
 
 
-@pytest.mark.parametrize("pipeline", [0, 1, 2, 3])
-@pytest.mark.parametrize("interleave", [0, 1])
+@pytest.mark.parametrize("pipeline", [0, 1])
 @pytest.mark.parametrize("brdf,shadow,samples", [(1, 0, 1), (0, 1, 2)])
-def test_render_parity_batched_frames(device, suzanne, pipeline, interleave, brdf, shadow, samples):
-    """pbr_kernel_launch_batch, frame after frame or with pixels running ahead into their next frame:
-    the pixels stay the reference's."""
+def test_render_parity_batched_frames(device, suzanne, pipeline, brdf, shadow, samples):
+    """pbr_kernel_launch_batch: the pixels stay the reference's."""
     p = Hh.Prepared(suzanne, 112, 80, brdf=brdf, shadow_rays=shadow, samples=samples, max_depth=4)
-    got, gdbg, gstats, want, wdbg, wstats = _batch_both(device, p, 6, pipeline, interleave)
+    got, gdbg, gstats, want, wdbg, wstats = _batch_both(device, p, 6, pipeline)
     assert Hh.mean_relative_error(got, want) <= RADIANCE_MRE_TOLERANCE
     assert Hh.images_equal(got, want)
     assert Hh.images_equal(gdbg, wdbg)
@@ -228,16 +224,13 @@ def test_render_batched_frames_depth_of_field_and_long_batches(device, suzanne):
     got, gdbg, gstats, want, wdbg, wstats = _batch_both(device, p, 5, 0)
     assert Hh.images_equal(got, want)
     assert np.array_equal(gstats, wstats)
-    # more frames than one device batch holds (PT_MAX_BATCH = 32), continuing an accumulated image
+    # a long batch, continuing an accumulated image
     p = Hh.Prepared(suzanne, 48, 32, max_depth=3)
     ds = Hh.DeviceScene(device, p)
     start, _ = ds.frames(2)
     seq, _ = ds.frames(35, image=start.copy(), first=2, host_roundtrip=False)
-    for interleave in (0, 1):
-        device.setTuning("batch_interleave", interleave)
-        bat, _ = ds.frames_batch(35, image=start.copy(), first=2)
-        device.setTuning("batch_interleave", 0)
-        assert Hh.images_equal(seq, bat)
+    bat, _ = ds.frames_batch(35, image=start.copy(), first=2)
+    assert Hh.images_equal(seq, bat)
 
 
 def test_render_parity_soup(device, oracle):
@@ -266,7 +259,7 @@ def test_non_multiple_image_size_and_tiles(device, suzanne):
     device.setTile(-1, -1)
     assert Hh.images_equal(stitched, full)
     # interleaved stripes (pbr_set_tile_stripes): 3 "ranks", stripes of 4 and of 2 rows, every pipeline
-    for stripe, pipeline in ((4, 0), (2, 0), (4, 2), (4, 3), (8, 1)):
+    for stripe, pipeline in ((4, 0), (2, 0), (8, 1)):
         world = 48 // (stripe * (4 if stripe < 8 else 2))
         world = max(world, 2)
         if 48 % (stripe * world):
@@ -312,3 +305,155 @@ def test_error_reporting(device, suzanne):
     bad["brdf"] = 7
     with pytest.raises(pbr_b200.PbrError):
         device.loadProgram(bad)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# The ordered walk (pbr_set_traversal(1), csrc/pt_wide.cuh): same hit face, leaf and t bits, same image bits.
+# The visit counters and the debug image are the ordered walk's own and are not compared.
+
+def _ordered(device):
+    class _Ctx:
+        def __enter__(self_):
+            device.setTraversal(1)
+            device.traversalInfo(reset=True)
+
+        def __exit__(self_, *a):
+            device.setTraversal(-1)
+    return _Ctx()
+
+
+@pytest.mark.parametrize("brdf,shadow,samples", [(1, 0, 1), (0, 0, 1), (1, 1, 1), (0, 1, 2)])
+def test_ordered_walk_frames_suzanne(device, suzanne, brdf, shadow, samples):
+    p = Hh.Prepared(suzanne, 128, 96, brdf=brdf, shadow_rays=shadow, samples=samples, max_depth=4)
+    ds = Hh.DeviceScene(device, p)
+    device.setPipeline(0)
+    try:
+        with _ordered(device):
+            got, _ = ds.frames(3)
+            info = device.traversalInfo()
+    finally:
+        device.setPipeline(-1)
+    want, _, wstats = p.oracle_frames(3)
+    assert info["last_used"] == 1 and info["wide_available"] == 1
+    assert info["ordered_rays"] == int(wstats[0]) + int(wstats[1])          # every ray of the frames took the ordered walk
+    assert Hh.mean_relative_error(got, want) <= RADIANCE_MRE_TOLERANCE
+    assert Hh.images_equal(got, want)
+
+
+def test_ordered_walk_is_automatic_without_debug_image(device, suzanne):
+    p = Hh.Prepared(suzanne, 96, 64, max_depth=4)
+    ds = Hh.DeviceScene(device, p)
+    want, wdbg, _ = p.oracle_frames(2)
+    device.setPipeline(0)
+    try:
+        got, gdbg = ds.frames(2)                                    # debug image on (the default of a pbr_ctx)
+        assert device.traversalInfo()["last_used"] == 0
+        assert Hh.images_equal(got, want) and Hh.images_equal(gdbg, wdbg)
+        device.setDebugImage(False)
+        got, _ = ds.frames(2)
+        assert device.traversalInfo()["last_used"] == 1
+        assert Hh.images_equal(got, want)
+        device.setTraversal(0)                                      # forced reference order
+        got, _ = ds.frames(2)
+        assert device.traversalInfo()["last_used"] == 0
+        assert Hh.images_equal(got, want)
+    finally:
+        device.setTraversal(-1)
+        device.setDebugImage(True)
+        device.setPipeline(-1)
+
+
+@pytest.mark.parametrize("kw", [dict(), dict(skip_ahead=False), dict(max_faces=1)])
+def test_ordered_walk_explicit_rays(device, oracle, kw):
+    import pbr_b200
+    s = pbr_b200.scenes.soup(60000, seed=31)
+    p = Hh.Prepared(s, 64, 64, eye=(0.0, 0.0, 3.5), bvh_kwargs=kw)
+    ds = Hh.DeviceScene(device, p)
+    rays = np.concatenate([Hh.primary_rays(p, 200, 120), Hh.random_rays(30001, 6, -1.0, 1.0)])
+    rng = np.random.default_rng(3)
+    rays[-5000:, 7] = rng.uniform(0.0, 2.0, 5000).astype(np.float32)          # finite initial ray.t
+    want, _ = p.oracle_trace(rays)
+    with _ordered(device):
+        got = ds.trace(rays)
+        info = device.traversalInfo()
+    assert info["last_used"] == 1 and info["ordered_rays"] == len(rays)
+    assert np.array_equal(got["hitFace"], want["hitFace"]) and np.array_equal(got["leaf"], want["leaf"])
+    assert np.array_equal(got["t"].view(np.uint32), want["t"].view(np.uint32))
+    # any-hit rays keep the reference-order engine even when the ordered walk is forced
+    hits = want
+    sh = Hh.shadow_rays_from_hits(rays, hits, (0.0, 3.0, 0.0))
+    want_s, _ = p.oracle_trace(sh, any_hit=True)
+    with _ordered(device):
+        got_s = ds.trace(sh, any_hit=True)
+        assert device.traversalInfo()["last_used"] == 0
+    assert np.array_equal(got_s["hitFace"], want_s["hitFace"]) and np.array_equal(got_s["visits"], want_s["visits"])
+
+
+def test_ordered_walk_flat_coplanar_geometry_rewalks(device, oracle):
+    """Zero-thickness leaf boxes, coplanar overlapping layers: hits in front of their own leaf box, ties between leaves.
+    The ambiguity rule sends those rays through the reference-order walk; every hit is still the reference's."""
+    import test_wide_walk as T
+    p = Hh.Prepared(T.flat_floor_scene(), 160, 96, eye=(0.3, 1.5, 3.0), center=(0.0, 0.2, 1.0), max_depth=4)
+    ds = Hh.DeviceScene(device, p)
+    rays = T.rays_for(p, 60000, 11, -1.9, 1.9, grid=(320, 180))
+    rays[-30000:, 1] = np.abs(rays[-30000:, 1]) + 0.01
+    want, _ = p.oracle_trace(rays)
+    with _ordered(device):
+        got = ds.trace(rays)
+        info = device.traversalInfo()
+    assert info["rewalked_rays"] > 0
+    assert np.array_equal(got["hitFace"], want["hitFace"]) and np.array_equal(got["leaf"], want["leaf"])
+    assert np.array_equal(got["t"].view(np.uint32), want["t"].view(np.uint32))
+    device.setPipeline(0)
+    try:
+        with _ordered(device):
+            img, _ = ds.frames(2)
+    finally:
+        device.setPipeline(-1)
+    ref, _, _ = p.oracle_frames(2)
+    assert Hh.images_equal(img, ref)
+
+
+def test_ordered_walk_refused_for_foreign_node_arrays(device, suzanne):
+    """A node array the ordered walk cannot honour: automatic mode keeps the reference-order walk, forcing it fails loudly."""
+    import pbr_b200
+    p = Hh.Prepared(suzanne, 64, 48, max_depth=3)
+    leaf = np.where(p.nodes[1:, 3] >= 0.0)[0] + 1
+    p.nodes = p.nodes.copy()
+    p.nodes[leaf[5], 0] -= 10.0                    # a leaf box sticking out of its parent's
+    ds = Hh.DeviceScene(device, p)
+    want, _, _ = p.oracle_frames(1)
+    device.setPipeline(0)
+    device.setDebugImage(False)
+    try:
+        got, _ = ds.frames(1)
+        info = device.traversalInfo()
+        assert info["last_used"] == 0 and info["wide_available"] == 0 and "not inside" in info["why_not"]
+        assert Hh.images_equal(got, want)
+        device.setTraversal(1)
+        with pytest.raises(pbr_b200.capi.PbrError):
+            ds.frames(1)
+    finally:
+        device.setTraversal(-1)
+        device.setDebugImage(True)
+        device.setPipeline(-1)
+
+
+def test_ordered_walk_top_of_tree_budgets(device, oracle):
+    """The number of nodes staged in shared memory renumbers the tree and changes nothing else."""
+    import pbr_b200
+    s = pbr_b200.scenes.soup(40000, seed=8)
+    p = Hh.Prepared(s, 64, 64, eye=(0.0, 0.0, 3.5))
+    ds = Hh.DeviceScene(device, p)
+    rays = np.concatenate([Hh.primary_rays(p, 160, 90), Hh.random_rays(20000, 2, -1.0, 1.0)])
+    want, _ = p.oracle_trace(rays)
+    try:
+        for top in (1, 5, 21, 85, 341, 1365):
+            device.setTuning("wide_top", top)
+            with _ordered(device):
+                got = ds.trace(rays)
+                assert device.traversalInfo()["wide_top"] == min(top, device.traversalInfo()["wide_nodes"])
+            assert np.array_equal(got["hitFace"], want["hitFace"]) and np.array_equal(got["leaf"], want["leaf"]), top
+            assert np.array_equal(got["t"].view(np.uint32), want["t"].view(np.uint32)), top
+    finally:
+        device.setTuning("wide_top", 85)

@@ -1,0 +1,227 @@
+/*
+ * wide_walk_model.cpp -- TEST INFRASTRUCTURE: a CPU model of the ordered wide-BVH walk (csrc/pt_wide.cuh) next to
+ * a literal copy of the reference-order walk (traverse, source/opencl/pt_bvh.cl:82-123), built as a shared library
+ * by tests/test_wide_walk.py.
+ *
+ * What it pins, without a GPU:
+ *   - the product's wide-BVH builder (csrc/wide_bvh.h, the very header pbr_capi.cu includes) on real trees;
+ *   - the exactness argument of the ordered walk: for every ray, (t bits, face, leaf) of the ordered walk -- nearest
+ *     child first, pruning with a margin, "ambiguous" rays re-walked in reference order -- equal those of the
+ *     reference-order walk;
+ *   - statistics: wide-node visits, triangle tests, stack depth, how many rays fall back.
+ *
+ * Arithmetic: include/pbr_pinned_math.h, -ffp-contract=off (the same contract as oracle/ and csrc/).
+ */
+#include <math.h>
+#include <stdint.h>
+#include <string.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "../include/pbr_pinned_math.h"
+#include "../physically-based-rendering_b200/csrc/wide_bvh.h"
+
+namespace {
+
+struct V3 { float x, y, z; };
+inline V3 sub(V3 a, V3 b) { return {a.x - b.x, a.y - b.y, a.z - b.z}; }
+inline V3 cross(V3 a, V3 b) { return {a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x}; }
+inline float dot(V3 a, V3 b) { return (a.x * b.x + a.y * b.y) + a.z * b.z; }
+
+const float EPS5 = 0.00001f;
+
+struct Scene {
+	const float* nodes; int numNodes;
+	const uint32_t* facesV; int numFaces;
+	const float* vertices;          /* float4 per vertex */
+};
+
+/* intersectBox (pt_intersect.cl:11-25) */
+bool intersectBox(V3 o, V3 inv, const float* lo, const float* hi, float& tNear, float& tFar) {
+	const float t1x = (lo[0] - o.x) * inv.x, t1y = (lo[1] - o.y) * inv.y, t1z = (lo[2] - o.z) * inv.z;
+	const float t2x = (hi[0] - o.x) * inv.x, t2y = (hi[1] - o.y) * inv.y, t2z = (hi[2] - o.z) * inv.z;
+	const float tMinX = fminf(t1x, t2x), tMinY = fminf(t1y, t2y), tMinZ = fminf(t1z, t2z);
+	const float tMaxX = fmaxf(t1x, t2x), tMaxY = fmaxf(t1y, t2y), tMaxZ = fmaxf(t1z, t2z);
+	tNear = fmaxf(fmaxf(tMinX, tMinY), tMinZ);
+	tFar = fminf(fminf(tMaxX, tMaxY), fminf(tMaxZ, INFINITY));
+	return tNear <= tFar;
+}
+
+/* flatTriAndRayIntersect (pt_intersect.cl:92-129): t of the face against a ray whose current ray.t is `rt`;
+ * INFINITY when rejected */
+float faceT(const Scene& S, int face, V3 o, V3 d, float tNear, float rt) {
+	const uint32_t* fv = S.facesV + 4 * (size_t) face;
+	const float* pa = S.vertices + 4 * (size_t) fv[0];
+	const float* pb = S.vertices + 4 * (size_t) fv[1];
+	const float* pc = S.vertices + 4 * (size_t) fv[2];
+	const V3 a = {pa[0], pa[1], pa[2]}, b = {pb[0], pb[1], pb[2]}, c = {pc[0], pc[1], pc[2]};
+	const float f = fmaxf(0.0f, tNear - 0.001f);
+	const V3 co = {fmaf(d.x, f, o.x), fmaf(d.y, f, o.y), fmaf(d.z, f, o.z)};
+	const V3 e1 = sub(b, a), e2 = sub(c, a), tv = sub(co, a);
+	const V3 pv = cross(d, e2), qv = cross(tv, e1);
+	const float invDet = pm::rcp(dot(e1, pv));
+	float t = dot(e2, qv) * invDet;
+	if (t >= rt || t < EPS5) return INFINITY;
+	const float u = dot(tv, pv) * invDet, v = dot(d, qv) * invDet;
+	if (u + v > 1.0f || fminf(u, v) < 0.0f) return INFINITY;
+	return t + f;
+}
+
+struct Hit { float t; int face; int leaf; uint32_t nodes, tris; };
+
+/* traverse (pt_bvh.cl:82-123), no lights */
+Hit strictWalk(const Scene& S, V3 o, V3 d, float rt0) {
+	Hit h = {rt0, 0, -1, 0, 0};
+	const V3 inv = {pm::rcp(d.x), pm::rcp(d.y), pm::rcp(d.z)};
+	int index = 1;
+	if (S.numNodes < 2) return h;
+	do {
+		h.nodes++;
+		const float* lo = S.nodes + 8 * (size_t) index;
+		const float* hi = lo + 4;
+		const int cur = index;
+		index = (lo[3] <= -1.0f) ? (int) hi[3] : cur + 1;
+		float tNear, tFar;
+		const bool hit = intersectBox(o, inv, lo, hi, tNear, tFar) && tFar > EPS5 && h.t > tNear;
+		if (!hit) continue;
+		index = cur + 1;
+		if (lo[3] >= 0.0f) {
+			const int f0 = (int) lo[3];
+			float t = faceT(S, f0, o, d, tNear, h.t);
+			h.tris++;
+			if (h.t > t) { h.t = t; h.face = f0; h.leaf = cur; }
+			if (hi[3] != -1.0f) {
+				const int f1 = (int) hi[3];
+				t = faceT(S, f1, o, d, tNear, h.t);
+				h.tris++;
+				if (h.t > t) { h.t = t; h.face = f1; h.leaf = cur; }
+			}
+		}
+	} while (index > 0 && index < S.numNodes);
+	return h;
+}
+
+struct FastStats { uint64_t wideVisits = 0, triTests = 0, fallbacks = 0, overflow = 0, insaneWinners = 0; int maxStack = 0; };
+
+inline float pruneLimit(float rt) { return rt + (0.0022f + 2e-6f * rt); }
+
+/* The ordered walk as the device runs it (csrc/pt_wide.cuh), one ray at a time: a work item is an inner node or a
+ * leaf; visiting an inner node tests its four child boxes, keeps the nearest child that is still in reach as the next
+ * item and pushes the others (leaves included) with their tNear; a leaf item tests its faces; an exhausted item pops
+ * the stack, skipping entries that have fallen out of reach. */
+Hit fastWalk(const Scene& S, const wbvh::Result& W, V3 o, V3 d, float rt0, int stackCap, FastStats& st) {
+	const V3 inv = {pm::rcp(d.x), pm::rcp(d.y), pm::rcp(d.z)};
+	float rt = rt0, bestTn = -INFINITY, t2 = rt0;
+	int face = 0, leaf = -1;
+	uint32_t nn = 0, nt = 0;
+	std::vector<std::pair<int, float>> stack;
+	bool overflow = false;
+	int item = 0;                       /* >= 0 inner node, < 0 leaf ref */
+	float itemTn = 0.0f;
+	bool have = !W.nodes.empty();
+	float lim = pruneLimit(rt);
+	auto pop = [&]() {
+		have = false;
+		while (!stack.empty()) {
+			const std::pair<int, float> e = stack.back();
+			stack.pop_back();
+			if (e.second <= lim) { item = e.first; itemTn = e.second; have = true; break; }
+		}
+	};
+	while (have && !overflow) {
+		if (item >= 0) {
+			nn++;
+			const wbvh::Node& N = W.nodes[(size_t) item];
+			int curRef = wbvh::REF_EMPTY;
+			float curTn = INFINITY;
+			for (int j = 0; j < 4; j++) {
+				const wbvh::Child& C = N.c[j];
+				float tNear, tFar;
+				const bool hit = intersectBox(o, inv, C.lo, C.hi, tNear, tFar) && tFar > EPS5 && C.ref != wbvh::REF_EMPTY;
+				if (!(hit && tNear <= lim && tNear < INFINITY)) continue;
+				int pushRef = C.ref;
+				float pushTn = tNear;
+				if (tNear < curTn) { pushRef = curRef; pushTn = curTn; curRef = C.ref; curTn = tNear; }
+				if (pushRef != wbvh::REF_EMPTY) {
+					if ((int) stack.size() >= stackCap) { overflow = true; break; }
+					stack.push_back({pushRef, pushTn});
+				}
+			}
+			st.maxStack = std::max(st.maxStack, (int) stack.size());
+			if (curRef != wbvh::REF_EMPTY) { item = curRef; itemTn = curTn; }
+			else pop();
+		}
+		else {
+			const int f0 = (int) ((uint32_t) item & wbvh::REF_FACE_MASK);
+			float tl = faceT(S, f0, o, d, itemTn, INFINITY);
+			int fl = f0;
+			nt++;
+			if ((uint32_t) item & wbvh::REF_TWO) {
+				const float t1 = faceT(S, f0 + 1, o, d, itemTn, INFINITY);
+				nt++;
+				if (t1 < tl) { tl = t1; fl = f0 + 1; }
+			}
+			if (tl < INFINITY) {
+				if (tl < rt || (tl == rt && leaf >= 0 && fl < face)) {
+					t2 = fminf(t2, rt);
+					rt = tl; face = fl; leaf = W.faceLeaf[(size_t) fl]; bestTn = itemTn;
+				}
+				else t2 = fminf(t2, tl);
+				lim = pruneLimit(rt);
+			}
+			pop();
+		}
+	}
+	st.wideVisits += nn; st.triTests += nt;
+	const bool insane = rt < bestTn;
+	if (insane) st.insaneWinners++;
+	if (overflow) st.overflow++;
+	if (overflow || (insane && t2 <= bestTn)) {
+		st.fallbacks++;
+		Hit h = strictWalk(S, o, d, rt0);
+		h.nodes += nn; h.tris += nt;
+		return h;
+	}
+	return {rt, face, leaf, nn, nt};
+}
+
+} /* namespace */
+
+extern "C" {
+
+/* rays: n x 8 floats (origin.xyz, -, dir.xyz, t0).  out: n x 4 int32 (t bits, face, leaf, -) for both walks.
+ * stats: wide nodes, wide depth, top count, leaf refs, inner refs, sum strict nodes, sum strict tris, sum wide visits,
+ *        sum fast tris, fallbacks, overflows, insane winners, max stack, mismatches.
+ * Returns 0, or 1 when the builder refused the tree (why -> msg). */
+int wide_model_run(const float* nodes, int numNodes, const uint32_t* facesV, int numFaces, const float* vertices,
+                   const float* rays, long long n, int stackCap, int topBudget,
+                   int32_t* outStrict, int32_t* outFast, long long* stats, char* msg, int msgLen) {
+	const wbvh::Result W = wbvh::build(nodes, numNodes, numFaces, topBudget);
+	if (!W.ok) {
+		if (msg && msgLen > 0) { strncpy(msg, W.why.c_str(), (size_t) msgLen - 1); msg[msgLen - 1] = 0; }
+		return 1;
+	}
+	const Scene S = {nodes, numNodes, facesV, numFaces, vertices};
+	FastStats st;
+	long long sn = 0, stt = 0, mism = 0;
+	for (long long i = 0; i < n; i++) {
+		const float* r = rays + 8 * i;
+		const V3 o = {r[0], r[1], r[2]}, d = {r[4], r[5], r[6]};
+		const Hit a = strictWalk(S, o, d, r[7]);
+		const Hit b = fastWalk(S, W, o, d, r[7], stackCap, st);
+		sn += a.nodes; stt += a.tris;
+		int32_t ta, tb;
+		memcpy(&ta, &a.t, 4); memcpy(&tb, &b.t, 4);
+		outStrict[4 * i] = ta; outStrict[4 * i + 1] = a.face; outStrict[4 * i + 2] = a.leaf; outStrict[4 * i + 3] = (int32_t) a.nodes;
+		outFast[4 * i] = tb; outFast[4 * i + 1] = b.face; outFast[4 * i + 2] = b.leaf; outFast[4 * i + 3] = (int32_t) b.nodes;
+		if (ta != tb || a.face != b.face || a.leaf != b.leaf) mism++;
+	}
+	stats[0] = (long long) W.nodes.size(); stats[1] = W.depth; stats[2] = W.topCount; stats[3] = W.leafRefs; stats[4] = W.innerRefs;
+	stats[5] = sn; stats[6] = stt; stats[7] = (long long) st.wideVisits; stats[8] = (long long) st.triTests;
+	stats[9] = (long long) st.fallbacks; stats[10] = (long long) st.overflow; stats[11] = (long long) st.insaneWinners;
+	stats[12] = st.maxStack; stats[13] = mism;
+	return 0;
+}
+
+}

@@ -146,6 +146,7 @@ int pbr_pipeline_in_use(pbr_ctx* ctx, int32_t* mode);
  * ping-pong between imageOut and a scratch image. */
 int pbr_kernel_launch_batch(pbr_ctx* ctx, pbr_kernel k, int32_t n_frames, const float* seeds, const float* pixel_weights);
 /* Scheduling knobs (never change a pixel): "node_phase_min", "refill_min" (reference-order traversal engine),
+ * "wide_node_phase_min", "wide_refill_min" (the same two thresholds for the ordered walk),
  * "traverse_blocks" / "wide_blocks" (cap on resident blocks per SM of the reference-order / ordered traversal kernels,
  * 0 = all that fit), "wide_top" (how many nodes of the top of the 4-wide BVH the ordered walk stages in shared memory;
  * the tree is renumbered at the next launch), "shadow_stage" (1: shadow rays are a wavefront stage of their own, walked

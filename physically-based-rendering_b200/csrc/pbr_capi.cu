@@ -109,7 +109,9 @@ struct pbr_ctx {
 	int* faceLeaf = nullptr;
 	size_t wideCap = 0, faceLeafCap = 0;       /* wide nodes / faces allocated */
 	int wideCount = 0, wideTop = 0, wideDepth = 0;
-	int wideTopBudget = 85;                    /* tuning "wide_top": nodes staged in shared memory (1 + 4 + 16 + 64) */
+	int wideTopBudget = 21;                    /* tuning "wide_top": nodes staged in shared memory (1 + 4 + 16: measured +0.8 %
+	                                              over none on C2; 85 costs occupancy and loses 0.6 %) */
+	int wideNodePhaseMin = 20, wideRefillMin = 8;   /* the engine's two thresholds as measured best for the ordered walk */
 	bool wideBuilt = false, wideOk = false;
 	std::string wideWhy;
 	uint64_t wideVersion = ~0ull;              /* geometryVersion the wide tree was built for */
@@ -391,8 +393,8 @@ void fillScene(pbr_ctx* ctx, SceneDev& S, bool useWide) {
 	S.wideTop = useWide ? ctx->wideTop : 0;
 	S.faceLeaf = useWide ? ctx->faceLeaf : nullptr;
 	S.numNodes = ctx->numNodesDev;
-	S.nodePhaseMin = ctx->nodePhaseMin;
-	S.refillMin = ctx->refillMin;
+	S.nodePhaseMin = useWide ? ctx->wideNodePhaseMin : ctx->nodePhaseMin;
+	S.refillMin = useWide ? ctx->wideRefillMin : ctx->refillMin;
 }
 
 template <typename K>
@@ -1147,6 +1149,8 @@ int pbr_set_tuning(pbr_ctx* ctx, const char* key, int32_t value) {
 	else if (k == "refill_min" && value >= 1 && value <= 32) ctx->refillMin = value;
 	else if (k == "traverse_blocks" && value >= 0 && value <= 32) ctx->traverseBlocks = value;
 	else if (k == "wide_blocks" && value >= 0 && value <= 32) ctx->wideBlocks = value;
+	else if (k == "wide_node_phase_min" && value >= 1 && value <= 32) ctx->wideNodePhaseMin = value;
+	else if (k == "wide_refill_min" && value >= 1 && value <= 32) ctx->wideRefillMin = value;
 	else if (k == "wide_top" && value >= 1 && value <= 1365) ctx->wideTopBudget = value;      /* rebuilt at the next launch */
 	else if (k == "shadow_stage" && (value == 0 || value == 1)) ctx->shadowStage = value;
 	else return fail(ctx, PBR_ERR_INVALID, "pbr_set_tuning: unknown key or value out of range: " + k);

@@ -90,7 +90,37 @@ struct WideLane {
 	bool overflow;
 };
 
-enum { WIDE_IDLE = 0, WIDE_NODE = 1, WIDE_LEAF = 2, WIDE_FINISHED = 3 };
+enum { WIDE_IDLE = 0, WIDE_POP = 1, WIDE_NODE = 2, WIDE_LEAF = 3, WIDE_FINISHED = 4 };
+
+/* intersectBox (pt_intersect.cl:11-25) on a child record (min.x, max.x, min.y, max.y, min.z, max.z): the same
+ * operations on the same operands in the same order -- (bound - o) * invDir, fmin / fmax per axis, max of the mins,
+ * min of the maxes -- with the two planes of an axis in one packed FADD2 / FMUL2 (IEEE round-to-nearest per half,
+ * so the bits are those of the scalar instructions). */
+__device__ __forceinline__ bool wideBoxTest(const vec3 o, const vec3 inv, const float4 a, const float4 b, float& tNear, float& tFar) {
+	float t1x, t2x, t1y, t2y, t1z, t2z;
+	asm("{\n\t.reg .b64 p, q, r;\n\t"
+	    "mov.b64 p, {%2, %3};\n\tmov.b64 q, {%4, %4};\n\tsub.rn.f32x2 r, p, q;\n\tmov.b64 q, {%5, %5};\n\tmul.rn.f32x2 r, r, q;\n\t"
+	    "mov.b64 {%0, %1}, r;\n\t}" : "=f"(t1x), "=f"(t2x) : "f"(a.x), "f"(a.y), "f"(o.x), "f"(inv.x));
+	asm("{\n\t.reg .b64 p, q, r;\n\t"
+	    "mov.b64 p, {%2, %3};\n\tmov.b64 q, {%4, %4};\n\tsub.rn.f32x2 r, p, q;\n\tmov.b64 q, {%5, %5};\n\tmul.rn.f32x2 r, r, q;\n\t"
+	    "mov.b64 {%0, %1}, r;\n\t}" : "=f"(t1y), "=f"(t2y) : "f"(a.z), "f"(a.w), "f"(o.y), "f"(inv.y));
+	asm("{\n\t.reg .b64 p, q, r;\n\t"
+	    "mov.b64 p, {%2, %3};\n\tmov.b64 q, {%4, %4};\n\tsub.rn.f32x2 r, p, q;\n\tmov.b64 q, {%5, %5};\n\tmul.rn.f32x2 r, r, q;\n\t"
+	    "mov.b64 {%0, %1}, r;\n\t}" : "=f"(t1z), "=f"(t2z) : "f"(b.x), "f"(b.y), "f"(o.z), "f"(inv.z));
+	const float tMinX = fminf(t1x, t2x), tMinY = fminf(t1y, t2y), tMinZ = fminf(t1z, t2z);
+	const float tMaxX = fmaxf(t1x, t2x), tMaxY = fmaxf(t1y, t2y), tMaxZ = fmaxf(t1z, t2z);
+	tNear = fmaxf(fmaxf(tMinX, tMinY), tMinZ);
+	tFar = fminf(fminf(tMaxX, tMaxY), fminf(tMaxZ, PM_INF_F));
+	return (tNear <= tFar);
+}
+
+/* compare-exchange of two (tNear, reference) pairs: the nearer one first, ties keep their order */
+__device__ __forceinline__ void wideOrder(float& ka, int& ra, float& kb, int& rb) {
+	const bool swap = kb < ka;
+	const float k0 = swap ? kb : ka, k1 = swap ? ka : kb;
+	const int r0 = swap ? rb : ra, r1 = swap ? ra : rb;
+	ka = k0; kb = k1; ra = r0; rb = r1;
+}
 
 template <bool ANY_HIT, typename RaySource, typename Counter>
 __device__ __forceinline__ void wideEngine(
@@ -108,20 +138,6 @@ __device__ __forceinline__ void wideEngine(
 	int state = WIDE_IDLE;
 	bool exhausted = false;
 	Counter slot = 0;
-
-	/* next item: the nearest stack entry still in reach, or the ray is done */
-	#define WIDE_POP() do { \
-		state = WIDE_FINISHED; \
-		while (L.sp > 0) { \
-			L.sp--; \
-			const uint2 e_ = (L.sp < PT_WIDE_STACK_SM) ? stackSm[L.sp * PT_WIDE_BLOCK] : stackLocal[L.sp - PT_WIDE_STACK_SM]; \
-			if (__uint_as_float(e_.y) <= L.lim) { \
-				L.item = (int) e_.x; L.itemTn = __uint_as_float(e_.y); \
-				state = (L.item >= 0) ? WIDE_NODE : WIDE_LEAF; \
-				break; \
-			} \
-		} \
-	} while (0)
 
 	while (true) {
 		/* ---- retire */
@@ -175,8 +191,20 @@ __device__ __forceinline__ void wideEngine(
 		}
 		if (__ballot_sync(FULL, state != WIDE_IDLE) == 0u) break;
 
-		/* ---- node phase: lanes whose item is an inner node visit it */
+		/* ---- node phase: lanes without an item take the nearest stack entry still in reach (one attempt per round),
+		 * lanes whose item is an inner node visit it */
 		while (true) {
+			if (state == WIDE_POP) {
+				if (L.sp == 0) state = WIDE_FINISHED;
+				else {
+					L.sp--;
+					const uint2 e = (L.sp < PT_WIDE_STACK_SM) ? stackSm[L.sp * PT_WIDE_BLOCK] : stackLocal[L.sp - PT_WIDE_STACK_SM];
+					if (__uint_as_float(e.y) <= L.lim) {
+						L.item = (int) e.x; L.itemTn = __uint_as_float(e.y);
+						state = (L.item >= 0) ? WIDE_NODE : WIDE_LEAF;
+					}
+				}
+			}
 			if (state == WIDE_NODE) {
 				L.nn++;
 				float4 a[4], b[4];
@@ -189,20 +217,37 @@ __device__ __forceinline__ void wideEngine(
 					#pragma unroll
 					for (int k = 0; k < 4; k++) loadNode(S.wide, L.item * 4 + k, a[k], b[k]);
 				}
-				int curRef = PT_WIDE_EMPTY;
-				float curTn = PM_INF_F;
+				/* the four children: entry distance if still in reach, else INFINITY (reference -> PT_WIDE_EMPTY) */
+				float key[4];
+				int ref[4];
 				#pragma unroll
 				for (int k = 0; k < 4; k++) {
-					const int ref = __float_as_int(b[k].z);
 					float tNear, tFar;
-					const float4 lo = make_float4(a[k].x, a[k].y, a[k].z, 0.0f), hi = make_float4(a[k].w, b[k].x, b[k].y, 0.0f);
-					const bool hit = intersectBox(L.o, L.inv, lo, hi, tNear, tFar) && tFar > PT_EPSILON5 && ref != PT_WIDE_EMPTY;
-					if (hit && tNear <= L.lim && tNear < PM_INF_F) {
-						int pushRef = ref;
-						float pushTn = tNear;
-						if (tNear < curTn) { pushRef = curRef; pushTn = curTn; curRef = ref; curTn = tNear; }
-						if (pushRef != PT_WIDE_EMPTY) {
-							const uint2 e = make_uint2((uint32_t) pushRef, __float_as_uint(pushTn));
+					const int r = __float_as_int(b[k].z);
+					const bool in = wideBoxTest(L.o, L.inv, a[k], b[k], tNear, tFar) && tFar > PT_EPSILON5 && r != PT_WIDE_EMPTY &&
+						tNear <= L.lim && tNear < PM_INF_F;
+					key[k] = in ? tNear : PM_INF_F;
+					ref[k] = in ? r : PT_WIDE_EMPTY;
+				}
+				/* nearest first (five compare-exchanges); the others go on the stack, farthest first */
+				wideOrder(key[0], ref[0], key[1], ref[1]);
+				wideOrder(key[2], ref[2], key[3], ref[3]);
+				wideOrder(key[0], ref[0], key[2], ref[2]);
+				wideOrder(key[1], ref[1], key[3], ref[3]);
+				wideOrder(key[1], ref[1], key[2], ref[2]);
+				const int n = (ref[0] != PT_WIDE_EMPTY) + (ref[1] != PT_WIDE_EMPTY) + (ref[2] != PT_WIDE_EMPTY) + (ref[3] != PT_WIDE_EMPTY);
+				if (L.sp + 3 <= PT_WIDE_STACK_SM) {
+					int at = L.sp;
+					if (n > 3) { stackSm[at * PT_WIDE_BLOCK] = make_uint2((uint32_t) ref[3], __float_as_uint(key[3])); at++; }
+					if (n > 2) { stackSm[at * PT_WIDE_BLOCK] = make_uint2((uint32_t) ref[2], __float_as_uint(key[2])); at++; }
+					if (n > 1) { stackSm[at * PT_WIDE_BLOCK] = make_uint2((uint32_t) ref[1], __float_as_uint(key[1])); at++; }
+					L.sp = at;
+				}
+				else {
+					#pragma unroll
+					for (int k = 3; k >= 1; k--) {
+						if (n > k) {
+							const uint2 e = make_uint2((uint32_t) ref[k], __float_as_uint(key[k]));
 							if (L.sp < PT_WIDE_STACK_SM) stackSm[L.sp * PT_WIDE_BLOCK] = e;
 							else if (L.sp < PT_WIDE_STACK_SM + PT_WIDE_STACK_LOCAL) stackLocal[L.sp - PT_WIDE_STACK_SM] = e;
 							else L.overflow = true;
@@ -210,14 +255,10 @@ __device__ __forceinline__ void wideEngine(
 						}
 					}
 				}
-				if (L.overflow) state = WIDE_FINISHED;                 /* (never on the scenes measured; the rewalk takes over) */
-				else if (curRef != PT_WIDE_EMPTY) {
-					L.item = curRef; L.itemTn = curTn;
-					state = (curRef >= 0) ? WIDE_NODE : WIDE_LEAF;
-				}
-				else WIDE_POP();
+				L.item = ref[0]; L.itemTn = key[0];
+				state = L.overflow ? WIDE_FINISHED : (n == 0 ? WIDE_POP : (ref[0] >= 0 ? WIDE_NODE : WIDE_LEAF));
 			}
-			if (__popc(__ballot_sync(FULL, state == WIDE_NODE)) < S.nodePhaseMin) break;
+			if (__popc(__ballot_sync(FULL, state == WIDE_NODE || state == WIDE_POP)) < S.nodePhaseMin) break;
 		}
 
 		/* ---- triangle phase: lanes whose item is a leaf test its faces (reference order inside the leaf) */
@@ -236,25 +277,21 @@ __device__ __forceinline__ void wideEngine(
 				L.nt++;
 				if (t1 < tl) { tl = t1; fl = f0 + 1; }
 			}
+			state = WIDE_POP;
 			if (ANY_HIT) {
 				/* occluded iff some candidate face is closer than the light (pt_bvh.cl:170-172) */
 				if (tl < L.tLight) { L.rt = tl; state = WIDE_FINISHED; }
-				else WIDE_POP();
 			}
-			else {
-				if (tl < PM_INF_F) {
-					if (tl < L.rt || (tl == L.rt && L.bestTn > -PM_INF_F && fl < L.hitFace)) {
-						L.t2 = fminf(L.t2, L.rt);
-						L.rt = tl; L.hitFace = fl; L.bestTn = L.itemTn;
-						L.lim = widePruneLimit(tl);
-					}
-					else L.t2 = fminf(L.t2, tl);
+			else if (tl < PM_INF_F) {
+				if (tl < L.rt || (tl == L.rt && L.bestTn > -PM_INF_F && fl < L.hitFace)) {
+					L.t2 = fminf(L.t2, L.rt);
+					L.rt = tl; L.hitFace = fl; L.bestTn = L.itemTn;
+					L.lim = widePruneLimit(tl);
 				}
-				WIDE_POP();
+				else L.t2 = fminf(L.t2, tl);
 			}
 		}
 	}
-	#undef WIDE_POP
 }
 
 /* Stage the top of the tree; every thread of the block must call. */

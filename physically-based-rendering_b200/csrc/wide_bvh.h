@@ -9,7 +9,8 @@
  * checks the properties the ordered walk relies on, and collapses it into nodes of up to four children:
  *
  *     Node  = 4 x Child, 128 bytes, one cache line
- *     Child = box min xyz, box max xyz (binary32, copied bit for bit from the reference node), ref, aux
+ *     Child = box as (min.x, max.x, min.y, max.y, min.z, max.z) -- binary32, copied bit for bit from the reference
+ *             node; min / max of an axis side by side so that one packed FADD2 / FMUL2 handles both slab planes --, ref, aux
  *             ref  >= 0          inner child: index of its Node
  *             ref  bit 31 set    leaf: bits 0..29 first face, bit 30 = the leaf has a second face (first + 1)
  *             ref  == REF_EMPTY  unused slot (box is NaN: never hit)
@@ -40,10 +41,11 @@
 namespace wbvh {
 
 struct Child {
-	float lo[3];
-	float hi[3];
+	float b[6];                   /* min.x, max.x, min.y, max.y, min.z, max.z */
 	int32_t ref;
 	int32_t aux;
+	float lo(int a) const { return b[2 * a]; }
+	float hi(int a) const { return b[2 * a + 1]; }
 };
 
 struct Node {
@@ -268,19 +270,14 @@ inline Result build(const float* src, int numNodes, int numFaces, int topBudget)
 		for (int k = 0; k < 4; k++) {
 			Child& C = N.c[k];
 			if (k >= T.n || T.kind[k] == 0) {
-				for (int a = 0; a < 3; a++) { C.lo[a] = nan; C.hi[a] = nan; }
+				for (int a = 0; a < 6; a++) C.b[a] = nan;
 				C.ref = REF_EMPTY;
 				C.aux = 0;
 				continue;
 			}
-			if (T.src[k] >= 0) {
-				memcpy(C.lo, B.lo(T.src[k]), 12);
-				memcpy(C.hi, B.hi(T.src[k]), 12);
-			}
-			else {
-				memcpy(C.lo, T.box[k], 12);
-				memcpy(C.hi, T.box[k] + 3, 12);
-			}
+			const float* blo = T.src[k] >= 0 ? B.lo(T.src[k]) : T.box[k];
+			const float* bhi = T.src[k] >= 0 ? B.hi(T.src[k]) : T.box[k] + 3;
+			for (int a = 0; a < 3; a++) { C.b[2 * a] = blo[a]; C.b[2 * a + 1] = bhi[a]; }
 			if (T.kind[k] == 1) {
 				const int r = T.src[k];
 				const uint32_t f0 = (uint32_t) (long long) B.lo(r)[3];

@@ -15,7 +15,8 @@ import pbr_b200  # noqa: E402,F401
 from pbr_b200 import host, scenes  # noqa: E402
 import helpers as Hh  # noqa: E402
 
-tops = [int(a) for a in sys.argv[1:]] or [85]
+# arguments: settings of the ordered walk to time, each "top,node_phase_min,refill_min" (default 21,20,8)
+settings = [tuple(int(x) for x in a.split(",")) for a in sys.argv[1:]] or [(21, 20, 8)]
 w = dict(bench.WORKLOADS["c2"])
 cfg = host.Config()
 bench.host_config(cfg, w)
@@ -78,9 +79,11 @@ def run(label):
 
 dev.setTraversal(0)
 run("reference")
-for top in tops:
+for top, npm, rm in settings:
     dev.setTuning("wide_top", top)
+    dev.setTuning("wide_node_phase_min", npm)
+    dev.setTuning("wide_refill_min", rm)
     dev.setTraversal(1)
-    run("ordered top=%d" % top)
+    run("ord %d/%d/%d" % (top, npm, rm))
 print(dev.traversalInfo())
 r.close()

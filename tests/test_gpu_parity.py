@@ -456,4 +456,4 @@ def test_ordered_walk_top_of_tree_budgets(device, oracle):
             assert np.array_equal(got["hitFace"], want["hitFace"]) and np.array_equal(got["leaf"], want["leaf"]), top
             assert np.array_equal(got["t"].view(np.uint32), want["t"].view(np.uint32)), top
     finally:
-        device.setTuning("wide_top", 85)
+        device.setTuning("wide_top", 21)

@@ -133,20 +133,26 @@ Hit fastWalk(const Scene& S, const wbvh::Result& W, V3 o, V3 d, float rt0, int s
 		if (item >= 0) {
 			nn++;
 			const wbvh::Node& N = W.nodes[(size_t) item];
-			int curRef = wbvh::REF_EMPTY;
-			float curTn = INFINITY;
+			/* the children still in reach, sorted by entry distance (ties: child order): the nearest is visited next,
+			 * the others are pushed farthest first */
+			int refs[4], n = 0;
+			float tns[4];
 			for (int j = 0; j < 4; j++) {
 				const wbvh::Child& C = N.c[j];
 				float tNear, tFar;
-				const bool hit = intersectBox(o, inv, C.lo, C.hi, tNear, tFar) && tFar > EPS5 && C.ref != wbvh::REF_EMPTY;
+				const float lo[3] = {C.lo(0), C.lo(1), C.lo(2)}, hi[3] = {C.hi(0), C.hi(1), C.hi(2)};
+				const bool hit = intersectBox(o, inv, lo, hi, tNear, tFar) && tFar > EPS5 && C.ref != wbvh::REF_EMPTY;
 				if (!(hit && tNear <= lim && tNear < INFINITY)) continue;
-				int pushRef = C.ref;
-				float pushTn = tNear;
-				if (tNear < curTn) { pushRef = curRef; pushTn = curTn; curRef = C.ref; curTn = tNear; }
-				if (pushRef != wbvh::REF_EMPTY) {
-					if ((int) stack.size() >= stackCap) { overflow = true; break; }
-					stack.push_back({pushRef, pushTn});
-				}
+				int k = n++;
+				while (k > 0 && tns[k - 1] > tNear) { tns[k] = tns[k - 1]; refs[k] = refs[k - 1]; k--; }
+				tns[k] = tNear; refs[k] = C.ref;
+			}
+			int curRef = wbvh::REF_EMPTY;
+			float curTn = INFINITY;
+			if (n > 0) { curRef = refs[0]; curTn = tns[0]; }
+			for (int k = n - 1; k >= 1; k--) {
+				if ((int) stack.size() >= stackCap) { overflow = true; break; }
+				stack.push_back({refs[k], tns[k]});
 			}
 			st.maxStack = std::max(st.maxStack, (int) stack.size());
 			if (curRef != wbvh::REF_EMPTY) { item = curRef; itemTn = curTn; }

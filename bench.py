@@ -16,15 +16,17 @@ Metric: Mrays/s = (calls of traverse() + traverseShadows()) / time, whole job ov
   e2e   : the same job through the host API a user of the reference calls (PathTracer::generateImage
           via libpbr_host.so): every frame the accumulated image is read back into pinned host memory,
           kernel arguments (seed, weight, camera) go host -> device.
-  N > 1 : samples are sharded -- every rank renders whole frames with its own seeds (weak scaling, N x
-          the samples per second) and ONE NCCL all-reduce per frame forms the displayed frame
-          (--shard tiles: rows are sharded instead, one all-gather per frame, strong scaling).
-Extra objects: roofline (dominant kernel = traverse: algorithmic bytes / its summed CUDA-event time,
-against the measured HBM peak), cpu_baseline (the CPU oracle on the host cores, bounded sample),
-clocks (sampled during the timed region).
+  N > 1 : PathTracer::setRanks -- samples are sharded, every rank renders whole frames with its own seeds
+          (weak scaling, N x the samples per second) and ONE NCCL all-reduce per frame, issued by the
+          library itself, forms the delivered frame.  `strong` adds the strong-scaling view: ONE image,
+          rows sharded in stripes, one all-gather per frame, against rank 0 rendering it alone.
+Extra objects: roofline (dominant kernel = traverse: the bytes it asks for / its summed CUDA-event time,
+against the measured HBM peak; ncu counters of the SAME build when committed), reference_walk (the step
+with the reference's visiting order), verify (N = 1: the GPU's frames against the CPU arm's, bit for bit),
+cpu_baseline (the reference's own kernel on the host cores, bounded sample), clocks.
 
---impl reference times the reference's own algorithm on the host CPU (the oracle port -- the
-reference itself cannot be built here: no OpenCL ICD, Boost, GLM, Qt) on the same workload.
+--impl reference times the reference's own kernel source (oracle/_ref: source/opencl/*.cl compiled for
+the host by oracle/build_ref.py; the restatement in oracle/ when that is missing) on all host cores.
 """
 import argparse
 import json
@@ -64,9 +66,12 @@ def parse_args():
     ap.add_argument("--spp", type=int)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--verify", action="store_true",
-                    help="N > 1, spp sharding: rank 0 re-renders every rank's frames alone and compares the mean with "
-                         "the combined image of the pipelined step")
+    ap.add_argument("--traversal", type=int, default=-1, choices=[-1, 0, 1],
+                    help="pbr_set_traversal: -1 automatic (the ordered walk, since no debug image is requested), 0 the "
+                         "reference's visiting order, 1 the ordered walk")
+    ap.add_argument("--no-reference-walk", action="store_true")
+    ap.add_argument("--no-strong", action="store_true")
+    ap.add_argument("--no-strong-c4", action="store_true")
     return ap.parse_args()
 
 
@@ -91,16 +96,6 @@ def measured_peak():
             return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     except Exception:
         return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
-
-
-def ncu_traffic():
-    """dram bytes per traverse launch from the committed ncu --set full summary, if there is one."""
-    path = os.path.join(ROOT, "profiles", "traverse_ncu_summary.json")
-    try:
-        with open(path) as fh:
-            return json.load(fh).get("dram_bytes_per_launch")
-    except Exception:
-        return None
 
 
 class ClockSampler(threading.Thread):
@@ -170,11 +165,46 @@ def host_config(cfg, w):
 
 # ------------------------------------------------------------------------------------------------ ours
 
+WALK_NAMES = {0: "reference-order walk (stackless pre-order, pt_bvh.cl:82-123)",
+              1: "ordered walk over the 4-wide BVH collapsed from the uploaded node array (same hits, same image bits)"}
+
+
+def ncu_summary(build_id):
+    """Counters of the dominant kernel from the committed `ncu --set full` summary -- only when it was taken of the
+    very build that is being timed (pbr_build_id)."""
+    path = os.path.join(ROOT, "profiles", "traverse_ncu_summary.json")
+    try:
+        with open(path) as fh:
+            doc = json.load(fh)
+    except Exception:
+        return None, "no profiles/traverse_ncu_summary.json"
+    if doc.get("build_id") != build_id:
+        return None, "profiles/traverse_ncu_summary.json is of build %s, this library is %s" % (doc.get("build_id"), build_id)
+    return doc, None
+
+
+def time_steps(torch, dist, world, step, steps, fence):
+    """K steps on the device: CUDA events on the stream the kernels run on, barrier + synchronize on both sides."""
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    start.record()
+    for _ in range(steps):
+        step()
+    fence()
+    end.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    return start.elapsed_time(end)
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
     import pbr_b200
-    from pbr_b200 import host, multigpu, scenes
+    from pbr_b200 import capi, host, scenes
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -184,123 +214,14 @@ def run_ours(args):
     torch.cuda.set_device(local_rank)
     dev_t = torch.device("cuda", local_rank)
     if world > 1:
+        # torch.distributed is plumbing here: barrier, max over ranks, handing the NCCL id around.  The per-frame
+        # collective on the image is the library's own (pbr_frame_combine inside PathTracer::setRanks).
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         os.environ.setdefault("MASTER_PORT", "29511")
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev_t)
     w = workload(args)
     W, H, SPP = w["width"], w["height"], w["spp"]
-
-    cfg = host.Config()
-    host_config(cfg, w)
-    scene = scenes.soup(w["tris"], seed=12345)
-    r = host.Renderer(local_rank)
-    t0 = time.perf_counter()
-    r.load_scene(scene)
-    load_s = time.perf_counter() - t0
-    info = r.info()
-    r.set_deterministic(True)
-    dev = r.device()
-    dev.setStream(torch.cuda.current_stream().cuda_stream)
-    dev.profileEnable(True)
-
     tiles = args.shard == "tiles" and world > 1
-    if world > 1 and not tiles:
-        r.set_seed_schedule(world, rank)
-    if tiles:
-        y0, y1 = multigpu.tile_rows(H, rank, world)
-        r.set_tile(y0, y1)
-
-    views = {}
-
-    def image_tensor():
-        _, hd = r.handles()
-        ptr, _ = dev.devicePtr(hd["image"])
-        if ptr not in views:
-            views[ptr] = multigpu.DeviceImage(ptr, H, W, dev_t).tensor
-        return views[ptr]
-
-    display = torch.empty((H, W, 4), dtype=torch.float32, device=dev_t) if world > 1 else None
-    # N > 1: the cross-rank combine of frame k (a copy + one collective) runs on its own stream while frame k+1
-    # is traced.  Frame k+1 only READS the image frame k wrote; frame k+2 overwrites it, so it waits for the
-    # combine of frame k (two events, by parity).
-    render_stream = torch.cuda.current_stream()
-    display_stream = torch.cuda.Stream() if world > 1 else None
-    combined = [None, None]
-    frame_no = [0]
-
-    def frame():
-        j = frame_no[0]
-        frame_no[0] += 1
-        if world > 1 and combined[j & 1] is not None:
-            render_stream.wait_event(combined[j & 1])
-        r.render_frames(1)
-        if world > 1:
-            img = image_tensor()
-            rendered = torch.cuda.Event()
-            rendered.record(render_stream)
-            with torch.cuda.stream(display_stream):
-                display_stream.wait_event(rendered)
-                if tiles:
-                    multigpu.combine_tiles(img, rank, world)
-                else:
-                    multigpu.combine_spp(img, world, out=display)
-                combined[j & 1] = torch.cuda.Event()
-                combined[j & 1].record(display_stream)
-            # (rows: the next frame only needs this rank's own rows of the previous image, which it wrote
-            #  itself; the gathered rows are for display)
-
-    def step_resident():
-        r.reset_sample_count()
-        if world == 1:
-            r.render_frames(SPP)         # one pbr_kernel_launch_batch call, the frames run back to back
-        else:
-            for _ in range(SPP):
-                frame()                  # every frame is combined across ranks (progressive display)
-            render_stream.wait_stream(display_stream)
-
-    pinned = torch.empty((H, W, 4), dtype=torch.float32).pin_memory()
-    pinned_np = pinned.numpy()
-    pinned2 = [pinned, torch.empty((H, W, 4), dtype=torch.float32).pin_memory()] if world > 1 and rank == 0 else None
-    landed = [None, None]
-    delivered = [0]
-
-    def step_e2e(last=False):
-        if world > 1:
-            r.reset_sample_count()
-        for i in range(SPP):
-            if world == 1:
-                # one generateImage() per frame, every frame read back into pinned memory; with render-ahead the
-                # next frame is traced while this one is copied.  The accumulation simply continues from step to
-                # step (no reset: a reset would discard the frame traced ahead), and the very last call of the
-                # run switches render-ahead off first, so no frame is traced that is not delivered.
-                if last and i == SPP - 1:
-                    r.set_render_ahead(False)
-                r.generate_image(out=pinned_np)
-            else:
-                frame()
-                if rank == 0:
-                    # one consumer of the displayed frame: rank 0's host.  The copy of frame j is enqueued behind its
-                    # combine; the host then waits for the copy of frame j - 1, so that it never stalls the launches
-                    # of the frame being traced (every frame is delivered, one frame later; two pinned buffers).
-                    j = delivered[0]
-                    delivered[0] += 1
-                    with torch.cuda.stream(display_stream):
-                        pinned2[j & 1].copy_(display if not tiles else image_tensor(), non_blocking=True)
-                        landed[j & 1] = torch.cuda.Event()
-                        landed[j & 1].record(display_stream)
-                    if tiles:
-                        combined[(frame_no[0] - 1) & 1] = landed[j & 1]   # the copy reads the image frame + 2 overwrites
-                    if landed[(j - 1) & 1] is not None:
-                        landed[(j - 1) & 1].synchronize()
-        if world > 1:
-            render_stream.wait_stream(display_stream)
-            if rank == 0:
-                display_stream.synchronize()                 # the last frame of the step has landed too
-
-    def sync_all():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
 
     def max_over_ranks(x):
         if world == 1:
@@ -311,48 +232,107 @@ def run_ours(args):
 
     def sum_over_ranks(a):
         if world == 1:
-            return a
+            return np.asarray(a, np.float64)
         t = torch.tensor(np.asarray(a, np.float64), device=dev_t)
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         return t.cpu().numpy()
 
+    def new_comm_id():
+        box = [host.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        return box[0]
+
+    def make_renderer(scene, sharding):
+        r = host.Renderer(local_rank)
+        t0 = time.perf_counter()
+        r.load_scene(scene)
+        load_s = time.perf_counter() - t0
+        r.set_deterministic(True)
+        r.set_traversal(args.traversal)
+        d = r.device()
+        d.setStream(torch.cuda.current_stream().cuda_stream)
+        d.profileEnable(True)
+        if world > 1:
+            r.set_ranks(rank, world, new_comm_id(), sharding)
+        return r, d, load_s
+
+    cfg = host.Config()
+    host_config(cfg, w)
+    scene = scenes.soup(w["tris"], seed=12345)
+    r, dev, load_s = make_renderer(scene, "stripes" if tiles else "spp")
+    info = r.info()
+
+    def step_resident():
+        r.reset_sample_count()
+        r.render_frames(SPP)             # N = 1: one pbr_kernel_launch_batch; N > 1: every frame ends with the collective
+
+    pinned = torch.empty((H, W, 4), dtype=torch.float32).pin_memory()
+    pinned_np = pinned.numpy()
+
+    def step_e2e(last=False):
+        # one generateImage() per frame, every frame read back into pinned host memory; with render-ahead the next
+        # frame is traced while this one is copied.  The accumulation simply continues from step to step (a reset would
+        # discard the frame traced ahead), and the very last call switches render-ahead off first, so that no frame is
+        # traced that is not delivered.  N > 1: rank 0's host is the one consumer of the combined frame.
+        for i in range(SPP):
+            if rank == 0:
+                if last and i == SPP - 1:
+                    r.set_render_ahead(False)
+                r.generate_image(out=pinned_np)
+            else:
+                r.render_frames(1)
+
     # ---- device-resident timing ----------------------------------------------------------------
     for _ in range(args.warmup):
         step_resident()
-    sync_all()
+    r.finish()
     dev.stats(reset=True)
     dev.profileRead(reset=True)
+    dev.traversalInfo(reset=True)
     sampler = ClockSampler(local_rank)
     sampler.start()
-    start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    sync_all()
-    start.record()
-    for _ in range(args.steps):
-        step_resident()
-    end.record()
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    ms_local = start.elapsed_time(end)
+    ms_local = time_steps(torch, dist, world, step_resident, args.steps, r.comm_fence)
     clocks = sampler.result()
     ms_total = max_over_ranks(ms_local)
     stats_local = dev.stats(reset=True).astype(np.float64)
     prof = dev.profileRead(reset=True)
+    tinfo = dev.traversalInfo(reset=True)
     stats_all = sum_over_ranks(stats_local)
     launches_all = float(sum_over_ranks(np.array([prof["launches"]], np.float64))[0])
     rays_all = stats_all[0] + stats_all[1]
     value = rays_all / (ms_total * 1e-3) / 1e6
     frames_all = args.steps * SPP * (1 if tiles else world)
     samples_per_s = frames_all * W * H / (ms_total * 1e-3)
+    walk = int(tinfo["last_used"])
+    pipeline = dev.pipelineInUse()
 
-    # roofline of the dominant kernel (this rank's traverse launches)
+    # ---- roofline of the dominant kernel (this rank's traverse launches) -------------------------
     peak, peak_src = measured_peak()
-    algo_bytes = ALGO_BYTES_PER_NODE * stats_local[2] + ALGO_BYTES_PER_TRI * stats_local[3]
+    if walk == 1:
+        kernel = "traverseWideKernel"
+        bytes_node, bytes_tri = 128, 36        # what the ordered walk asks for: one 128-byte wide node per visit, 36 B per face
+    else:
+        kernel = "traverseKernel"
+        bytes_node, bytes_tri = ALGO_BYTES_PER_NODE, ALGO_BYTES_PER_TRI
+    algo_bytes = bytes_node * stats_local[2] + bytes_tri * stats_local[3]
     trav_ms = prof["traverse_ms"]
     achieved = algo_bytes / (trav_ms * 1e-3) / 1e9 if trav_ms > 0 else 0.0
+    build = capi.build_id()
+    ncu, ncu_note = ncu_summary(build)
+    per_kernel = (ncu or {}).get("kernels", {}).get(kernel)
     roofline = {
-        "bound": "hbm", "kernel": "traverseKernel", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
-        "frac": round(achieved / peak, 4), "traffic": ncu_traffic(), "peak_source": peak_src,
+        "bound": "hbm", "bound_note": "nominally HBM (SURVEY.md 8d); in fact the walk is served from L1 / L2 and limited by the L1 "
+                 "load pipe (LSU wavefronts) and issue slots -- see traffic, l2_hit, lsu_wavefront_pct",
+        "kernel": kernel, "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
+        "frac": round(achieved / peak, 4), "peak_source": peak_src,
+        "traffic": per_kernel.get("dram_bytes_per_launch") if per_kernel else None,
+        "l1_hit": per_kernel.get("l1_hit_pct") if per_kernel else None,
+        "l2_hit": per_kernel.get("l2_hit_pct") if per_kernel else None,
+        "lsu_wavefront_pct": per_kernel.get("lsu_wavefront_pct") if per_kernel else None,
+        "issue_active_pct": per_kernel.get("issue_active_pct") if per_kernel else None,
+        "threads_per_inst": per_kernel.get("threads_per_inst") if per_kernel else None,
+        "ncu_build_id": (ncu or {}).get("build_id"), "ncu_note": ncu_note, "build_id": build,
+        "algorithmic_bytes": "%d B x node visits + %d B x triangle tests, both counted by the kernel" % (bytes_node, bytes_tri),
         "launches": int(prof["traverse_launches"]),
         "avg_launch_ms": round(trav_ms / max(1, prof["traverse_launches"]), 4),
         "algorithmic_bytes_per_launch": round(algo_bytes / max(1, prof["traverse_launches"])),
@@ -360,22 +340,51 @@ def run_ours(args):
         "shade_share_of_step": round(prof["shade_ms"] / ms_local, 4),
         "nodes_per_ray": round(stats_local[2] / max(1.0, stats_local[0]), 2),
         "tri_tests_per_ray": round(stats_local[3] / max(1.0, stats_local[0]), 2),
+        "rewalked_rays": int(tinfo["rewalked_rays"]),
     }
+
+    # ---- the same step with the reference-order walk (N = 1): what the ordered walk replaces ------
+    reference_walk = None
+    if world == 1 and walk == 1 and not args.no_reference_walk:
+        r.set_traversal(0)
+        for _ in range(2):
+            step_resident()
+        r.finish()
+        dev.stats(reset=True)
+        dev.profileRead(reset=True)
+        k = max(3, args.steps // 4)
+        ms_ref = time_steps(torch, dist, world, step_resident, k, r.comm_fence)
+        st = dev.stats(reset=True).astype(np.float64)
+        pr = dev.profileRead(reset=True)
+        ref_bytes = ALGO_BYTES_PER_NODE * st[2] + ALGO_BYTES_PER_TRI * st[3]
+        reference_walk = {
+            "value": round((st[0] + st[1]) / (ms_ref * 1e-3) / 1e6, 2), "unit": "Mrays/s", "ms_per_step": round(ms_ref / k, 3),
+            "steps": k, "kernel": "traverseKernel", "nodes_per_ray": round(st[2] / max(1.0, st[0]), 2),
+            "tri_tests_per_ray": round(st[3] / max(1.0, st[0]), 2),
+            "algorithmic_gbs": round(ref_bytes / (pr["traverse_ms"] * 1e-3) / 1e9, 1),
+            "frac_of_peak": round(ref_bytes / (pr["traverse_ms"] * 1e-3) / 1e9 / peak, 4),
+            "what": "pbr_set_traversal(0): visit counters and debug image bit-exact as well; 32 B x nodes + 64 B x triangle tests "
+                    "(SURVEY.md 8d) over the summed traverse time",
+        }
+        r.set_traversal(args.traversal)
 
     # ---- end to end through the host API ---------------------------------------------------------
     e2e = None
     if not args.no_e2e:
-        if world == 1:
-            r.reset_sample_count()
+        r.reset_sample_count()
+        r.set_render_ahead(True)
         for i in range(max(1, args.warmup // 2)):
             step_e2e(last=True)
-        sync_all()
+        r.finish()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
         dev.stats(reset=True)
-        if world == 1:
-            r.set_render_ahead(True)
+        r.set_render_ahead(True)
         t0 = time.perf_counter()
         for i in range(args.steps):
             step_e2e(last=(i == args.steps - 1))
+        r.finish()
         torch.cuda.synchronize()
         e2e_s = max_over_ranks(time.perf_counter() - t0)
         e_stats = sum_over_ranks(dev.stats(reset=True).astype(np.float64))
@@ -385,70 +394,53 @@ def run_ours(args):
             "d2h_bytes_per_step": SPP * W * H * 16,            # accumulated frame per frame (N > 1: rank 0 reads it)
             "ms_per_step": round(e2e_s * 1e3 / args.steps, 3),
             "api": "PathTracer::generateImage (libpbr_host.so) per frame, every frame into a pinned host image, "
-                   "setRenderAhead(true): the next frame is traced while this one is copied" if world == 1 else
-                   "PathTracer::renderFrames(1) per rank + combine on a side stream; rank 0 reads every combined "
-                   "frame into pinned host memory (double-buffered: it waits for frame j - 1 while frame j + 1 is traced)",
+                   "setRenderAhead(true): the next frame is traced while this one is copied" + (
+                       "; N > 1: PathTracer::setRanks, every frame ends with the library's own collective, rank 0's host "
+                       "receives every combined frame" if world > 1 else ""),
         }
+        r.set_render_ahead(False)
 
-    # ---- optional: is the pipelined multi-GPU image the right one? ---------------------------------
-    verify = None
-    if args.verify and world > 1 and tiles:
-        step_resident()
-        sync_all()
-        if rank == 0:
-            shown = image_tensor().clone()
-            r.set_tile(0, H)
-            r.reset_sample_count()
-            r.render_frames(SPP)
-            torch.cuda.synchronize()
-            want = image_tensor()
-            same = (shown == want) | (torch.isnan(shown) & torch.isnan(want))
-            verify = {"bit_identical_pixels": int(same.all(dim=2).sum()), "pixels": W * H,
-                      "what": "all-gathered image of one pipelined step vs the same frames rendered whole on rank 0"}
-            y0, y1 = multigpu.tile_rows(H, rank, world)
-            r.set_tile(y0, y1)
-        sync_all()
-    if args.verify and world > 1 and not tiles:
-        step_resident()
-        sync_all()
-        if rank == 0:
-            shown = display.clone()
-            acc = torch.zeros_like(shown, dtype=torch.float64)
-            for rr in range(world):
-                r.set_seed_schedule(world, rr)
-                r.reset_sample_count()
-                r.render_frames(SPP)
-                torch.cuda.synchronize()
-                acc += image_tensor().double()
-            r.set_seed_schedule(world, rank)
-            want = (acc / world)[..., :3]
-            got = shown[..., :3].double()
-            ok = torch.isfinite(want) & torch.isfinite(got)
-            diff = (want - got).abs()[ok]
-            verify = {"max_abs_diff": float(diff.max()), "mean": float(want[ok].mean()),
-                      "pixels_compared": int(ok.all(dim=2).sum()), "what": "combined image of one pipelined step vs "
-                      "the mean of all ranks' accumulations re-rendered on rank 0"}
-        sync_all()
+    # ---- strong scaling of ONE image (N > 1): rows of every frame sharded in interleaved stripes ----
+    strong = None
+    if world > 1 and not args.no_strong:
+        strong = {}
+        try:
+            strong["c2"] = strong_scaling(torch, dist, world, rank, r, dev, W, H, SPP, max(3, args.steps // 2), max_over_ranks,
+                                          sum_over_ranks, w["name"], already_stripes=tiles)
+            if not args.no_strong_c4 and not w["reduced"]:
+                r.close()
+                r = None
+                c4 = dict(width=3840, height=2160, spp=8)
+                cfg.reset()
+                cfg.update({"window.width": c4["width"], "window.height": c4["height"], "render.max_depth": 3, "logging.level": 1,
+                            "camera.eye.x": 0.0, "camera.eye.y": 1.2, "camera.eye.z": 1.8,
+                            "camera.center.x": 0.0, "camera.center.y": 0.55, "camera.center.z": 1.0})
+                grid = scenes.displaced_grid(2237, 2236, patches=8)
+                r, dev, _ = make_renderer(grid, "stripes")
+                strong["c4"] = strong_scaling(torch, dist, world, rank, r, dev, c4["width"], c4["height"], c4["spp"], 3, max_over_ranks,
+                                              sum_over_ranks, "C4 displaced-grid-10M-tris 3840x2160 %dspp" % c4["spp"], already_stripes=True)
+        except Exception as e:          # the headline line must not die with an optional measurement
+            strong["error"] = repr(e)
 
-    # ---- CPU baseline (rank 0, N = 1 only) ---------------------------------------------------------
+    # ---- CPU baseline + parity at the bench configuration (rank 0, N = 1 only) ---------------------
     cpu_baseline = None
+    verify = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu_baseline, cpu_frames, cpu_image = cpu_baseline_sample(w, r.flat(), scene)
         # parity at the bench configuration itself: the frames the CPU arm has just rendered with the reference
         # kernel (same seeds, same accumulation from a black image) against the same frames on the GPU, bit for bit
-        r.set_render_ahead(False)
-        r.reset_sample_count()
-        r.render_frames(cpu_frames)
-        gpu_image = r.read_image()
         sys.path.insert(0, os.path.join(ROOT, "tests"))
         import helpers as Hh
-        verify = {
-            "frames": cpu_frames, "pixels": W * H,
-            "bit_identical_pixels": Hh.count_identical_pixels(gpu_image, cpu_image),
-            "mre": Hh.mean_relative_error(gpu_image, cpu_image),
-            "what": "accumulated image after %d frame(s): GPU (%s) vs the CPU arm's %s kernel, all four channels" % (
-                cpu_frames, "reference-order walk", cpu_baseline["kind"]),
-        }
+        verify = {"frames": cpu_frames, "pixels": W * H, "against": "the CPU arm's %s kernel, all four channels" % cpu_baseline["kind"]}
+        for mode, name in ((args.traversal, "as_timed"), (0, "reference_order_walk")):
+            r.set_traversal(mode)
+            r.reset_sample_count()
+            r.render_frames(cpu_frames)
+            gpu_image = r.read_image()
+            verify[name] = {"bit_identical_pixels": Hh.count_identical_pixels(gpu_image, cpu_image),
+                            "mre": Hh.mean_relative_error(gpu_image, cpu_image),
+                            "walk": WALK_NAMES[int(dev.traversalInfo()["last_used"])]}
+        r.set_traversal(args.traversal)
 
     if rank == 0:
         line = {
@@ -458,22 +450,69 @@ def run_ours(args):
             "config": {
                 "workload": w["name"], "triangles": w["tris"], "width": W, "height": H, "spp_per_step": SPP,
                 "frames_per_step_per_rank": SPP, "max_depth": 3, "max_added_depth": 5, "brdf": 1,
-                "sharding": ("tiles+allgather" if tiles else "spp+allreduce") if world > 1 else "none",
+                "sharding": ("stripes+allgather" if tiles else "spp+allreduce") + " inside libpbr_b200.so (PathTracer::setRanks)"
+                if world > 1 else "none",
                 "bvh_nodes": info["emitted_nodes"], "bvh_build_s": round(info["bvh_build_seconds"], 2),
                 "scene_load_s": round(load_s, 2),
-                "pipeline": {0: "wavefront", 1: "megakernel", 2: "persistent", 3: "carry-over", -1: "undecided"}[dev.pipelineInUse()] +
-                       " (chosen by measurement on the first frames)",
-                       "l2_policy": "working set > L2: nodes+tris %.0f MB, path state %.0f MB, images %.0f MB" % (
-                    (info["emitted_nodes"] * 32 + info["faces"] * 36) / 1e6, W * H * 104 / 1e6, W * H * 48 / 1e6),
+                "traversal": WALK_NAMES[walk] + ("; chosen automatically: no debug image is requested" if args.traversal < 0 else "; forced"),
+                "wide_bvh": {"nodes": tinfo["wide_nodes"], "depth": tinfo["wide_depth"], "staged_in_shared_memory": tinfo["wide_top"],
+                             "build_ms": round(tinfo["wide_build_ms"], 1)} if walk == 1 else None,
+                "pipeline": {0: "wavefront", 1: "megakernel", -1: "wavefront (batched frames)"}[pipeline] +
+                            " (chosen by measurement on the first frames)",
+                "l2_policy": "working set > L2: scene %.0f MB (wide nodes + triangles%s), path state %.0f MB, images %.0f MB" % (
+                    (tinfo["wide_nodes"] * 128 + info["faces"] * 36) / 1e6 if walk == 1 else (info["emitted_nodes"] * 32 + info["faces"] * 36) / 1e6,
+                    "" if walk == 1 else "; reference nodes", W * H * 104 / 1e6, W * H * 48 / 1e6),
             },
             "samples_per_s": round(samples_per_s), "rays_per_step": round(rays_all / args.steps),
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches_all), "verify": verify,
-            "roofline": roofline, "cpu_baseline": cpu_baseline,
+            "roofline": roofline, "reference_walk": reference_walk, "strong": strong, "cpu_baseline": cpu_baseline,
         }
         print(json.dumps(line), flush=True)
-    r.close()
+    if r is not None:
+        r.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+def strong_scaling(torch, dist, world, rank, r, dev, W, H, spp, steps, max_over_ranks, sum_over_ranks, name, already_stripes):
+    """ONE image rendered by all ranks together: every frame's rows sharded in interleaved stripes, completed with one
+    all-gather per frame (bit-identical to one GPU) -- against the same frames rendered by rank 0 alone."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import helpers as Hh
+    sharding = "stripes" if H % world == 0 else "rows"
+    if not already_stripes:
+        r.set_sharding(sharding)
+
+    def step():
+        r.reset_sample_count()
+        r.render_frames(spp)
+
+    for _ in range(2):
+        step()
+    r.finish()
+    dev.stats(reset=True)
+    ms = max_over_ranks(time_steps(torch, dist, world, step, steps, r.comm_fence))
+    st = sum_over_ranks(dev.stats(reset=True).astype(np.float64))
+    r.finish()
+    shown = r.read_image() if rank == 0 else None
+    dist.barrier()
+    # the same job on one GPU (rank 0 alone; the others wait)
+    out = {"workload": name, "sharding": sharding + " + one all-gather per frame (pbr_frame_combine)", "steps": steps,
+           "ms_per_step": round(ms / steps, 3), "value": round((st[0] + st[1]) / (ms * 1e-3) / 1e6, 2), "unit": "Mrays/s"}
+    r.set_sharding("none")
+    if rank == 0:
+        for _ in range(2):
+            step()
+        r.finish()
+        ms1 = time_steps(torch, None, 1, step, steps, lambda: None)
+        whole = r.read_image()
+        out.update({
+            "one_gpu_ms_per_step": round(ms1 / steps, 3), "speedup": round(ms1 / ms, 3), "efficiency": round(ms1 / ms / world, 4),
+            "bit_identical_pixels": Hh.count_identical_pixels(shown, whole), "pixels": W * H,
+        })
+    dist.barrier()
+    r.set_sharding(sharding)
+    return out
 
 
 def _c2_defines(w, num_nodes, sky):

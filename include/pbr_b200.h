@@ -43,6 +43,7 @@ typedef uint64_t pbr_kernel;   /* stands in for cl_kernel */
 #define PBR_ERR_NO_DEVICE 10002    /* no usable CUDA device          (CL_DEVICE_NOT_FOUND)     */
 #define PBR_ERR_NOT_READY 10003    /* launch before program/args set (CL_INVALID_KERNEL_ARGS)  */
 #define PBR_ERR_UNSUPPORTED 10004  /* define / kernel name not known (CL_INVALID_KERNEL_NAME)  */
+#define PBR_ERR_NCCL_BASE 20000    /* + ncclResult_t of a failed NCCL call                     */
 
 /* ---- context ------------------------------------------------------------------------------- */
 
@@ -53,6 +54,9 @@ int pbr_create(int device, pbr_ctx** out);
 int pbr_destroy(pbr_ctx* ctx);
 const char* pbr_last_error(pbr_ctx* ctx);
 /* Device name and SM count (CL::getDefaultDevice debug dump, CL.cpp:377-419). */
+/* Twelve hex digits identifying the sources this library was built from (sha1 over the .cu / .cuh / .h files of csrc and the public
+ * headers).  Profiles under profiles/ record it; bench.py only quotes counters of the build it is timing. */
+const char* pbr_build_id(void);
 int pbr_device_info(pbr_ctx* ctx, char* name, size_t name_len, int* sm_count, size_t* total_mem);
 
 /* ---- buffers and images -------------------------------------------------------------------- */
@@ -186,6 +190,34 @@ int pbr_traversal_info(pbr_ctx* ctx, pbr_traversal_info_t* out, int32_t reset);
  *   [3] triangle tests    [4] shaded hits              [5] BVH nodes visited by traverseShadows()
  * These are the inputs of the algorithmic-byte formula of SURVEY.md 8d. */
 int pbr_stats(pbr_ctx* ctx, uint64_t out[6], int32_t reset);
+
+/* ---- multi-GPU: one process (one pbr_ctx) per GPU, the scene replicated, ONE NCCL collective per frame on the float
+ * accumulation buffer.  Replaces the reference's single-device assumption (CL.cpp:355, 470, 521: first
+ * platform, first GPU, one queue).  libnccl.so.2 is loaded by pbr_comm_init; a single GPU needs no NCCL at all.
+ *   rank 0:      pbr_comm_unique_id(id)  -> hand the 128 bytes to the other ranks (file, pipe, MPI, torch.distributed ...)
+ *   every rank:  pbr_comm_init(ctx, id, rank, world)
+ *   per frame:   pbr_kernel_launch(...); pbr_frame_combine(ctx, imageOut, mode, display)
+ * pbr_frame_combine returns at once: the collective runs on the communicator's own stream behind the frame just launched,
+ * while the next frame is traced.  The library orders what has to be ordered: a later launch that overwrites an image a
+ * combine still uses (PathTracer's ping-pong pair: frame k + 2 and the combine of frame k), and pbr_image_read /
+ * pbr_image_read_begin of such an image, wait for it on the device.
+ *   PBR_COMBINE_SPP   every rank rendered whole frames with its own seeds: out = sum over ranks of image / world (one
+ *                     scale-and-copy pass + ncclAllReduce); `image` keeps accumulating untouched.  Not bit-identical to
+ *                     one GPU rendering the same frames (summation order): tolerance, see tests.
+ *   PBR_COMBINE_ROWS  every rank rendered its rows (pbr_set_tile with the block pbr_tile_rows gives it, or
+ *                     pbr_set_tile_stripes): the other ranks' rows are gathered into `image` in place (ncclAllGather; grouped
+ *                     ncclBroadcast for unequal blocks; pack + all-gather + unpack for stripes).  Bit-identical to one GPU. */
+#define PBR_COMBINE_SPP 0
+#define PBR_COMBINE_ROWS 1
+int pbr_comm_unique_id(void* id128);
+int pbr_comm_init(pbr_ctx* ctx, const void* id128, int32_t rank, int32_t world);
+int pbr_comm_info(pbr_ctx* ctx, int32_t* rank, int32_t* world, int32_t* nccl_version);
+int pbr_comm_destroy(pbr_ctx* ctx);
+int pbr_frame_combine(pbr_ctx* ctx, pbr_mem image, int32_t mode, pbr_mem out);
+/* Make the render stream wait (on the device) for every combine enqueued so far. */
+int pbr_comm_fence(pbr_ctx* ctx);
+/* Rows [y0, y1) of rank `rank` of `world`: contiguous blocks of multiples of 4 rows covering [0, height). */
+int pbr_tile_rows(int32_t height, int32_t rank, int32_t world, int32_t* y0, int32_t* y1);
 
 /* Issue all device work of this context on a caller-owned CUDA stream (a cudaStream_t passed as
  * void*, e.g. torch.cuda.current_stream().cuda_stream; 0 is the legacy default stream) so that the

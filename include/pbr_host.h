@@ -81,6 +81,19 @@ int pbrh_renderer_set_render_ahead(pbrh_renderer* r, int32_t enabled);
 int pbrh_renderer_set_tile(pbrh_renderer* r, int32_t y0, int32_t y1);
 /* interleaved stripes of rows for load balance (pbr_set_tile_stripes); stripe_rows <= 0 = off */
 int pbrh_renderer_set_tile_stripes(pbrh_renderer* r, int32_t stripe_rows, int32_t world, int32_t rank);
+/* Multi-GPU, one process per GPU (PathTracer::setRanks; replaces the single-device assumption of CL.cpp:355,470,521).
+ * Rank 0 calls pbrh_comm_unique_id and hands the 128 bytes to the others by any means; every rank then calls
+ * pbrh_renderer_set_ranks after loading the scene.  sharding: 0 samples (own seeds per rank, delivered frame = mean over
+ * ranks), 1 contiguous row blocks, 2 interleaved stripes of rows.  From then on every frame ends with ONE NCCL collective
+ * inside the library, overlapped with the next frame. */
+int pbrh_comm_unique_id(void* id128);
+int pbrh_renderer_set_ranks(pbrh_renderer* r, int32_t rank, int32_t world, const void* id128, int32_t sharding);
+/* another sharding on the same communicator (restarts the accumulation); 3 = none: this rank renders whole frames alone */
+int pbrh_renderer_set_sharding(pbrh_renderer* r, int32_t sharding);
+/* the render stream waits, on the device, for every collective enqueued so far (for device-side timing) */
+int pbrh_renderer_comm_fence(pbrh_renderer* r);
+/* -1 automatic, 0 the reference's visiting order, 1 the ordered walk over the 4-wide BVH (pbr_set_traversal) */
+int pbrh_renderer_set_traversal(pbrh_renderer* r, int32_t mode);
 /* PathTracer::generateImage: one frame, accumulated image into out[W*H*4]; debug may be NULL */
 int pbrh_renderer_generate_image(pbrh_renderer* r, float* out, float* debug);
 /* n frames resident on the device, nothing read back */

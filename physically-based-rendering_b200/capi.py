@@ -15,7 +15,7 @@ LIB_PATH = os.path.join(_HERE, "csrc", "libpbr_b200.so")
 
 # Every symbol include/pbr_b200.h declares (checked by tests/test_capi_symbols.py).
 SYMBOLS = [
-    "pbr_create", "pbr_destroy", "pbr_last_error", "pbr_device_info",
+    "pbr_create", "pbr_destroy", "pbr_last_error", "pbr_build_id", "pbr_device_info",
     "pbr_buffer_create", "pbr_buffer_create_empty", "pbr_buffer_update", "pbr_buffer_read",
     "pbr_image_create", "pbr_image_write", "pbr_image_read", "pbr_image_copy", "pbr_mem_device_ptr",
     "pbr_free_buffers", "pbr_host_alloc", "pbr_host_free",
@@ -23,6 +23,7 @@ SYMBOLS = [
     "pbr_finish", "pbr_kernel_time_ms",
     "pbr_image_read_begin", "pbr_image_read_end", "pbr_set_tile", "pbr_set_tile_stripes", "pbr_set_pipeline", "pbr_pipeline_in_use", "pbr_set_tuning", "pbr_kernel_launch_batch", "pbr_set_debug_image", "pbr_stats",
     "pbr_set_traversal", "pbr_traversal_info",
+    "pbr_comm_unique_id", "pbr_comm_init", "pbr_comm_info", "pbr_comm_destroy", "pbr_frame_combine", "pbr_comm_fence", "pbr_tile_rows",
     "pbr_trace", "pbr_trace_device", "pbr_pinned_math_eval",
     "pbr_set_stream", "pbr_profile_enable", "pbr_profile_read",
 ]
@@ -100,6 +101,13 @@ def load_library():
         "pbr_stats": [vp, vp, i32],
         "pbr_set_traversal": [vp, i32],
         "pbr_traversal_info": [vp, vp, i32],
+        "pbr_comm_unique_id": [vp],
+        "pbr_comm_init": [vp, vp, i32, i32],
+        "pbr_comm_info": [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)],
+        "pbr_comm_destroy": [vp],
+        "pbr_frame_combine": [vp, u64, i32, u64],
+        "pbr_comm_fence": [vp],
+        "pbr_tile_rows": [i32, i32, i32, C.POINTER(i32), C.POINTER(i32)],
         "pbr_trace": [vp, u64, u64, u64, u64, i32, vp, i64, i32, vp],
         "pbr_trace_device": [vp, u64, u64, u64, u64, i32, u64, i64, i32, u64],
         "pbr_pinned_math_eval": [vp, i32, vp, vp, i64, vp],
@@ -113,8 +121,15 @@ def load_library():
         f.restype = C.c_int
     lib.pbr_last_error.argtypes = [vp]
     lib.pbr_last_error.restype = C.c_char_p
+    lib.pbr_build_id.argtypes = []
+    lib.pbr_build_id.restype = C.c_char_p
     _lib = lib
     return lib
+
+
+def build_id():
+    """pbr_build_id(): which sources the loaded libpbr_b200.so was built from."""
+    return load_library().pbr_build_id().decode()
 
 
 def _p(a):
@@ -277,6 +292,42 @@ class Device:
         out = np.zeros(6, np.uint64)
         self._ck(self.lib.pbr_stats(self.ctx, _p(out), int(reset)), "pbr_stats")
         return out
+
+    # ---- multi-GPU (one pbr_ctx per process and GPU) -------------------------------------------
+    @staticmethod
+    def commUniqueId():
+        buf = (C.c_char * 128)()
+        rc = load_library().pbr_comm_unique_id(buf)
+        if rc != 0:
+            raise PbrError("pbr_comm_unique_id failed (%d): libnccl.so.2 not loadable?" % rc)
+        return bytes(buf)
+
+    def commInit(self, nccl_id, rank, world):
+        buf = (C.c_char * 128).from_buffer_copy(bytes(nccl_id))
+        self._ck(self.lib.pbr_comm_init(self.ctx, buf, rank, world), "pbr_comm_init")
+
+    def commInfo(self):
+        r, w, v = C.c_int32(), C.c_int32(), C.c_int32()
+        self._ck(self.lib.pbr_comm_info(self.ctx, C.byref(r), C.byref(w), C.byref(v)), "pbr_comm_info")
+        return r.value, w.value, v.value
+
+    def commDestroy(self):
+        self._ck(self.lib.pbr_comm_destroy(self.ctx), "pbr_comm_destroy")
+
+    def frameCombine(self, image, mode, out=0):
+        """mode: 0 samples (out = mean over ranks of image), 1 rows (the other ranks' rows gathered into image)."""
+        self._ck(self.lib.pbr_frame_combine(self.ctx, image, mode, out), "pbr_frame_combine")
+
+    def commFence(self):
+        self._ck(self.lib.pbr_comm_fence(self.ctx), "pbr_comm_fence")
+
+    @staticmethod
+    def tileRows(height, rank, world):
+        y0, y1 = C.c_int32(), C.c_int32()
+        rc = load_library().pbr_tile_rows(height, rank, world, C.byref(y0), C.byref(y1))
+        if rc != 0:
+            raise PbrError("pbr_tile_rows: bad arguments")
+        return y0.value, y1.value
 
     def setTraversal(self, mode):
         """-1 automatic (default), 0 the reference's visiting order, 1 the ordered walk over the 4-wide BVH."""

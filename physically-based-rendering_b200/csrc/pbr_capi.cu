@@ -7,6 +7,8 @@
  * argument slots (PathTracer.cpp:88-125).  No CPU fallback: every entry point needs a CUDA device.
  */
 #include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>                 /* types only: the library is dlopen'ed by pbr_comm_init, so one GPU needs no NCCL */
 #include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -33,6 +35,8 @@ struct Mem {
 	size_t width = 0, height = 0;
 	bool alive = false;
 	uint64_t epoch = 0;               /* bumped whenever the contents may have changed (create, update, free) */
+	cudaEvent_t evCombined = nullptr; /* pbr_frame_combine still reads (or all-gathers into) this image until then */
+	bool combinePending = false;
 };
 
 struct KernelArgs {
@@ -142,6 +146,16 @@ struct pbr_ctx {
 	int refillMin = 4;                         /* PBR_REFILL_MIN overrides (tuning) */
 	unsigned long long* stats = nullptr;       /* 8 counters: the six of pbr_stats, re-walked rays, rays of the ordered walk */
 	unsigned long long* cursor64 = nullptr;    /* work cursor of traceRaysKernel */
+
+	/* multi-GPU (pbr_comm_init): one process per GPU, one NCCL collective per frame on a stream of its own */
+	ncclComm_t comm = nullptr;
+	int commRank = 0, commWorld = 1;
+	cudaStream_t commStream = nullptr;
+	cudaEvent_t evRendered = nullptr;
+	float4* commSend = nullptr;
+	float4* commRecv = nullptr;
+	size_t commSendCap = 0, commRecvCap = 0;   /* float4s */
+	uint64_t combines = 0;
 };
 
 namespace {
@@ -581,6 +595,101 @@ int runFrame(pbr_ctx* ctx, const FrameParams& P, int nPaths) {
 	return runWavefront<BRDF, SHADOW, PHONG>(ctx, P, W, nPaths);
 }
 
+/* ---- NCCL, loaded on demand ---------------------------------------------------------------------------- */
+
+struct NcclApi {
+	void* handle = nullptr;
+	decltype(&ncclGetUniqueId) GetUniqueId = nullptr;
+	decltype(&ncclCommInitRank) CommInitRank = nullptr;
+	decltype(&ncclCommDestroy) CommDestroy = nullptr;
+	decltype(&ncclAllReduce) AllReduce = nullptr;
+	decltype(&ncclAllGather) AllGather = nullptr;
+	decltype(&ncclBroadcast) Broadcast = nullptr;
+	decltype(&ncclGroupStart) GroupStart = nullptr;
+	decltype(&ncclGroupEnd) GroupEnd = nullptr;
+	decltype(&ncclGetErrorString) GetErrorString = nullptr;
+	decltype(&ncclGetVersion) GetVersion = nullptr;
+	std::string error;
+};
+
+NcclApi& nccl() {
+	static NcclApi api;
+	if (api.handle || !api.error.empty()) return api;
+	/* a process that already runs NCCL (torch.distributed) gets that copy: same SONAME */
+	for (const char* name : {"libnccl.so.2", "libnccl.so"}) {
+		api.handle = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
+		if (api.handle) break;
+	}
+	if (!api.handle) { api.error = std::string("cannot load libnccl.so.2: ") + dlerror(); return api; }
+	bool ok = true;
+	auto sym = [&](const char* n) { void* p = dlsym(api.handle, n); if (!p) { ok = false; api.error = std::string("libnccl lacks ") + n; } return p; };
+	api.GetUniqueId = (decltype(api.GetUniqueId)) sym("ncclGetUniqueId");
+	api.CommInitRank = (decltype(api.CommInitRank)) sym("ncclCommInitRank");
+	api.CommDestroy = (decltype(api.CommDestroy)) sym("ncclCommDestroy");
+	api.AllReduce = (decltype(api.AllReduce)) sym("ncclAllReduce");
+	api.AllGather = (decltype(api.AllGather)) sym("ncclAllGather");
+	api.Broadcast = (decltype(api.Broadcast)) sym("ncclBroadcast");
+	api.GroupStart = (decltype(api.GroupStart)) sym("ncclGroupStart");
+	api.GroupEnd = (decltype(api.GroupEnd)) sym("ncclGroupEnd");
+	api.GetErrorString = (decltype(api.GetErrorString)) sym("ncclGetErrorString");
+	api.GetVersion = (decltype(api.GetVersion)) sym("ncclGetVersion");
+	if (!ok) { dlclose(api.handle); api.handle = nullptr; }
+	return api;
+}
+
+int ncclFail(pbr_ctx* ctx, ncclResult_t r, const char* what) {
+	if (r == ncclSuccess) return PBR_OK;
+	std::string m = std::string(what) + ": " + (nccl().GetErrorString ? nccl().GetErrorString(r) : "NCCL error");
+	if (ctx) ctx->lastError = m;
+	return PBR_ERR_NCCL_BASE + (int) r;
+}
+#define NK(call) do { ncclResult_t r_ = (call); if (r_ != ncclSuccess) return ncclFail(ctx, r_, #call); } while (0)
+
+/* out = image / world: the one pass before the all-reduce (the sum of the pre-divided images is the mean) */
+__global__ void scaleCopyKernel(const float4* __restrict__ in, float4* __restrict__ out, const size_t n, const float s) {
+	const size_t stride = (size_t) gridDim.x * blockDim.x;
+	for (size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+		const float4 v = in[i];
+		out[i] = make_float4(v.x * s, v.y * s, v.z * s, v.w * s);
+	}
+}
+
+/* interleaved stripes (pbr_set_tile_stripes): this rank's stripes, packed / every other rank's stripes, unpacked.
+ * rowF4 = float4s per image row; local row r of rank k is image row (r / stripe) * stripe * world + k * stripe + r % stripe */
+__global__ void packStripesKernel(const float4* __restrict__ image, float4* __restrict__ send, const int rowF4, const int localRows,
+                                  const int stripe, const int world, const int rank) {
+	const size_t n = (size_t) rowF4 * localRows, step = (size_t) gridDim.x * blockDim.x;
+	for (size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += step) {
+		const int r = (int) (i / rowF4), x = (int) (i % rowF4);
+		const int y = (r / stripe) * stripe * world + rank * stripe + r % stripe;
+		send[i] = image[(size_t) y * rowF4 + x];
+	}
+}
+
+__global__ void unpackStripesKernel(float4* __restrict__ image, const float4* __restrict__ recv, const int rowF4, const int localRows,
+                                    const int stripe, const int world, const int rank) {
+	const size_t per = (size_t) rowF4 * localRows, n = per * world, step = (size_t) gridDim.x * blockDim.x;
+	for (size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += step) {
+		const int k = (int) (i / per);
+		if (k == rank) continue;                   /* its own rows are in place */
+		const size_t j = i % per;
+		const int r = (int) (j / rowF4), x = (int) (j % rowF4);
+		const int y = (r / stripe) * stripe * world + k * stripe + r % stripe;
+		image[(size_t) y * rowF4 + x] = recv[i];
+	}
+}
+
+/* A launch that overwrites an image waits for the combine that still reads it (frame k + 2 and the combine of frame k
+ * share a buffer of PathTracer's ping-pong pair); with depth of field a frame also READS other pixels of imageIn, which
+ * a row gather is still filling. */
+int waitForCombine(pbr_ctx* ctx, Mem* m) {
+	if (m && m->combinePending) {
+		CK(cudaStreamWaitEvent(ctx->stream, m->evCombined, 0));
+		m->combinePending = false;
+	}
+	return PBR_OK;
+}
+
 bool parseSky(const char* v, pbr_float4* out) {
 	/* "(float4)( %f, %f, %f, 0.0f )" (PathTracer.cpp:470-472, 515) */
 	const char* p = strstr(v, ")(");
@@ -664,6 +773,12 @@ int pbr_destroy(pbr_ctx* ctx) {
 	cudaEventDestroy(ctx->evStart); cudaEventDestroy(ctx->evStop);
 	for (const pbr_ctx::Timed& t : ctx->timedInFlight) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
 	for (cudaEvent_t e : ctx->eventPool) cudaEventDestroy(e);
+	if (ctx->commStream) cudaStreamSynchronize(ctx->commStream);
+	if (ctx->comm && nccl().CommDestroy) nccl().CommDestroy(ctx->comm);
+	if (ctx->commStream) cudaStreamDestroy(ctx->commStream);
+	if (ctx->evRendered) cudaEventDestroy(ctx->evRendered);
+	cudaFree(ctx->commSend); cudaFree(ctx->commRecv);
+	for (Mem& m : ctx->mems) if (m.evCombined) cudaEventDestroy(m.evCombined);
 	if (ctx->copyStream) { cudaStreamSynchronize(ctx->copyStream); cudaStreamDestroy(ctx->copyStream); }
 	if (ctx->evCopy) cudaEventDestroy(ctx->evCopy);
 	for (int i = 0; i < 8; i++) if (ctx->evAuto[i]) cudaEventDestroy(ctx->evAuto[i]);
@@ -673,6 +788,11 @@ int pbr_destroy(pbr_ctx* ctx) {
 }
 
 const char* pbr_last_error(pbr_ctx* ctx) { return ctx ? ctx->lastError.c_str() : "no context"; }
+
+#ifndef PBR_BUILD_ID
+#define PBR_BUILD_ID "unknown"
+#endif
+const char* pbr_build_id(void) { return PBR_BUILD_ID; }
 
 int pbr_device_info(pbr_ctx* ctx, char* name, size_t name_len, int* sm_count, size_t* total_mem) {
 	if (!ctx) return PBR_ERR_INVALID;
@@ -763,6 +883,8 @@ int pbr_image_read(pbr_ctx* ctx, pbr_mem image, size_t width, size_t height, flo
 	if (!m || !m->image || width != m->width || height != m->height || !host)
 		return fail(ctx, PBR_ERR_INVALID, "pbr_image_read: bad image or size");
 	CK(cudaSetDevice(ctx->device));
+	int rc = waitForCombine(ctx, m);
+	if (rc) return rc;
 	CK(cudaMemcpyAsync(host, m->dptr, m->bytes, cudaMemcpyDeviceToHost, ctx->stream));
 	CK(cudaStreamSynchronize(ctx->stream));
 	return PBR_OK;
@@ -781,6 +903,7 @@ int pbr_image_read_begin(pbr_ctx* ctx, pbr_mem image, size_t width, size_t heigh
 	}
 	CK(cudaEventRecord(ctx->evCopy, ctx->stream));
 	CK(cudaStreamWaitEvent(ctx->copyStream, ctx->evCopy, 0));
+	if (m->combinePending) CK(cudaStreamWaitEvent(ctx->copyStream, m->evCombined, 0));
 	CK(cudaMemcpyAsync(host, m->dptr, m->bytes, cudaMemcpyDeviceToHost, ctx->copyStream));
 	ctx->copyInFlight = true;
 	return PBR_OK;
@@ -1041,6 +1164,9 @@ int pbr_kernel_launch(pbr_ctx* ctx, pbr_kernel k) {
 	if (rc) return rc;
 	CK(cudaSetDevice(ctx->device));
 	KernelArgs& a = ctx->args;
+	rc = waitForCombine(ctx, getMem(ctx, a.mem[12]));
+	if (rc) return rc;
+	if (a.cam.focusPoint.x >= 0 && a.cam.focusPoint.y >= 0) { rc = waitForCombine(ctx, getMem(ctx, a.mem[11])); if (rc) return rc; }
 	CK(cudaEventRecord(ctx->evStart, ctx->stream));
 	rc = launchFrames(ctx, 1, &a.seed, &a.pixelWeight, a.mem[11], a.mem[12]);
 	if (rc) return rc;
@@ -1056,6 +1182,10 @@ int pbr_kernel_launch_batch(pbr_ctx* ctx, pbr_kernel k, int32_t n_frames, const 
 	CK(cudaSetDevice(ctx->device));
 	KernelArgs& a = ctx->args;
 	const pbr_mem hIn = a.mem[11], hOut = a.mem[12];
+	rc = waitForCombine(ctx, getMem(ctx, hOut));
+	if (rc) return rc;
+	rc = waitForCombine(ctx, getMem(ctx, hIn));
+	if (rc) return rc;
 	CK(cudaEventRecord(ctx->evStart, ctx->stream));
 	const bool depthOfField = a.cam.focusPoint.x >= 0 && a.cam.focusPoint.y >= 0;
 	if (!depthOfField) {
@@ -1096,6 +1226,7 @@ int pbr_finish(pbr_ctx* ctx) {
 	if (!ctx) return PBR_ERR_INVALID;
 	CK(cudaSetDevice(ctx->device));
 	CK(cudaStreamSynchronize(ctx->stream));
+	if (ctx->commStream) CK(cudaStreamSynchronize(ctx->commStream));
 	return PBR_OK;
 }
 
@@ -1198,6 +1329,168 @@ int pbr_traversal_info(pbr_ctx* ctx, pbr_traversal_info_t* out, int32_t reset) {
 	out->rewalked_rays = c[0];
 	out->ordered_rays = c[1];
 	strncpy(out->why_not, ctx->wideWhy.c_str(), sizeof(out->why_not) - 1);
+	return PBR_OK;
+}
+
+/* ---- multi-GPU ------------------------------------------------------------------------------------------- */
+
+int pbr_tile_rows(int32_t height, int32_t rank, int32_t world, int32_t* y0, int32_t* y1) {
+	if (height <= 0 || world < 1 || rank < 0 || rank >= world || !y0 || !y1) return PBR_ERR_INVALID;
+	const long long align = 4, blocks = (height + align - 1) / align;
+	const long long b0 = blocks * rank / world, b1 = blocks * (rank + 1) / world;
+	*y0 = (int32_t) std::min<long long>(b0 * align, height);
+	*y1 = (int32_t) std::min<long long>(b1 * align, height);
+	return PBR_OK;
+}
+
+int pbr_comm_unique_id(void* id128) {
+	if (!id128) return PBR_ERR_INVALID;
+	NcclApi& N = nccl();
+	if (!N.handle) return PBR_ERR_UNSUPPORTED;
+	ncclUniqueId id;
+	const ncclResult_t r = N.GetUniqueId(&id);
+	if (r != ncclSuccess) return PBR_ERR_NCCL_BASE + (int) r;
+	memcpy(id128, &id, sizeof(id));
+	return PBR_OK;
+}
+
+int pbr_comm_init(pbr_ctx* ctx, const void* id128, int32_t rank, int32_t world) {
+	if (!ctx || !id128 || world < 1 || rank < 0 || rank >= world) return PBR_ERR_INVALID;
+	if (ctx->comm) return fail(ctx, PBR_ERR_INVALID, "pbr_comm_init: this context already has a communicator");
+	NcclApi& N = nccl();
+	if (!N.handle) return fail(ctx, PBR_ERR_UNSUPPORTED, "pbr_comm_init: " + N.error);
+	CK(cudaSetDevice(ctx->device));
+	ncclUniqueId id;
+	memcpy(&id, id128, sizeof(id));
+	NK(N.CommInitRank(&ctx->comm, world, id, rank));
+	ctx->commRank = rank;
+	ctx->commWorld = world;
+	CK(cudaStreamCreateWithFlags(&ctx->commStream, cudaStreamNonBlocking));
+	CK(cudaEventCreateWithFlags(&ctx->evRendered, cudaEventDisableTiming));
+	return PBR_OK;
+}
+
+int pbr_comm_info(pbr_ctx* ctx, int32_t* rank, int32_t* world, int32_t* nccl_version) {
+	if (!ctx) return PBR_ERR_INVALID;
+	if (rank) *rank = ctx->commRank;
+	if (world) *world = ctx->comm ? ctx->commWorld : 1;
+	if (nccl_version) {
+		int v = 0;
+		if (ctx->comm && nccl().GetVersion) nccl().GetVersion(&v);
+		*nccl_version = v;
+	}
+	return PBR_OK;
+}
+
+int pbr_comm_destroy(pbr_ctx* ctx) {
+	if (!ctx) return PBR_ERR_INVALID;
+	if (!ctx->comm) return PBR_OK;
+	CK(cudaSetDevice(ctx->device));
+	CK(cudaStreamSynchronize(ctx->commStream));
+	NK(nccl().CommDestroy(ctx->comm));
+	ctx->comm = nullptr;
+	ctx->commWorld = 1;
+	ctx->commRank = 0;
+	for (Mem& m : ctx->mems) m.combinePending = false;
+	return PBR_OK;
+}
+
+/* One collective per frame, enqueued on the communicator's own stream behind everything the render
+ * stream has been given so far, so that the next frame is traced while this one crosses NVLink. */
+int pbr_frame_combine(pbr_ctx* ctx, pbr_mem image, int32_t mode, pbr_mem out) {
+	if (!ctx) return PBR_ERR_INVALID;
+	Mem* img = getMem(ctx, image);
+	if (!img || !img->image) return fail(ctx, PBR_ERR_INVALID, "pbr_frame_combine: not an image");
+	if (!ctx->comm) return fail(ctx, PBR_ERR_NOT_READY, "pbr_frame_combine before pbr_comm_init");
+	NcclApi& N = nccl();
+	CK(cudaSetDevice(ctx->device));
+	const int world = ctx->commWorld, rank = ctx->commRank;
+	const size_t nF4 = img->width * img->height;
+	CK(cudaEventRecord(ctx->evRendered, ctx->stream));
+	CK(cudaStreamWaitEvent(ctx->commStream, ctx->evRendered, 0));
+	Mem* pending = img;
+	if (mode == PBR_COMBINE_SPP) {
+		Mem* dst = getMem(ctx, out);
+		if (!dst || !dst->image || dst->bytes != img->bytes || dst == img)
+			return fail(ctx, PBR_ERR_INVALID, "pbr_frame_combine(SPP): `out` must be another image of the same size");
+		if (dst->combinePending) CK(cudaStreamWaitEvent(ctx->commStream, dst->evCombined, 0));
+		ctx->prof.launches++; ctx->prof.other_launches++;
+		scaleCopyKernel<<<ctx->smCount * 4, 256, 0, ctx->commStream>>>((const float4*) img->dptr, (float4*) dst->dptr, nF4, 1.0f / (float) world);
+		CK(cudaGetLastError());
+		/* `image` is free again once it has been copied; `out` is busy until the collective is done */
+		if (!img->evCombined) CK(cudaEventCreateWithFlags(&img->evCombined, cudaEventDisableTiming));
+		CK(cudaEventRecord(img->evCombined, ctx->commStream));
+		img->combinePending = true;
+		pending = nullptr;
+		NK(N.AllReduce(dst->dptr, dst->dptr, nF4 * 4, ncclFloat, ncclSum, ctx->comm, ctx->commStream));
+		if (!dst->evCombined) CK(cudaEventCreateWithFlags(&dst->evCombined, cudaEventDisableTiming));
+		CK(cudaEventRecord(dst->evCombined, ctx->commStream));
+		dst->combinePending = true;
+	}
+	else if (mode == PBR_COMBINE_ROWS) {
+		const int H = (int) img->height, rowF4 = (int) img->width;
+		if (ctx->stripeRows > 0) {
+			if (ctx->stripeWorld != world || ctx->stripeRank != rank || H % (ctx->stripeRows * world) != 0)
+				return fail(ctx, PBR_ERR_INVALID, "pbr_frame_combine(ROWS): pbr_set_tile_stripes does not match the communicator");
+			const int localRows = H / world;
+			const size_t per = (size_t) localRows * rowF4;
+			if (per > ctx->commSendCap) { cudaFree(ctx->commSend); ctx->commSend = nullptr; CK(cudaMalloc(&ctx->commSend, per * 16)); ctx->commSendCap = per; }
+			if (per * world > ctx->commRecvCap) { cudaFree(ctx->commRecv); ctx->commRecv = nullptr; CK(cudaMalloc(&ctx->commRecv, per * world * 16)); ctx->commRecvCap = per * world; }
+			ctx->prof.launches += 2; ctx->prof.other_launches += 2;
+			packStripesKernel<<<ctx->smCount * 4, 256, 0, ctx->commStream>>>((const float4*) img->dptr, ctx->commSend, rowF4, localRows, ctx->stripeRows, world, rank);
+			NK(N.AllGather(ctx->commSend, ctx->commRecv, per * 4, ncclFloat, ctx->comm, ctx->commStream));
+			unpackStripesKernel<<<ctx->smCount * 4, 256, 0, ctx->commStream>>>((float4*) img->dptr, ctx->commRecv, rowF4, localRows, ctx->stripeRows, world, rank);
+			CK(cudaGetLastError());
+		}
+		else {
+			/* contiguous row blocks, the partition of pbr_tile_rows: gathered in place, no packing */
+			std::vector<int32_t> y0((size_t) world), y1((size_t) world);
+			bool equal = true;
+			for (int r = 0; r < world; r++) {
+				pbr_tile_rows(H, r, world, &y0[(size_t) r], &y1[(size_t) r]);
+				if (y1[(size_t) r] - y0[(size_t) r] != y1[0] - y0[0]) equal = false;
+			}
+			const int myY0 = ctx->tileY0 < 0 ? 0 : ctx->tileY0, myY1 = ctx->tileY1 < 0 ? H : ctx->tileY1;
+			if (myY0 != y0[(size_t) rank] || myY1 != y1[(size_t) rank])
+				return fail(ctx, PBR_ERR_INVALID, "pbr_frame_combine(ROWS): pbr_set_tile is not this rank's block of pbr_tile_rows");
+			float* base = (float*) img->dptr;
+			if (equal) {
+				const size_t cnt = (size_t) (y1[0] - y0[0]) * rowF4 * 4;
+				NK(N.AllGather(base + (size_t) rank * cnt, base, cnt, ncclFloat, ctx->comm, ctx->commStream));
+			}
+			else {
+				NK(N.GroupStart());
+				for (int r = 0; r < world; r++) {
+					float* p = base + (size_t) y0[(size_t) r] * rowF4 * 4;
+					const size_t cnt = (size_t) (y1[(size_t) r] - y0[(size_t) r]) * rowF4 * 4;
+					const ncclResult_t e = N.Broadcast(p, p, cnt, ncclFloat, r, ctx->comm, ctx->commStream);
+					if (e != ncclSuccess) { N.GroupEnd(); return ncclFail(ctx, e, "ncclBroadcast"); }
+				}
+				NK(N.GroupEnd());
+			}
+		}
+	}
+	else return fail(ctx, PBR_ERR_INVALID, "pbr_frame_combine: unknown mode");
+	if (pending) {
+		if (!pending->evCombined) CK(cudaEventCreateWithFlags(&pending->evCombined, cudaEventDisableTiming));
+		CK(cudaEventRecord(pending->evCombined, ctx->commStream));
+		pending->combinePending = true;
+	}
+	ctx->combines++;
+	return PBR_OK;
+}
+
+/* Block the render stream (not the host) until the combines enqueued so far are done. */
+int pbr_comm_fence(pbr_ctx* ctx) {
+	if (!ctx) return PBR_ERR_INVALID;
+	if (!ctx->comm) return PBR_OK;
+	CK(cudaSetDevice(ctx->device));
+	for (Mem& m : ctx->mems) {
+		if (m.alive && m.combinePending) {
+			CK(cudaStreamWaitEvent(ctx->stream, m.evCombined, 0));
+			m.combinePending = false;
+		}
+	}
 	return PBR_OK;
 }
 

@@ -31,6 +31,8 @@ SYMBOLS = [
     "pbrh_renderer_reset_sample_count", "pbrh_renderer_set_focus", "pbrh_renderer_set_eye",
     "pbrh_renderer_rotate_camera", "pbrh_renderer_move_camera", "pbrh_renderer_info", "pbrh_renderer_stats", "pbrh_renderer_flat_get",
     "pbrh_renderer_camera", "pbrh_renderer_trace", "pbrh_renderer_handles",
+    "pbrh_comm_unique_id", "pbrh_renderer_set_ranks", "pbrh_renderer_set_traversal", "pbrh_renderer_set_sharding",
+    "pbrh_renderer_comm_fence",
     "pbrh_write_pfm", "pbrh_write_checkpoint", "pbrh_read_checkpoint",
 ]
 
@@ -84,6 +86,11 @@ def load_library():
     lib.pbrh_renderer_set_render_ahead.argtypes = [vp, i32]
     lib.pbrh_renderer_set_tile_stripes.argtypes = [vp, i32, i32, i32]
     lib.pbrh_renderer_set_tile.argtypes = [vp, i32, i32]
+    lib.pbrh_comm_unique_id.argtypes = [vp]
+    lib.pbrh_renderer_set_ranks.argtypes = [vp, i32, i32, vp, i32]
+    lib.pbrh_renderer_set_traversal.argtypes = [vp, i32]
+    lib.pbrh_renderer_set_sharding.argtypes = [vp, i32]
+    lib.pbrh_renderer_comm_fence.argtypes = [vp]
     lib.pbrh_renderer_generate_image.argtypes = [vp, f32p, f32p]
     lib.pbrh_renderer_render_frames.argtypes = [vp, i32]
     lib.pbrh_renderer_read_image.argtypes = [vp, f32p, f32p]
@@ -300,6 +307,27 @@ class Renderer:
     def set_tile_stripes(self, stripe_rows, world=1, rank=0):
         _ck(self.lib.pbrh_renderer_set_tile_stripes(self.h, stripe_rows, world, rank), "setTileStripes")
 
+    def set_ranks(self, rank, world, nccl_id, sharding="spp"):
+        """PathTracer::setRanks: this renderer is rank `rank` of `world` (one process per GPU); `nccl_id` are the 128 bytes
+        of comm_unique_id() of rank 0.  sharding: "spp" (own seeds, delivered frame = mean over ranks), "rows", "stripes".
+        Every frame then ends with one NCCL collective inside the library."""
+        mode = {"spp": 0, "rows": 1, "stripes": 2}[sharding]
+        buf = (C.c_char * 128).from_buffer_copy(bytes(nccl_id)) if world > 1 else None
+        _ck(self.lib.pbrh_renderer_set_ranks(self.h, rank, world, buf, mode), "PathTracer::setRanks")
+
+    def set_sharding(self, sharding):
+        """Another sharding on the communicator set_ranks created: "spp", "rows", "stripes", or "none" (this rank renders
+        whole frames on its own, no collective).  Restarts the accumulation."""
+        _ck(self.lib.pbrh_renderer_set_sharding(self.h, {"spp": 0, "rows": 1, "stripes": 2, "none": 3}[sharding]), "setSharding")
+
+    def comm_fence(self):
+        """The render stream waits, on the device, for the collectives enqueued so far."""
+        _ck(self.lib.pbrh_renderer_comm_fence(self.h), "commFence")
+
+    def set_traversal(self, mode):
+        """-1 automatic, 0 the reference's visiting order, 1 the ordered walk (pbr_set_traversal)."""
+        _ck(self.lib.pbrh_renderer_set_traversal(self.h, int(mode)), "setTraversal")
+
     def set_tile(self, y0, y1):
         _ck(self.lib.pbrh_renderer_set_tile(self.h, y0, y1), "setTileRows")
 
@@ -391,6 +419,14 @@ class Renderer:
         """capi.Device view of this renderer's pbr_ctx (streams, profiling, raw buffers)."""
         ctx, _ = self.handles()
         return capi.Device.from_ctx(ctx)
+
+
+def comm_unique_id():
+    """128 bytes identifying a new NCCL communicator (pbr_comm_unique_id): rank 0 creates it, every rank passes it to
+    Renderer.set_ranks."""
+    buf = (C.c_char * 128)()
+    _ck(load_library().pbrh_comm_unique_id(buf), "pbrh_comm_unique_id")
+    return bytes(buf)
 
 
 def write_pfm(path, image):

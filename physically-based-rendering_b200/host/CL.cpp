@@ -267,6 +267,31 @@ void CL::getStats( uint64_t out[6], bool reset ) {
 }
 
 
+bool CL::commUniqueId( void* id128 ) {
+	return pbr_comm_unique_id( id128 ) == 0;
+}
+
+
+bool CL::commInit( const void* id128, int rank, int world ) {
+	return this->checkError( pbr_comm_init( mContext, id128, rank, world ), "pbr_comm_init (ncclCommInitRank)" );
+}
+
+
+void CL::frameCombine( cl_mem image, int mode, cl_mem out ) {
+	this->checkError( pbr_frame_combine( mContext, image, mode, out ), "pbr_frame_combine" );
+}
+
+
+void CL::commFence() {
+	this->checkError( pbr_comm_fence( mContext ), "pbr_comm_fence" );
+}
+
+
+void CL::setTraversal( int mode ) {
+	this->checkError( pbr_set_traversal( mContext, mode ), "pbr_set_traversal" );
+}
+
+
 void* CL::allocHost( size_t bytes ) {
 	void* p = NULL;
 	this->checkError( pbr_host_alloc( mContext, bytes, &p ), "pbr_host_alloc" );

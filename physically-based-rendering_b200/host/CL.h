@@ -67,6 +67,13 @@ class CL {
 		void setTileStripes( int stripeRows, int world, int rank );
 		void setDebugImage( bool enabled );
 		void getStats( uint64_t out[6], bool reset );
+		/* multi-GPU (pbr_comm_*): one CL per process and GPU, one collective per frame */
+		static bool commUniqueId( void* id128 );
+		bool commInit( const void* id128, int rank, int world );
+		void frameCombine( cl_mem image, int mode, cl_mem out );
+		void commFence();
+		/* which walk finds the hits (pbr_set_traversal): -1 automatic, 0 reference order, 1 ordered */
+		void setTraversal( int mode );
 		void* allocHost( size_t bytes );
 		void freeHost( void* ptr );
 

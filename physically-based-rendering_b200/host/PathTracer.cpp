@@ -57,6 +57,11 @@ PathTracer::PathTracer( GLWidget* parent ) {
 	mAheadLaunched = false;
 	mSampleCountBeforeAhead = 0;
 	mHaveOutput = false;
+	mRank = 0;
+	mWorld = 1;
+	mSharding = SHARD_SPP;
+	mBufTextureDisplay[0] = mBufTextureDisplay[1] = 0;
+	mCombines = 0;
 	mTimeSinceStart = std::chrono::steady_clock::now();
 
 	memset( &mStructCam, 0, sizeof( mStructCam ) );
@@ -101,6 +106,86 @@ void PathTracer::launchFrame() {
 	this->clPathTracing( this->nextSeed() );
 	mSampleCount++;
 	mHaveOutput = true;
+	this->combineFrame();
+}
+
+
+/**
+ * The frame just launched is completed across the ranks: one collective, enqueued behind it on the communicator's
+ * stream (the next frame is traced meanwhile; the library orders the buffers, include/pbr_b200.h).
+ */
+void PathTracer::combineFrame() {
+	if( mWorld <= 1 || mSharding == SHARD_NONE ) { return; }
+	if( mSharding == SHARD_SPP ) {
+		mCL->frameCombine( mBufTextureOut, PBR_COMBINE_SPP, mBufTextureDisplay[mCombines & 1] );
+	}
+	else {
+		mCL->frameCombine( mBufTextureOut, PBR_COMBINE_ROWS, 0 );
+	}
+	mCombines++;
+}
+
+
+/** The image a caller receives: the accumulation buffer, or with SHARD_SPP the mean over ranks of the last frame. */
+cl_mem PathTracer::deliveredImage() const {
+	if( mWorld > 1 && mSharding == SHARD_SPP && mCombines > 0 ) { return mBufTextureDisplay[( mCombines - 1 ) & 1]; }
+	return mBufTextureOut;
+}
+
+
+bool PathTracer::setRanks( int rank, int world, const void* ncclId, int sharding ) {
+	this->dropFrameAhead();
+	if( world <= 1 ) { mWorld = 1; mRank = 0; return true; }
+	if( mCL == NULL ) {
+		Logger::logError( "[PathTracer] setRanks: load a model first (the device context is created with it)." );
+		return false;
+	}
+	if( mWorld > 1 ) {
+		Logger::logError( "[PathTracer] setRanks: this renderer already has its ranks (setSharding changes the sharding)." );
+		return false;
+	}
+	if( !mCL->commInit( ncclId, rank, world ) ) { return false; }
+	mRank = rank; mWorld = world;
+	mBufTextureDisplay[0] = mCL->createImage2DWriteOnly( mWidth, mHeight );
+	mBufTextureDisplay[1] = mCL->createImage2DWriteOnly( mWidth, mHeight );
+	return this->setSharding( sharding );
+}
+
+
+bool PathTracer::setSharding( int sharding ) {
+	this->dropFrameAhead();
+	if( mWorld <= 1 ) { return true; }
+	mCL->commFence();
+	mCL->setTileStripes( 0, 1, 0 );
+	mCL->setTile( -1, -1 );
+	this->setSeedSchedule( 1, 0 );
+	mCombines = 0;
+	this->resetSampleCount();
+	if( sharding == SHARD_SPP ) {
+		this->setSeedSchedule( (cl_uint) mWorld, (cl_uint) mRank );
+	}
+	else if( sharding == SHARD_STRIPES ) {
+		int stripe = 0;
+		if( mHeight % (cl_uint) mWorld == 0 ) {
+			const int local = (int) mHeight / mWorld;
+			for( int s = std::min( 8, local ); s > 0; s-- ) { if( local % s == 0 ) { stripe = s; break; } }
+		}
+		if( stripe == 0 ) {
+			Logger::logError( "[PathTracer] window.height is not a multiple of the number of ranks; use SHARD_ROWS." );
+			return false;
+		}
+		mCL->setTileStripes( stripe, mWorld, mRank );
+	}
+	else if( sharding == SHARD_ROWS ) {
+		int32_t y0 = 0, y1 = 0;
+		pbr_tile_rows( (int32_t) mHeight, mRank, mWorld, &y0, &y1 );
+		mCL->setTile( y0, y1 );
+	}
+	else if( sharding != SHARD_NONE ) {
+		return false;
+	}
+	mSharding = sharding;
+	return true;
 }
 
 
@@ -138,8 +223,9 @@ void PathTracer::generateImageInto( cl_float* target, cl_float* targetDebug ) {
 
 	if( mRenderAhead && targetDebug == NULL ) {
 		/* copy this frame out on the copy stream while the next one is traced: the next frame only reads
-		 * the image that is being copied (it is its imageIn) and writes the other one */
-		mCL->readImageOutputBegin( mBufTextureOut, mWidth, mHeight, target );
+		 * the image that is being copied (it is its imageIn) and writes the other one (with ranks: the copy waits for
+		 * this frame's collective, and the next frame's mean lands in the other display image) */
+		mCL->readImageOutputBegin( this->deliveredImage(), mWidth, mHeight, target );
 		mSampleCountBeforeAhead = mSampleCount;
 		mCL->setDebugImage( false );
 		this->launchFrame();
@@ -147,7 +233,7 @@ void PathTracer::generateImageInto( cl_float* target, cl_float* targetDebug ) {
 		mCL->readImageOutputEnd();
 		return;
 	}
-	mCL->readImageOutput( mBufTextureOut, mWidth, mHeight, target );
+	mCL->readImageOutput( this->deliveredImage(), mWidth, mHeight, target );
 	if( targetDebug != NULL ) {
 		mCL->readImageOutput( mBufTextureDebug, mWidth, mHeight, targetDebug );
 	}
@@ -170,6 +256,7 @@ void PathTracer::dropFrameAhead() {
 	mCL->setKernelArg( mKernelPathTracing, 11, sizeof( cl_mem ), &mBufTextureIn );
 	mCL->setKernelArg( mKernelPathTracing, 12, sizeof( cl_mem ), &mBufTextureOut );
 	mSampleCount = mSampleCountBeforeAhead;
+	if( mWorld > 1 && mSharding != SHARD_NONE ) { mCombines--; }           /* its mean over ranks is not wanted either */
 }
 
 
@@ -185,6 +272,11 @@ void PathTracer::renderFrames( cl_uint frames ) {
 	}
 	if( frames == 0 ) { return; }
 	mCL->setDebugImage( false );
+	if( mWorld > 1 && mSharding != SHARD_NONE ) {
+		/* every frame is completed across the ranks (progressive display): frame by frame through the ping-pong pair */
+		for( cl_uint i = 0; i < frames; i++ ) { this->launchFrame(); }
+		return;
+	}
 	this->updateEyeBuffer();
 	if( mHaveOutput ) {
 		std::swap( mBufTextureIn, mBufTextureOut );
@@ -206,7 +298,7 @@ void PathTracer::renderFrames( cl_uint frames ) {
 
 void PathTracer::readImage( cl_float* target, cl_float* targetDebug ) {
 	this->dropFrameAhead();
-	mCL->readImageOutput( mBufTextureOut, mWidth, mHeight, target );
+	mCL->readImageOutput( this->deliveredImage(), mWidth, mHeight, target );
 	if( targetDebug != NULL ) {
 		mCL->readImageOutput( mBufTextureDebug, mWidth, mHeight, targetDebug );
 	}

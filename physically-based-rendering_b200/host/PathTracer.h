@@ -87,6 +87,22 @@ class PathTracer {
 		void setTileRows( int y0, int y1 );
 		/** Interleaved rows for load balance: stripes of `stripeRows` rows, stripe index % world == rank. */
 		void setTileStripes( int stripeRows, int world, int rank );
+		/** Multi-GPU, one process per GPU: this renderer is rank `rank` of `world`; `ncclId` are the 128
+		 *  bytes of CL::commUniqueId() of rank 0.  From then on every frame ends with ONE collective inside the library:
+		 *    SHARD_SPP      every rank renders whole frames with its own seeds (seed schedule stride = world, offset =
+		 *                   rank); the frame delivered by generateImage / readImage is the mean over ranks;
+		 *    SHARD_ROWS     rank r renders the row block pbr_tile_rows gives it, the others are gathered in;
+		 *    SHARD_STRIPES  the same with interleaved stripes of rows (load balance).
+		 *  Replaces the reference's single-device assumption (CL.cpp:355, 470, 521). */
+		enum { SHARD_SPP = 0, SHARD_ROWS = 1, SHARD_STRIPES = 2, SHARD_NONE = 3 };   /* NONE: whole frames, no collective */
+		bool setRanks( int rank, int world, const void* ncclId, int sharding );
+		/** Another sharding on the communicator setRanks created (the accumulation restarts). */
+		bool setSharding( int sharding );
+		/** The render stream waits -- on the device -- for every collective enqueued so far. */
+		void commFence() { if( mWorld > 1 ) { mCL->commFence(); } }
+		int getWorld() const { return mWorld; }
+		/** -1 automatic (default), 0 the reference's visiting order, 1 the ordered walk (pbr_set_traversal). */
+		void setTraversal( int mode ) { mCL->setTraversal( mode ); }
 		cl_uint getSampleCount() const { return mAheadLaunched ? mSampleCountBeforeAhead : mSampleCount; }
 		/** Render ahead: generateImage() starts tracing the NEXT frame before it waits for the copy of this one,
 		 *  so the read-back is hidden behind the next frame.  Anything that changes what the next frame should
@@ -146,6 +162,11 @@ class PathTracer {
 		cl_uint mSampleCountBeforeAhead;
 		void dropFrameAhead();
 		bool mHaveOutput;             // imageOut holds a frame that the next launch must read as imageIn
+		int mRank, mWorld, mSharding;
+		cl_mem mBufTextureDisplay[2]; // SHARD_SPP: the mean over ranks of frame k lands in [k & 1]
+		cl_uint mCombines;
+		void combineFrame();
+		cl_mem deliveredImage() const;
 
 		cl_float* mTextureOut;        // pinned host copy of the frame, W*H*4
 		cl_float* mTextureDebugHost;  // pinned, allocated on first use

@@ -350,6 +350,41 @@ int pbrh_renderer_set_tile_stripes( pbrh_renderer* r, int32_t stripe_rows, int32
 	return 0;
 }
 
+int pbrh_comm_unique_id( void* id128 ) {
+	if( !id128 ) { return failMsg( "pbrh_comm_unique_id: null pointer" ); }
+	if( !CL::commUniqueId( id128 ) ) { return failMsg( "pbrh_comm_unique_id: NCCL is not available (libnccl.so.2 could not be loaded)" ); }
+	return 0;
+}
+
+int pbrh_renderer_set_ranks( pbrh_renderer* r, int32_t rank, int32_t world, const void* id128, int32_t sharding ) {
+	NEED_READY
+	if( world < 1 || rank < 0 || rank >= world || sharding < 0 || sharding > 2 || ( world > 1 && !id128 ) ) {
+		return failMsg( "pbrh_renderer_set_ranks: bad rank / world / sharding" );
+	}
+	if( !r->widget->getPathTracer()->setRanks( rank, world, id128, sharding ) ) {
+		return failMsg( "PathTracer::setRanks failed (see the log)" );
+	}
+	return 0;
+}
+
+int pbrh_renderer_set_sharding( pbrh_renderer* r, int32_t sharding ) {
+	NEED_READY
+	if( !r->widget->getPathTracer()->setSharding( sharding ) ) { return failMsg( "PathTracer::setSharding failed (see the log)" ); }
+	return 0;
+}
+
+int pbrh_renderer_comm_fence( pbrh_renderer* r ) {
+	NEED_READY
+	r->widget->getPathTracer()->commFence();
+	return 0;
+}
+
+int pbrh_renderer_set_traversal( pbrh_renderer* r, int32_t mode ) {
+	NEED_READY
+	r->widget->getPathTracer()->setTraversal( mode );
+	return 0;
+}
+
 int pbrh_renderer_set_render_ahead( pbrh_renderer* r, int32_t enabled ) {
 	r->widget->getPathTracer()->setRenderAhead( enabled != 0 );
 	return 0;

@@ -467,7 +467,7 @@ def run_ours(args):
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches_all), "verify": verify,
             "roofline": roofline, "reference_walk": reference_walk, "strong": strong, "cpu_baseline": cpu_baseline,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if r is not None:
         r.close()
     if world > 1:
@@ -639,10 +639,29 @@ def run_reference(args):
         "e2e": {"value": value, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
+
+
+_STDOUT_FD = None
+
+
+def emit(line):
+    """The ONE JSON line, on the real stdout."""
+    data = (json.dumps(line) + "\n").encode()
+    if _STDOUT_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_STDOUT_FD, data)
 
 
 def main():
+    # Libraries talk on fd 1 (NCCL prints its version there when a communicator is created): everything but the
+    # result line goes to stderr.
+    global _STDOUT_FD
+    sys.stdout.flush()
+    _STDOUT_FD = os.dup(1)
+    os.dup2(2, 1)
     args = parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -91,6 +91,12 @@ int main( int argc, char** argv ) {
 	}
 
 	CL::setDefaultDevice( device );
+	int W = 0, H = 0;
+	unsigned sampleCount = 0;
+	std::vector<float> image;
+	{
+	/* (a scope of its own: the renderer -- and with it this rank's NCCL communicator -- is gone on EVERY rank before
+	 *  rank 0 starts waiting for the others) */
 	GLWidget widget;
 	widget.getPathTracer()->setDeterministicSeeds( deterministic );
 	widget.loadModel( dir, file );
@@ -119,8 +125,8 @@ int main( int argc, char** argv ) {
 		}
 		if( !pt->setRanks( rank, ranks, id, shard ) ) { return 1; }
 	}
-	const int W = (int) pt->getWidth(), H = (int) pt->getHeight();
-	std::vector<float> image( (size_t) W * H * 4, 0.0f );
+	W = (int) pt->getWidth(); H = (int) pt->getHeight();
+	image.assign( (size_t) W * H * 4, 0.0f );
 
 	if( !resume.empty() ) {
 		unsigned sc = 0;
@@ -142,6 +148,9 @@ int main( int argc, char** argv ) {
 		ranks > 1 ? ( "rank " + std::to_string( rank ) + " of " + std::to_string( ranks ) + ": " ).c_str() : "",
 		frames, W, H, sec, frames * (double) W * H * Cfg::get().value<int>( Cfg::RENDER_SAMPLES ) / sec * 1e-6,
 		(double) ( stats[0] + stats[1] ) / sec * 1e-6, pt->getSampleCount() );
+	sampleCount = pt->getSampleCount();
+	pt->getCL()->finish();
+	}
 	if( rank != 0 ) { return 0; }
 	int failed = 0;
 	for( size_t i = 0; i < children.size(); i++ ) {
@@ -155,7 +164,7 @@ int main( int argc, char** argv ) {
 		fprintf( stderr, "%s\n", pbrh_last_error() );
 		return 1;
 	}
-	if( !checkpoint.empty() && pbrh_write_checkpoint( checkpoint.c_str(), image.data(), W, H, pt->getSampleCount() ) != 0 ) {
+	if( !checkpoint.empty() && pbrh_write_checkpoint( checkpoint.c_str(), image.data(), W, H, sampleCount ) != 0 ) {
 		fprintf( stderr, "%s\n", pbrh_last_error() );
 		return 1;
 	}

@@ -6,9 +6,10 @@
     compute-sanitizer --tool initcheck python scripts/sanitize.py
 
 Covers: scene repack, raygen / traverse / shade (BRDF 0 and 1), the shadow-ray stage (as a wavefront stage and
-inline), depth of field, SAMPLES > 1, Phong tessellation, the four pipelines (wavefront, megakernel, persistent
-rings, carry-over), batched frames with and without interleaving, tile rows and stripes, explicit closest-hit
-and any-hit rays, the pinned-math probe.  Every frame is also compared with the wavefront's (same bits)."""
+inline), depth of field, SAMPLES > 1, Phong tessellation, both pipelines (wavefront, megakernel), both walks (the
+reference's visiting order, the ordered walk over the 4-wide BVH -- shared-memory stack and top-of-tree staging
+included), batched frames, tile rows and stripes, explicit closest-hit and any-hit rays under both walks, the
+pinned-math probe.  Every frame is also compared with the reference-order wavefront's (same bits)."""
 import os
 import sys
 
@@ -22,7 +23,7 @@ import helpers as Hh  # noqa: E402
 from oracle import oracle as O  # noqa: E402   (scene loading only; the check against it is tests/)
 
 W, H = 48, 32
-SKIP = set(a[5:] for a in sys.argv[1:] if a.startswith("--no-"))      # e.g. --no-persistent
+SKIP = set(a[5:] for a in sys.argv[1:] if a.startswith("--no-"))      # e.g. --no-megakernel
 CASES = [
     ("sa", dict(brdf=1, max_depth=4)),
     ("schlick_shadow_ms", dict(brdf=0, shadow_rays=1, samples=2, max_depth=3)),
@@ -43,27 +44,29 @@ def main():
             want, wdbg = ds.frames(2)
             for label, setup in [
                 ("megakernel", lambda: dev.setPipeline(1)),
-                ("persistent", lambda: dev.setPipeline(2)),
-                ("carry-over", lambda: dev.setPipeline(3)),
                 ("shadow inline", lambda: (dev.setPipeline(0), dev.setTuning("shadow_stage", 0))),
                 ("measured choice", lambda: dev.setPipeline(-1)),
+                ("ordered walk", lambda: (dev.setPipeline(0), dev.setTraversal(1))),
+                ("ordered, top 1", lambda: (dev.setPipeline(0), dev.setTraversal(1), dev.setTuning("wide_top", 1))),
             ]:
                 if label in SKIP:
                     continue
                 setup()
+                ordered = label.startswith("ordered") and "phong_tessellation" not in kw
+                if label.startswith("ordered") and not ordered:
+                    dev.setTraversal(-1)                      # (PHONGTESS keeps the reference-order walk)
                 got, gdbg = ds.frames(2)
-                ok = Hh.images_equal(got, want) and Hh.images_equal(gdbg, wdbg)
+                ok = Hh.images_equal(got, want) and (ordered or Hh.images_equal(gdbg, wdbg))
                 bad += not ok
                 print("%-18s %-16s %s" % (name, label, "same bits" if ok else "DIFFERENT"), flush=True)
                 dev.setTuning("shadow_stage", 1)
+                dev.setTuning("wide_top", 21)
+                dev.setTraversal(-1)
             dev.setPipeline(0)
-            for inter in (0, 1):
-                dev.setTuning("batch_interleave", inter)
-                got, _ = ds.frames_batch(2)
-                ok = Hh.images_equal(got, want)
-                bad += not ok
-                print("%-18s %-16s %s" % (name, "batch interleave=%d" % inter, "same bits" if ok else "DIFFERENT"), flush=True)
-            dev.setTuning("batch_interleave", 0)
+            got, _ = ds.frames_batch(2)
+            ok = Hh.images_equal(got, want)
+            bad += not ok
+            print("%-18s %-16s %s" % (name, "batch", "same bits" if ok else "DIFFERENT"), flush=True)
             # rows [8, 24) only, then stripes of 4 rows for rank 1 of 2
             dev.setTile(8, 24)
             got, _ = ds.frames(2)
@@ -81,8 +84,13 @@ def main():
                 hits = ds.trace(rays)
                 sh = Hh.shadow_rays_from_hits(rays, hits, (0.5, 4.0, 1.0))
                 occl = ds.trace(sh, any_hit=True)
-                print("explicit rays: %d closest hits, %d occluded shadow rays" % (
-                    int((hits["hitFace"] >= 0).sum()), int((occl["t"] < sh[:, 7]).sum())), flush=True)
+                dev.setTraversal(1)
+                hits2 = ds.trace(rays)
+                dev.setTraversal(-1)
+                same = np.array_equal(hits["hitFace"], hits2["hitFace"]) and np.array_equal(hits["t"].view(np.uint32), hits2["t"].view(np.uint32))
+                bad += not same
+                print("explicit rays: %d closest hits, %d occluded shadow rays, ordered walk %s" % (
+                    int((hits["hitFace"] >= 0).sum()), int((occl["t"] < sh[:, 7]).sum()), "same hits" if same else "DIFFERENT"), flush=True)
         x = np.linspace(-3, 3, 257, dtype=np.float32)
         for op in range(5):
             dev.pinnedMath(op, x if op != 3 else np.clip(x, -1, 1))

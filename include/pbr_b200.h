@@ -154,7 +154,10 @@ int pbr_kernel_launch_batch(pbr_ctx* ctx, pbr_kernel k, int32_t n_frames, const 
  * "traverse_blocks" / "wide_blocks" (cap on resident blocks per SM of the reference-order / ordered traversal kernels,
  * 0 = all that fit), "wide_top" (how many nodes of the top of the 4-wide BVH the ordered walk stages in shared memory;
  * the tree is renumbered at the next launch), "shadow_stage" (1: shadow rays are a wavefront stage of their own, walked
- * by the traversal engine; 0: inside the shade kernel).
+ * by the traversal engine; 0: inside the shade kernel), "frames_in_flight" (1..4, default 4: how many consecutive frames of a
+ * pbr_kernel_launch_batch are traced concurrently, each on a stream and in a wave state of its own; finished pixels leave
+ * their frame's radiance in a per-frame buffer and are mixed into imageOut in frame order -- same bits; 1 = one frame
+ * after the other).
  * The environment variables PBR_NODE_PHASE_MIN, PBR_REFILL_MIN, PBR_PIPELINE, PBR_TRAVERSAL set the initial values.
  * Stands where opencl.localgroupsize stands in the reference's config.json. */
 int pbr_set_tuning(pbr_ctx* ctx, const char* key, int32_t value);
@@ -214,6 +217,10 @@ int pbr_comm_init(pbr_ctx* ctx, const void* id128, int32_t rank, int32_t world);
 int pbr_comm_info(pbr_ctx* ctx, int32_t* rank, int32_t* world, int32_t* nccl_version);
 int pbr_comm_destroy(pbr_ctx* ctx);
 int pbr_frame_combine(pbr_ctx* ctx, pbr_mem image, int32_t mode, pbr_mem out);
+/* The same inside pbr_kernel_launch_batch: after every frame f of a batch, pbr_frame_combine(imageOut, mode,
+ * f + first_parity even ? out0 : out1).  mode -1 switches it off.  (With several frames in flight the batch keeps tracing
+ * the next frames while a frame is mixed and combined.) */
+int pbr_set_batch_combine(pbr_ctx* ctx, int32_t mode, pbr_mem out0, pbr_mem out1, int32_t first_parity);
 /* Make the render stream wait (on the device) for every combine enqueued so far. */
 int pbr_comm_fence(pbr_ctx* ctx);
 /* Rows [y0, y1) of rank `rank` of `world`: contiguous blocks of multiples of 4 rows covering [0, height). */

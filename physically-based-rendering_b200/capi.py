@@ -23,7 +23,7 @@ SYMBOLS = [
     "pbr_finish", "pbr_kernel_time_ms",
     "pbr_image_read_begin", "pbr_image_read_end", "pbr_set_tile", "pbr_set_tile_stripes", "pbr_set_pipeline", "pbr_pipeline_in_use", "pbr_set_tuning", "pbr_kernel_launch_batch", "pbr_set_debug_image", "pbr_stats",
     "pbr_set_traversal", "pbr_traversal_info",
-    "pbr_comm_unique_id", "pbr_comm_init", "pbr_comm_info", "pbr_comm_destroy", "pbr_frame_combine", "pbr_comm_fence", "pbr_tile_rows",
+    "pbr_comm_unique_id", "pbr_comm_init", "pbr_comm_info", "pbr_comm_destroy", "pbr_frame_combine", "pbr_set_batch_combine", "pbr_comm_fence", "pbr_tile_rows",
     "pbr_trace", "pbr_trace_device", "pbr_pinned_math_eval",
     "pbr_set_stream", "pbr_profile_enable", "pbr_profile_read",
 ]
@@ -106,6 +106,7 @@ def load_library():
         "pbr_comm_info": [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)],
         "pbr_comm_destroy": [vp],
         "pbr_frame_combine": [vp, u64, i32, u64],
+        "pbr_set_batch_combine": [vp, i32, u64, u64, i32],
         "pbr_comm_fence": [vp],
         "pbr_tile_rows": [i32, i32, i32, C.POINTER(i32), C.POINTER(i32)],
         "pbr_trace": [vp, u64, u64, u64, u64, i32, vp, i64, i32, vp],
@@ -317,6 +318,9 @@ class Device:
     def frameCombine(self, image, mode, out=0):
         """mode: 0 samples (out = mean over ranks of image), 1 rows (the other ranks' rows gathered into image)."""
         self._ck(self.lib.pbr_frame_combine(self.ctx, image, mode, out), "pbr_frame_combine")
+
+    def setBatchCombine(self, mode, out0=0, out1=0, first_parity=0):
+        self._ck(self.lib.pbr_set_batch_combine(self.ctx, mode, out0, out1, first_parity), "pbr_set_batch_combine")
 
     def commFence(self):
         self._ck(self.lib.pbr_comm_fence(self.ctx), "pbr_comm_fence")

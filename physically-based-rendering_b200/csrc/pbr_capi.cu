@@ -122,18 +122,40 @@ struct pbr_ctx {
 	int wideBudgetBuilt = -1;
 	double wideBuildMs = 0.0;
 
-	/* wavefront state */
-	WaveState wave = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-	float4* hitN = nullptr;                    /* allocated with the wave state, used when PHONGTESS */
-	QueueCtl qctl = {nullptr, {nullptr, nullptr}};
-	size_t waveCap = 0;
-	/* shadow rays as a wavefront stage (render.shadow_rays): ray per path, queue; qctl.ctrl[3] count, [4] cursor */
-	float4* shadowO = nullptr;
-	float4* shadowD = nullptr;
-	uint32_t* shadowQ = nullptr;
-	size_t shadowCap = 0;
+	/* wavefront state: one set per frame in flight (pbr_kernel_launch_batch overlaps the tracing of consecutive
+	 * frames on streams of their own; a single launch uses set 0 on the context's stream) */
+	struct WaveSet {
+		WaveState wave = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+		float4* hitN = nullptr;                /* allocated with the wave state, used when PHONGTESS */
+		QueueCtl qctl = {nullptr, {nullptr, nullptr}};
+		size_t waveCap = 0;
+		/* shadow rays as a wavefront stage (render.shadow_rays): ray per path, queue; qctl.ctrl[3] count, [4] cursor */
+		float4* shadowO = nullptr;
+		float4* shadowD = nullptr;
+		uint32_t* shadowQ = nullptr;
+		size_t shadowCap = 0;
+		/* frames in flight: the frame's own radiance (rgb, focus) before it is mixed into the accumulation image */
+		float4* frameOut = nullptr;
+		size_t frameOutCap = 0;
+		cudaStream_t stream = nullptr;
+		cudaEvent_t evTraced = nullptr, evConsumed = nullptr;
+		bool consumedPending = false;
+	};
+	enum { MAX_IN_FLIGHT = 4 };
+	WaveSet sets[MAX_IN_FLIGHT];
+	int framesInFlight = 4;                    /* tuning "frames_in_flight": 1 -> 2 -> 3 -> 4 = 1356 -> 1548 -> 1599 -> 1619 Mrays/s on C2 */
+	cudaEvent_t evBatchStart = nullptr;
+	int batchCombineMode = -1;                 /* pbr_set_batch_combine */
+	pbr_mem batchCombineOut[2] = {0, 0};
+	int batchCombineParity = 0;
 	int shadowStage = 1;                       /* tuning "shadow_stage": 0 = walk shadow rays inside the shade kernel */
 
+	FrameParams lastFrameParams;               /* of the frame launched last (the deferred mix needs them) */
+	int lastNumPaths = 0;
+	bool launchUseWide = false;
+	int launchSet = 0;                         /* which wave set / stream the frame being launched uses (launchFrames) */
+	cudaStream_t launchStream = nullptr;
+	float4* launchFrameOut = nullptr;          /* != NULL: the frame's radiance goes here, mixing is deferred */
 	int traverseBlocks = 0;                    /* tuning: cap on resident traverse blocks per SM (0 = all that fit) */
 	int wideBlocks = 0;                        /* tuning "wide_blocks": the same for the ordered walk's kernels */
 
@@ -423,39 +445,54 @@ int wideLaunchShape(pbr_ctx* ctx, K kernel, int* grid, size_t* shared) {
 	return PBR_OK;
 }
 
-int ensureWave(pbr_ctx* ctx, size_t nPaths) {
-	if (nPaths <= ctx->waveCap) return PBR_OK;
-	WaveState& W = ctx->wave;
-	cudaFree(W.rayO); cudaFree(W.rayD); cudaFree(W.colS); cudaFree(W.finF); cudaFree(W.misc); cudaFree(W.dbg); cudaFree(ctx->hitN);
-	cudaFree(ctx->qctl.queue[0]); cudaFree(ctx->qctl.queue[1]);
+int ensureWave(pbr_ctx* ctx, pbr_ctx::WaveSet& T, size_t nPaths) {
+	if (!T.qctl.ctrl) {
+		CK(cudaMalloc(&T.qctl.ctrl, 8 * sizeof(uint32_t)));
+		CK(cudaMemsetAsync(T.qctl.ctrl, 0, 8 * sizeof(uint32_t), ctx->stream));
+		CK(cudaStreamSynchronize(ctx->stream));
+	}
+	if (nPaths <= T.waveCap) return PBR_OK;
+	WaveState& W = T.wave;
+	cudaFree(W.rayO); cudaFree(W.rayD); cudaFree(W.colS); cudaFree(W.finF); cudaFree(W.misc); cudaFree(W.dbg); cudaFree(T.hitN);
+	cudaFree(T.qctl.queue[0]); cudaFree(T.qctl.queue[1]);
 	W = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-	ctx->hitN = nullptr;
-	ctx->qctl.queue[0] = ctx->qctl.queue[1] = nullptr;
-	ctx->waveCap = 0;
+	T.hitN = nullptr;
+	T.qctl.queue[0] = T.qctl.queue[1] = nullptr;
+	T.waveCap = 0;
 	CK(cudaMalloc(&W.rayO, nPaths * 16));
 	CK(cudaMalloc(&W.rayD, nPaths * 16));
 	CK(cudaMalloc(&W.colS, nPaths * 16));
 	CK(cudaMalloc(&W.finF, nPaths * 16));
 	CK(cudaMalloc(&W.misc, nPaths * 16));
 	CK(cudaMalloc(&W.dbg, nPaths * 8));
-	CK(cudaMalloc(&ctx->hitN, nPaths * 16));
-	CK(cudaMalloc(&ctx->qctl.queue[0], nPaths * 4));
-	CK(cudaMalloc(&ctx->qctl.queue[1], nPaths * 4));
-	ctx->waveCap = nPaths;
+	CK(cudaMalloc(&T.hitN, nPaths * 16));
+	CK(cudaMalloc(&T.qctl.queue[0], nPaths * 4));
+	CK(cudaMalloc(&T.qctl.queue[1], nPaths * 4));
+	T.waveCap = nPaths;
 	return PBR_OK;
 }
 
-int ensureShadow(pbr_ctx* ctx, size_t nPaths) {
-	if (nPaths <= ctx->shadowCap) return PBR_OK;
-	cudaFree(ctx->shadowO); cudaFree(ctx->shadowD); cudaFree(ctx->shadowQ);
-	ctx->shadowO = ctx->shadowD = nullptr;
-	ctx->shadowQ = nullptr;
-	ctx->shadowCap = 0;
-	CK(cudaMalloc(&ctx->shadowO, nPaths * 16));
-	CK(cudaMalloc(&ctx->shadowD, nPaths * 16));
-	CK(cudaMalloc(&ctx->shadowQ, nPaths * 4));
-	ctx->shadowCap = nPaths;
+int ensureShadow(pbr_ctx* ctx, pbr_ctx::WaveSet& T, size_t nPaths) {
+	if (nPaths <= T.shadowCap) return PBR_OK;
+	cudaFree(T.shadowO); cudaFree(T.shadowD); cudaFree(T.shadowQ);
+	T.shadowO = T.shadowD = nullptr;
+	T.shadowQ = nullptr;
+	T.shadowCap = 0;
+	CK(cudaMalloc(&T.shadowO, nPaths * 16));
+	CK(cudaMalloc(&T.shadowD, nPaths * 16));
+	CK(cudaMalloc(&T.shadowQ, nPaths * 4));
+	T.shadowCap = nPaths;
 	return PBR_OK;
+}
+
+void freeWaveSet(pbr_ctx::WaveSet& T) {
+	WaveState& W = T.wave;
+	cudaFree(W.rayO); cudaFree(W.rayD); cudaFree(W.colS); cudaFree(W.finF); cudaFree(W.misc); cudaFree(W.dbg); cudaFree(T.hitN);
+	cudaFree(T.qctl.queue[0]); cudaFree(T.qctl.queue[1]); cudaFree(T.qctl.ctrl);
+	cudaFree(T.shadowO); cudaFree(T.shadowD); cudaFree(T.shadowQ); cudaFree(T.frameOut);
+	if (T.stream) { cudaStreamSynchronize(T.stream); cudaStreamDestroy(T.stream); }
+	if (T.evTraced) cudaEventDestroy(T.evTraced);
+	if (T.evConsumed) cudaEventDestroy(T.evConsumed);
 }
 
 /* extendDepth (pt_utils.cl:89-96) and the transparency branch of getNewRay (pt_brdf.cl:352-354) are the
@@ -489,8 +526,10 @@ int updateCanExtendDepth(pbr_ctx* ctx, pbr_mem hMaterials, int brdf) {
  * The traverse stage is the reference-order engine (traverseKernel) or, with P.scene.wide set, the ordered walk
  * (traverseWideKernel): both leave the same t / hitFace in the path state. */
 template <int BRDF, bool SHADOW, bool PHONG>
-int runWavefront(pbr_ctx* ctx, const FrameParams& P, WaveState W, int nPaths) {
-	const QueueCtl& Q = ctx->qctl;
+int runWavefront(pbr_ctx* ctx, const FrameParams& P, pbr_ctx::WaveSet& T, cudaStream_t stream, int nPaths) {
+	WaveState W = T.wave;
+	W.hitN = PHONG ? T.hitN : nullptr;
+	const QueueCtl& Q = T.qctl;
 	const bool useWide = !PHONG && P.scene.wide != nullptr;
 	int occT = 0, occS = 0;
 	CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occT, traverseKernel<PHONG>, 128, 0));
@@ -510,7 +549,7 @@ int runWavefront(pbr_ctx* ctx, const FrameParams& P, WaveState W, int nPaths) {
 	const bool shadowStage = SHADOW && P.scene.numLights > 0 && ctx->shadowStage != 0;
 	int gridG = 0;
 	if (shadowStage) {
-		int rc = ensureShadow(ctx, (size_t) nPaths);
+		int rc = ensureShadow(ctx, T, (size_t) nPaths);
 		if (rc) return rc;
 		int occG = 0;
 		CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occG, shadowGenKernel<BRDF, PHONG>, 128, 0));
@@ -521,8 +560,8 @@ int runWavefront(pbr_ctx* ctx, const FrameParams& P, WaveState W, int nPaths) {
 		}
 	}
 	{
-		LaunchScope ls(ctx, K_RAYGEN);
-		raygenKernel<<<ctx->smCount * 8, 256, 0, ctx->stream>>>(P, W, Q, nPaths);
+		LaunchScope ls(ctx, K_RAYGEN, stream);
+		raygenKernel<<<ctx->smCount * 8, 256, 0, stream>>>(P, W, Q, nPaths);
 	}
 	const int iterations = P.frameCount * P.samples * (P.maxDepth + (ctx->canExtendDepth ? P.maxAddedDepth : 0));
 	static const bool dump = getenv("PBR_PROFILE_DUMP") != nullptr;     /* diagnostics: one line per iteration */
@@ -531,41 +570,41 @@ int runWavefront(pbr_ctx* ctx, const FrameParams& P, WaveState W, int nPaths) {
 	for (int it = 0; it < iterations; it++) {
 		const int in = it & 1, out = in ^ 1;
 		const uint32_t* qIn = (it == 0) ? nullptr : Q.queue[in];
-		if (dump) cudaEventRecord(e0, ctx->stream);
+		if (dump) cudaEventRecord(e0, stream);
 		{
-			LaunchScope ls(ctx, K_TRAVERSE);
-			if (useWide) traverseWideKernel<<<gridW, PT_WIDE_BLOCK, sharedW, ctx->stream>>>(P.scene, W, qIn, Q.ctrl + in, Q.ctrl + 2, Q.ctrl + out, ctx->stats);
-			else traverseKernel<PHONG><<<gridT, 128, 0, ctx->stream>>>(P.scene, W, qIn, Q.ctrl + in, Q.ctrl + 2, Q.ctrl + out, ctx->stats);
+			LaunchScope ls(ctx, K_TRAVERSE, stream);
+			if (useWide) traverseWideKernel<<<gridW, PT_WIDE_BLOCK, sharedW, stream>>>(P.scene, W, qIn, Q.ctrl + in, Q.ctrl + 2, Q.ctrl + out, ctx->stats);
+			else traverseKernel<PHONG><<<gridT, 128, 0, stream>>>(P.scene, W, qIn, Q.ctrl + in, Q.ctrl + 2, Q.ctrl + out, ctx->stats);
 		}
-		if (dump) cudaEventRecord(e1, ctx->stream);
+		if (dump) cudaEventRecord(e1, stream);
 		if (shadowStage) {
 			{
-				LaunchScope ls(ctx, K_SHADE);
-				shadowGenKernel<BRDF, PHONG><<<gridG, 128, 0, ctx->stream>>>(
-					P, W, qIn, Q.ctrl + in, ctx->shadowO, ctx->shadowD, ctx->shadowQ, Q.ctrl + 3);
+				LaunchScope ls(ctx, K_SHADE, stream);
+				shadowGenKernel<BRDF, PHONG><<<gridG, 128, 0, stream>>>(
+					P, W, qIn, Q.ctrl + in, T.shadowO, T.shadowD, T.shadowQ, Q.ctrl + 3);
 			}
 			{
-				LaunchScope ls(ctx, K_TRAVERSE);
-				if (useWide) traverseWideShadowKernel<<<gridWS, PT_WIDE_BLOCK, sharedW, ctx->stream>>>(
-					P.scene, W, ctx->shadowO, ctx->shadowD, ctx->shadowQ, Q.ctrl + 3, Q.ctrl + 4, ctx->stats);
-				else traverseShadowKernel<PHONG><<<gridT, 128, 0, ctx->stream>>>(
-					P.scene, W, ctx->shadowO, ctx->shadowD, ctx->shadowQ, Q.ctrl + 3, Q.ctrl + 4, ctx->stats);
+				LaunchScope ls(ctx, K_TRAVERSE, stream);
+				if (useWide) traverseWideShadowKernel<<<gridWS, PT_WIDE_BLOCK, sharedW, stream>>>(
+					P.scene, W, T.shadowO, T.shadowD, T.shadowQ, Q.ctrl + 3, Q.ctrl + 4, ctx->stats);
+				else traverseShadowKernel<PHONG><<<gridT, 128, 0, stream>>>(
+					P.scene, W, T.shadowO, T.shadowD, T.shadowQ, Q.ctrl + 3, Q.ctrl + 4, ctx->stats);
 			}
 			{
-				LaunchScope ls(ctx, K_SHADE);
-				shadeKernel<BRDF, SHADOW, PHONG, true><<<gridS, 128, 0, ctx->stream>>>(
-					P, W, qIn, Q.ctrl + in, Q.queue[out], Q.ctrl + out, Q.ctrl + 2, Q.ctrl + 3, Q.ctrl + 4, ctx->shadowO);
+				LaunchScope ls(ctx, K_SHADE, stream);
+				shadeKernel<BRDF, SHADOW, PHONG, true><<<gridS, 128, 0, stream>>>(
+					P, W, qIn, Q.ctrl + in, Q.queue[out], Q.ctrl + out, Q.ctrl + 2, Q.ctrl + 3, Q.ctrl + 4, T.shadowO);
 			}
 		}
 		else {
-			LaunchScope ls(ctx, K_SHADE);
-			shadeKernel<BRDF, SHADOW, PHONG><<<gridS, 128, 0, ctx->stream>>>(P, W, qIn, Q.ctrl + in, Q.queue[out], Q.ctrl + out, Q.ctrl + 2);
+			LaunchScope ls(ctx, K_SHADE, stream);
+			shadeKernel<BRDF, SHADOW, PHONG><<<gridS, 128, 0, stream>>>(P, W, qIn, Q.ctrl + in, Q.queue[out], Q.ctrl + out, Q.ctrl + 2);
 		}
 		if (dump) {
-			cudaEventRecord(e2, ctx->stream);
+			cudaEventRecord(e2, stream);
 			uint32_t c[4] = {0, 0, 0, 0};
-			cudaMemcpyAsync(c, Q.ctrl, sizeof(c), cudaMemcpyDeviceToHost, ctx->stream);
-			cudaStreamSynchronize(ctx->stream);
+			cudaMemcpyAsync(c, Q.ctrl, sizeof(c), cudaMemcpyDeviceToHost, stream);
+			cudaStreamSynchronize(stream);
 			float tMs = 0.0f, sMs = 0.0f;
 			cudaEventElapsedTime(&tMs, e0, e1);
 			cudaEventElapsedTime(&sMs, e1, e2);
@@ -588,11 +627,10 @@ int runFrame(pbr_ctx* ctx, const FrameParams& P, int nPaths) {
 		CK(cudaGetLastError());
 		return PBR_OK;
 	}
-	int rc = ensureWave(ctx, (size_t) nPaths);
+	pbr_ctx::WaveSet& T = ctx->sets[ctx->launchSet];
+	int rc = ensureWave(ctx, T, (size_t) nPaths);
 	if (rc) return rc;
-	WaveState W = ctx->wave;
-	W.hitN = PHONG ? ctx->hitN : nullptr;
-	return runWavefront<BRDF, SHADOW, PHONG>(ctx, P, W, nPaths);
+	return runWavefront<BRDF, SHADOW, PHONG>(ctx, P, T, ctx->launchStream ? ctx->launchStream : ctx->stream, nPaths);
 }
 
 /* ---- NCCL, loaded on demand ---------------------------------------------------------------------------- */
@@ -735,13 +773,11 @@ int pbr_create(int device, pbr_ctx** out) {
 	cudaEventCreate(&ctx->evStart);
 	cudaEventCreate(&ctx->evStop);
 	if (cudaMalloc(&ctx->stats, 8 * sizeof(unsigned long long)) != cudaSuccess ||
-	    cudaMalloc(&ctx->cursor64, sizeof(unsigned long long)) != cudaSuccess ||
-	    cudaMalloc(&ctx->qctl.ctrl, 8 * sizeof(uint32_t)) != cudaSuccess) {
+	    cudaMalloc(&ctx->cursor64, sizeof(unsigned long long)) != cudaSuccess) {
 		delete ctx;
 		return PBR_ERR_NO_DEVICE;
 	}
 	cudaMemset(ctx->stats, 0, 8 * sizeof(unsigned long long));
-	cudaMemset(ctx->qctl.ctrl, 0, 8 * sizeof(uint32_t));
 	if (const char* e = getenv("PBR_NODE_PHASE_MIN")) {
 		const int v = atoi(e);
 		if (v >= 1 && v <= 32) ctx->nodePhaseMin = v;
@@ -765,11 +801,9 @@ int pbr_destroy(pbr_ctx* ctx) {
 	for (Mem& m : ctx->mems) if (m.alive && m.dptr) cudaFree(m.dptr);
 	for (void* p : ctx->pinned) cudaFreeHost(p);
 	cudaFree(ctx->nodes); cudaFree(ctx->tris); cudaFree(ctx->wide); cudaFree(ctx->faceLeaf);
-	WaveState& W = ctx->wave;
-	cudaFree(W.rayO); cudaFree(W.rayD); cudaFree(W.colS); cudaFree(W.finF); cudaFree(W.misc); cudaFree(W.dbg); cudaFree(ctx->hitN);
-	cudaFree(ctx->qctl.queue[0]); cudaFree(ctx->qctl.queue[1]); cudaFree(ctx->qctl.ctrl);
+	for (pbr_ctx::WaveSet& T : ctx->sets) freeWaveSet(T);
+	if (ctx->evBatchStart) cudaEventDestroy(ctx->evBatchStart);
 	cudaFree(ctx->stats); cudaFree(ctx->cursor64);
-	cudaFree(ctx->shadowO); cudaFree(ctx->shadowD); cudaFree(ctx->shadowQ);
 	cudaEventDestroy(ctx->evStart); cudaEventDestroy(ctx->evStop);
 	for (const pbr_ctx::Timed& t : ctx->timedInFlight) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
 	for (cudaEvent_t e : ctx->eventPool) cudaEventDestroy(e);
@@ -1036,6 +1070,24 @@ badsize:
 	return fail(ctx, PBR_ERR_INVALID, "clSetKernelArg: wrong argument size for slot " + std::to_string(index));
 }
 
+/* Everything a launch needs that is built once per scene and cached: the repacked scene, the "can a path be extended"
+ * answer, the walk (and with it the 4-wide BVH).  Work goes to the context's stream. */
+static int prepareLaunch(pbr_ctx* ctx) {
+	KernelArgs& a = ctx->args;
+	const pbr_defines& D = ctx->defines;
+	const bool phong = (D.phongtess == 1);
+	int rc = ensureScene(ctx, a.mem[4], a.mem[5], a.mem[7], D.bvh_num_nodes, phong, a.mem[6], a.mem[8]);
+	if (rc) return rc;
+	rc = updateCanExtendDepth(ctx, a.mem[9], D.brdf);
+	if (rc) return rc;
+	/* the reference's visit counters are observable through the debug image only */
+	bool useWide = false;
+	rc = chooseTraversal(ctx, ctx->debugImage || phong, &useWide);
+	if (rc) return rc;
+	ctx->launchUseWide = useWide;
+	return PBR_OK;
+}
+
 /* n consecutive frames (n <= PT_MAX_BATCH) in one pass over the device: frame f uses seeds[f] / weights[f];
  * frame 0 reads hIn, every later frame reads what the one before wrote to hOut. */
 static int launchFrames(pbr_ctx* ctx, int n, const float* seeds, const float* weights, pbr_mem hIn, pbr_mem hOut) {
@@ -1043,10 +1095,7 @@ static int launchFrames(pbr_ctx* ctx, int n, const float* seeds, const float* we
 	const pbr_defines& D = ctx->defines;
 
 	const bool phong = (D.phongtess == 1);
-	int rc = ensureScene(ctx, a.mem[4], a.mem[5], a.mem[7], D.bvh_num_nodes, phong, a.mem[6], a.mem[8]);
-	if (rc) return rc;
-
-	rc = updateCanExtendDepth(ctx, a.mem[9], D.brdf);
+	int rc = prepareLaunch(ctx);
 	if (rc) return rc;
 	Mem* materials = getMem(ctx, a.mem[9]);
 	Mem* lights = getMem(ctx, a.mem[10]);
@@ -1061,10 +1110,7 @@ static int launchFrames(pbr_ctx* ctx, int n, const float* seeds, const float* we
 	if ((size_t) D.num_lights * sizeof(pbr_light) > lights->bytes)
 		return fail(ctx, PBR_ERR_INVALID, "NUM_LIGHTS exceeds the lights buffer");
 
-	/* the reference's visit counters are observable through the debug image only */
-	bool useWide = false;
-	rc = chooseTraversal(ctx, ctx->debugImage || phong, &useWide);
-	if (rc) return rc;
+	const bool useWide = ctx->launchUseWide;
 	ctx->lastTraversal = useWide ? 1 : 0;
 
 	FrameParams P;
@@ -1099,10 +1145,13 @@ static int launchFrames(pbr_ctx* ctx, int n, const float* seeds, const float* we
 	P.imageIn = (const float4*) imageIn->dptr;
 	P.imageOut = (float4*) imageOut->dptr;
 	P.imageDebug = ctx->debugImage ? (float4*) imageDebug->dptr : nullptr;
+	P.frameOut = ctx->launchFrameOut;
 	P.stats = ctx->stats;
 
 	const int nPaths = D.img_width * (P.y1 - P.y0);
 	const bool shadow = (D.shadow_rays == 1);
+	ctx->lastFrameParams = P;
+	ctx->lastNumPaths = nPaths;
 
 	const int variant = (D.brdf == 1 ? 4 : 0) | (shadow ? 2 : 0) | (phong ? 1 : 0);
 
@@ -1188,12 +1237,83 @@ int pbr_kernel_launch_batch(pbr_ctx* ctx, pbr_kernel k, int32_t n_frames, const 
 	if (rc) return rc;
 	CK(cudaEventRecord(ctx->evStart, ctx->stream));
 	const bool depthOfField = a.cam.focusPoint.x >= 0 && a.cam.focusPoint.y >= 0;
-	if (!depthOfField) {
+	Mem* outM = getMem(ctx, hOut);
+	if (!outM) return fail(ctx, PBR_ERR_INVALID, "pathTracing: imageOut is not live");
+	const size_t outF4 = outM->bytes / 16;
+	const bool combine = ctx->batchCombineMode >= 0 && ctx->comm != nullptr;
+	/* Several frames in flight: a frame's rays do not depend on the frame before it -- only the final mix of a pixel does
+	 * (setColors reads the previous image, pt_rgb.cl:15).  So consecutive frames are traced on streams of their own, each
+	 * into its own wave state, finished pixels leave their radiance in a per-frame buffer, and mixFrameKernel folds the
+	 * frames into imageOut in order on the context's stream: the long tail of one frame's traverse launches is filled with
+	 * the next frame's work.  Same operands, same operations, same bits.  Not with the megakernel (nothing to overlap),
+	 * the debug image (written by the shade kernels) or depth of field (a frame reads the previous image when it starts). */
+	const int inFlight = (ctx->framesInFlight < n_frames ? ctx->framesInFlight : n_frames);
+	const bool overlap = !depthOfField && inFlight > 1 && !ctx->debugImage && (ctx->pipelineAuto || ctx->pipeline == 0);
+	if (!depthOfField && overlap) {
+		rc = prepareLaunch(ctx);                   /* (scene repack, wide BVH: on the context's stream, before the fork) */
+		if (rc) return rc;
+		if (!ctx->evBatchStart) CK(cudaEventCreateWithFlags(&ctx->evBatchStart, cudaEventDisableTiming));
+		CK(cudaEventRecord(ctx->evBatchStart, ctx->stream));
+		const int savedPipeline = ctx->pipeline;
+		const bool savedAuto = ctx->pipelineAuto;
+		ctx->pipeline = 0;
+		ctx->pipelineAuto = false;
+		for (int f = 0; f < n_frames && rc == PBR_OK; f++) {
+			pbr_ctx::WaveSet& T = ctx->sets[f % inFlight];
+			if (!T.stream) {
+				CK(cudaStreamCreateWithFlags(&T.stream, cudaStreamNonBlocking));
+				CK(cudaEventCreateWithFlags(&T.evTraced, cudaEventDisableTiming));
+				CK(cudaEventCreateWithFlags(&T.evConsumed, cudaEventDisableTiming));
+			}
+			if (outF4 > T.frameOutCap) {
+				cudaFree(T.frameOut);
+				T.frameOut = nullptr;
+				T.frameOutCap = 0;
+				CK(cudaMalloc(&T.frameOut, outF4 * 16));
+				T.frameOutCap = outF4;
+			}
+			/* this set's stream: behind everything before the batch, and behind the mix that last read its buffer */
+			if (f < inFlight) CK(cudaStreamWaitEvent(T.stream, ctx->evBatchStart, 0));
+			if (T.consumedPending) { CK(cudaStreamWaitEvent(T.stream, T.evConsumed, 0)); T.consumedPending = false; }
+			ctx->launchSet = f % inFlight;
+			ctx->launchStream = T.stream;
+			ctx->launchFrameOut = T.frameOut;
+			rc = launchFrames(ctx, 1, seeds + f, pixel_weights + f, f == 0 ? hIn : hOut, hOut);
+			ctx->launchSet = 0;
+			ctx->launchStream = nullptr;
+			ctx->launchFrameOut = nullptr;
+			if (rc) break;
+			CK(cudaEventRecord(T.evTraced, T.stream));
+			CK(cudaStreamWaitEvent(ctx->stream, T.evTraced, 0));
+			if (outM->combinePending) { CK(cudaStreamWaitEvent(ctx->stream, outM->evCombined, 0)); outM->combinePending = false; }
+			{
+				LaunchScope ls(ctx, K_SHADE);
+				mixFrameKernel<<<ctx->smCount * 8, 256, 0, ctx->stream>>>(ctx->lastFrameParams, T.frameOut, ctx->lastNumPaths);
+			}
+			CK(cudaGetLastError());
+			CK(cudaEventRecord(T.evConsumed, ctx->stream));
+			T.consumedPending = true;
+			if (combine) {
+				rc = pbr_frame_combine(ctx, hOut, ctx->batchCombineMode, ctx->batchCombineOut[(ctx->batchCombineParity + f) & 1]);
+				outM = getMem(ctx, hOut);
+			}
+		}
+		ctx->pipeline = savedPipeline;
+		ctx->pipelineAuto = savedAuto;
+		if (rc) return rc;
+	}
+	else if (!depthOfField) {
 		/* pixels are independent of each other, so everything after frame 0 can run in place in imageOut, frame after
 		 * frame (the rays of one bounce of one frame stay together, which the caches like) */
 		for (int f = 0; f < n_frames; f++) {
+			if (f > 0 && outM->combinePending) { CK(cudaStreamWaitEvent(ctx->stream, outM->evCombined, 0)); outM->combinePending = false; }
 			rc = launchFrames(ctx, 1, seeds + f, pixel_weights + f, f == 0 ? hIn : hOut, hOut);
 			if (rc) return rc;
+			if (combine) {
+				rc = pbr_frame_combine(ctx, hOut, ctx->batchCombineMode, ctx->batchCombineOut[(ctx->batchCombineParity + f) & 1]);
+				if (rc) return rc;
+				outM = getMem(ctx, hOut);
+			}
 		}
 	}
 	else {
@@ -1212,8 +1332,17 @@ int pbr_kernel_launch_batch(pbr_ctx* ctx, pbr_kernel k, int32_t n_frames, const 
 		pbr_mem prev = hIn;
 		for (int f = 0; f < n_frames; f++) {
 			const pbr_mem dst = ((n_frames - 1 - f) % 2 == 0) ? hOut : ctx->scratchImage;
+			rc = waitForCombine(ctx, getMem(ctx, dst));
+			if (rc) return rc;
 			rc = launchFrames(ctx, 1, seeds + f, pixel_weights + f, prev, dst);
 			if (rc) return rc;
+			if (combine) {
+				CK(cudaStreamSynchronize(ctx->stream));          /* (depth of field reads what the gather writes: no overlap here) */
+				rc = pbr_frame_combine(ctx, dst, ctx->batchCombineMode, ctx->batchCombineOut[(ctx->batchCombineParity + f) & 1]);
+				if (rc) return rc;
+				rc = pbr_comm_fence(ctx);
+				if (rc) return rc;
+			}
 			prev = dst;
 		}
 	}
@@ -1284,6 +1413,7 @@ int pbr_set_tuning(pbr_ctx* ctx, const char* key, int32_t value) {
 	else if (k == "wide_refill_min" && value >= 1 && value <= 32) ctx->wideRefillMin = value;
 	else if (k == "wide_top" && value >= 1 && value <= 1365) ctx->wideTopBudget = value;      /* rebuilt at the next launch */
 	else if (k == "shadow_stage" && (value == 0 || value == 1)) ctx->shadowStage = value;
+	else if (k == "frames_in_flight" && value >= 1 && value <= pbr_ctx::MAX_IN_FLIGHT) ctx->framesInFlight = value;
 	else return fail(ctx, PBR_ERR_INVALID, "pbr_set_tuning: unknown key or value out of range: " + k);
 	return PBR_OK;
 }
@@ -1477,6 +1607,15 @@ int pbr_frame_combine(pbr_ctx* ctx, pbr_mem image, int32_t mode, pbr_mem out) {
 		pending->combinePending = true;
 	}
 	ctx->combines++;
+	return PBR_OK;
+}
+
+int pbr_set_batch_combine(pbr_ctx* ctx, int32_t mode, pbr_mem out0, pbr_mem out1, int32_t first_parity) {
+	if (!ctx || mode < -1 || mode > PBR_COMBINE_ROWS) return PBR_ERR_INVALID;
+	ctx->batchCombineMode = mode;
+	ctx->batchCombineOut[0] = out0;
+	ctx->batchCombineOut[1] = out1;
+	ctx->batchCombineParity = first_parity & 1;
 	return PBR_OK;
 }
 

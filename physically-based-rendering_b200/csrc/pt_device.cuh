@@ -82,6 +82,8 @@ struct FrameParams {
 	const float4* imageIn;
 	float4* imageOut;
 	float4* imageDebug;           /* may be NULL */
+	float4* frameOut;             /* != NULL (frames in flight): a finished pixel leaves (its frame's radiance, focus) here
+	                                 and mixFrameKernel folds it into the accumulation image later, in frame order */
 	unsigned long long* stats;    /* 6 counters, see pbr_stats */
 	/* A launch may cover several consecutive frames (pbr_kernel_launch_batch): frame f of the batch uses
 	 * frameSeed[f] / frameWeight[f]; f = 0 reads imageIn, later frames read what the frame before wrote to
@@ -1219,6 +1221,10 @@ __device__ __forceinline__ void finishPixel(const FrameParams& P, PathState& s, 
 		fc = v3(fc.x / n, fc.y / n, fc.z / n);
 	}
 	const size_t o = (size_t) py * P.width + px;
+	if (P.frameOut) {
+		P.frameOut[o] = make_float4(fc.x, fc.y, fc.z, s.focus);
+		return;
+	}
 	const float4 in = (s.frame == 0u) ? P.imageIn[o] : P.imageOut[o];
 	const float pixelWeight = P.frameWeight[s.frame];
 	float4 out;

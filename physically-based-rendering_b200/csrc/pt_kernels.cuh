@@ -103,6 +103,25 @@ __global__ void __launch_bounds__(256) raygenKernel(const FrameParams P, const W
 	}
 }
 
+/* setColors (pt_rgb.cl:9-21) for a frame whose pixels were finished into FrameParams::frameOut: the same mix on the
+ * same operands, only later -- once the frame before it has been folded in. */
+__global__ void __launch_bounds__(256) mixFrameKernel(const FrameParams P, const float4* __restrict__ frameOut, const int nPaths) {
+	const int stride = gridDim.x * blockDim.x;
+	const float pixelWeight = P.frameWeight[0];
+	for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < nPaths; p += stride) {
+		int px, py;
+		pixelOf(P, p, px, py);
+		const size_t o = (size_t) py * P.width + px;
+		const float4 in = P.imageIn[o], fr = frameOut[o];
+		float4 out;
+		out.x = pm::mix_(fr.x, in.x, pixelWeight);
+		out.y = pm::mix_(fr.y, in.y, pixelWeight);
+		out.z = pm::mix_(fr.z, in.z, pixelWeight);
+		out.w = fr.w;
+		P.imageOut[o] = out;
+	}
+}
+
 /* ------------------------------------------------------------------ traverse */
 
 /*

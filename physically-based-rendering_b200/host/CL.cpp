@@ -282,6 +282,11 @@ void CL::frameCombine( cl_mem image, int mode, cl_mem out ) {
 }
 
 
+void CL::setBatchCombine( int mode, cl_mem out0, cl_mem out1, int firstParity ) {
+	this->checkError( pbr_set_batch_combine( mContext, mode, out0, out1, firstParity ), "pbr_set_batch_combine" );
+}
+
+
 void CL::commFence() {
 	this->checkError( pbr_comm_fence( mContext ), "pbr_comm_fence" );
 }

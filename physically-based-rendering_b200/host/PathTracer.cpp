@@ -272,11 +272,11 @@ void PathTracer::renderFrames( cl_uint frames ) {
 	}
 	if( frames == 0 ) { return; }
 	mCL->setDebugImage( false );
-	if( mWorld > 1 && mSharding != SHARD_NONE ) {
-		/* every frame is completed across the ranks (progressive display): frame by frame through the ping-pong pair */
-		for( cl_uint i = 0; i < frames; i++ ) { this->launchFrame(); }
-		return;
-	}
+	/* with ranks, every frame of the batch is completed across the ranks by the library (progressive display) */
+	const bool combine = mWorld > 1 && mSharding != SHARD_NONE;
+	mCL->setBatchCombine( combine ? ( mSharding == SHARD_SPP ? PBR_COMBINE_SPP : PBR_COMBINE_ROWS ) : -1,
+		mBufTextureDisplay[0], mBufTextureDisplay[1], (int) ( mCombines & 1 ) );
+	if( combine ) { mCombines += frames; }
 	this->updateEyeBuffer();
 	if( mHaveOutput ) {
 		std::swap( mBufTextureIn, mBufTextureOut );

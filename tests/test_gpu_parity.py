@@ -457,3 +457,36 @@ def test_ordered_walk_top_of_tree_budgets(device, oracle):
             assert np.array_equal(got["t"].view(np.uint32), want["t"].view(np.uint32)), top
     finally:
         device.setTuning("wide_top", 21)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# Several frames in flight (pbr_kernel_launch_batch, tuning "frames_in_flight"): consecutive frames traced on
+# streams of their own, mixed into the image in order -- the same bits as one frame after the other.
+
+@pytest.mark.parametrize("brdf,shadow,samples", [(1, 0, 1), (0, 1, 2)])
+@pytest.mark.parametrize("traversal", [0, 1])
+def test_frames_in_flight_same_bits(device, suzanne, brdf, shadow, samples, traversal):
+    p = Hh.Prepared(suzanne, 136, 88, brdf=brdf, shadow_rays=shadow, samples=samples, max_depth=4)
+    ds = Hh.DeviceScene(device, p)
+    want, _, wstats = p.oracle_frames(7)
+    device.setDebugImage(False)
+    device.setTraversal(traversal)
+    try:
+        for n in (1, 2, 3, 4):
+            device.setTuning("frames_in_flight", n)
+            device.stats(reset=True)
+            got, _ = ds.frames_batch(7)
+            st = device.stats(reset=True)
+            assert Hh.images_equal(got, want), "frames in flight: %d" % n
+            assert int(st[0]) + int(st[1]) == int(wstats[0]) + int(wstats[1])
+            # ... and continuing an accumulated image, with a tile set
+            start, _ = ds.frames_batch(3)
+            device.setTileStripes(4, 2, 1)
+            part, _ = ds.frames_batch(4, image=start.copy(), first=3)
+            device.setTileStripes(0)
+            rows = [y for y in range(p.H) if (y // 4) % 2 == 1]
+            assert Hh.images_equal(part[rows], want[rows]), "frames in flight: %d, stripes" % n
+    finally:
+        device.setTuning("frames_in_flight", 4)
+        device.setTraversal(-1)
+        device.setDebugImage(True)

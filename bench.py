@@ -251,7 +251,6 @@ def run_ours(args):
         r.set_traversal(args.traversal)
         d = r.device()
         d.setStream(torch.cuda.current_stream().cuda_stream)
-        d.profileEnable(True)
         if world > 1:
             r.set_ranks(rank, world, new_comm_id(), sharding)
         return r, d, load_s
@@ -269,18 +268,25 @@ def run_ours(args):
     pinned = torch.empty((H, W, 4), dtype=torch.float32).pin_memory()
     pinned_np = pinned.numpy()
 
-    def step_e2e(last=False):
+    FRAMES_IN_FLIGHT = 4                 # the library's default: consecutive frames of a batch traced concurrently
+    AHEAD = 3 if world == 1 else 1       # frames traced beyond the one being copied out (with ranks: two display images)
+
+    def run_e2e(steps):
         # one generateImage() per frame, every frame read back into pinned host memory; with render-ahead the next
-        # frame is traced while this one is copied.  The accumulation simply continues from step to step (a reset would
-        # discard the frame traced ahead), and the very last call switches render-ahead off first, so that no frame is
-        # traced that is not delivered.  N > 1: rank 0's host is the one consumer of the combined frame.
-        for i in range(SPP):
+        # frames are traced while this one is copied.  The accumulation simply continues from step to step (a reset
+        # would discard the frames traced ahead), and render-ahead is switched off AHEAD calls before the end, so that
+        # exactly steps * SPP frames are traced and every one of them is delivered.  N > 1: rank 0's host is the one
+        # consumer of the combined frame.
+        total = steps * SPP
+        r.set_render_ahead(AHEAD)
+        for j in range(total):
             if rank == 0:
-                if last and i == SPP - 1:
-                    r.set_render_ahead(False)
+                if j == total - AHEAD:
+                    r.set_render_ahead(0)
                 r.generate_image(out=pinned_np)
             else:
                 r.render_frames(1)
+        r.set_render_ahead(0)
 
     # ---- device-resident timing ----------------------------------------------------------------
     for _ in range(args.warmup):
@@ -294,11 +300,11 @@ def run_ours(args):
     ms_local = time_steps(torch, dist, world, step_resident, args.steps, r.comm_fence)
     clocks = sampler.result()
     ms_total = max_over_ranks(ms_local)
-    stats_local = dev.stats(reset=True).astype(np.float64)
-    prof = dev.profileRead(reset=True)
+    stats_timed = dev.stats(reset=True).astype(np.float64)
+    prof_timed = dev.profileRead(reset=True)
     tinfo = dev.traversalInfo(reset=True)
-    stats_all = sum_over_ranks(stats_local)
-    launches_all = float(sum_over_ranks(np.array([prof["launches"]], np.float64))[0])
+    stats_all = sum_over_ranks(stats_timed)
+    launches_all = float(sum_over_ranks(np.array([prof_timed["launches"]], np.float64))[0])
     rays_all = stats_all[0] + stats_all[1]
     value = rays_all / (ms_total * 1e-3) / 1e6
     frames_all = args.steps * SPP * (1 if tiles else world)
@@ -307,6 +313,21 @@ def run_ours(args):
     pipeline = dev.pipelineInUse()
 
     # ---- roofline of the dominant kernel (this rank's traverse launches) -------------------------
+    # The timed region above keeps several frames in flight: kernels of consecutive frames share the device, so the
+    # duration of ONE launch cannot be read off there.  The same step is therefore run once more with one frame after
+    # the other (frames_in_flight = 1) and every launch bracketed by CUDA events on its stream.
+    dev.setTuning("frames_in_flight", 1)
+    dev.profileEnable(True)
+    step_resident()
+    r.finish()
+    dev.stats(reset=True)
+    dev.profileRead(reset=True)
+    k_serial = max(3, args.steps // 3)
+    ms_serial = time_steps(torch, dist, world, step_resident, k_serial, r.comm_fence)
+    stats_local = dev.stats(reset=True).astype(np.float64)
+    prof = dev.profileRead(reset=True)
+    dev.profileEnable(False)
+    dev.setTuning("frames_in_flight", FRAMES_IN_FLIGHT)
     peak, peak_src = measured_peak()
     if walk == 1:
         kernel = "traverseWideKernel"
@@ -336,8 +357,10 @@ def run_ours(args):
         "launches": int(prof["traverse_launches"]),
         "avg_launch_ms": round(trav_ms / max(1, prof["traverse_launches"]), 4),
         "algorithmic_bytes_per_launch": round(algo_bytes / max(1, prof["traverse_launches"])),
-        "kernel_share_of_step": round(trav_ms / ms_local, 4),
-        "shade_share_of_step": round(prof["shade_ms"] / ms_local, 4),
+        "measured_on": "%d steps with one frame after the other (frames_in_flight = 1): %.3f ms per step, %.1f Mrays/s" % (
+            k_serial, ms_serial / k_serial, (stats_local[0] + stats_local[1]) / (ms_serial * 1e-3) / 1e6),
+        "kernel_share_of_step": round(trav_ms / ms_serial, 4),
+        "shade_share_of_step": round(prof["shade_ms"] / ms_serial, 4),
         "nodes_per_ray": round(stats_local[2] / max(1.0, stats_local[0]), 2),
         "tri_tests_per_ray": round(stats_local[3] / max(1.0, stats_local[0]), 2),
         "rewalked_rays": int(tinfo["rewalked_rays"]),
@@ -351,20 +374,29 @@ def run_ours(args):
             step_resident()
         r.finish()
         dev.stats(reset=True)
-        dev.profileRead(reset=True)
         k = max(3, args.steps // 4)
         ms_ref = time_steps(torch, dist, world, step_resident, k, r.comm_fence)
         st = dev.stats(reset=True).astype(np.float64)
+        dev.setTuning("frames_in_flight", 1)
+        dev.profileEnable(True)
+        step_resident()
+        r.finish()
+        dev.stats(reset=True)
+        dev.profileRead(reset=True)
+        time_steps(torch, dist, world, step_resident, k, r.comm_fence)
+        st1 = dev.stats(reset=True).astype(np.float64)
         pr = dev.profileRead(reset=True)
-        ref_bytes = ALGO_BYTES_PER_NODE * st[2] + ALGO_BYTES_PER_TRI * st[3]
+        dev.profileEnable(False)
+        dev.setTuning("frames_in_flight", FRAMES_IN_FLIGHT)
+        ref_bytes = ALGO_BYTES_PER_NODE * st1[2] + ALGO_BYTES_PER_TRI * st1[3]
         reference_walk = {
             "value": round((st[0] + st[1]) / (ms_ref * 1e-3) / 1e6, 2), "unit": "Mrays/s", "ms_per_step": round(ms_ref / k, 3),
             "steps": k, "kernel": "traverseKernel", "nodes_per_ray": round(st[2] / max(1.0, st[0]), 2),
             "tri_tests_per_ray": round(st[3] / max(1.0, st[0]), 2),
             "algorithmic_gbs": round(ref_bytes / (pr["traverse_ms"] * 1e-3) / 1e9, 1),
             "frac_of_peak": round(ref_bytes / (pr["traverse_ms"] * 1e-3) / 1e9 / peak, 4),
-            "what": "pbr_set_traversal(0): visit counters and debug image bit-exact as well; 32 B x nodes + 64 B x triangle tests "
-                    "(SURVEY.md 8d) over the summed traverse time",
+            "what": "pbr_set_traversal(0): visit counters and debug image bit-exact as well; algorithmic_gbs = 32 B x nodes + 64 B x "
+                    "triangle tests (SURVEY.md 8d) over the summed traverseKernel time of steps run one frame after the other",
         }
         r.set_traversal(args.traversal)
 
@@ -372,18 +404,14 @@ def run_ours(args):
     e2e = None
     if not args.no_e2e:
         r.reset_sample_count()
-        r.set_render_ahead(True)
-        for i in range(max(1, args.warmup // 2)):
-            step_e2e(last=True)
+        run_e2e(max(1, args.warmup // 2))
         r.finish()
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
         dev.stats(reset=True)
-        r.set_render_ahead(True)
         t0 = time.perf_counter()
-        for i in range(args.steps):
-            step_e2e(last=(i == args.steps - 1))
+        run_e2e(args.steps)
         r.finish()
         torch.cuda.synchronize()
         e2e_s = max_over_ranks(time.perf_counter() - t0)
@@ -394,11 +422,10 @@ def run_ours(args):
             "d2h_bytes_per_step": SPP * W * H * 16,            # accumulated frame per frame (N > 1: rank 0 reads it)
             "ms_per_step": round(e2e_s * 1e3 / args.steps, 3),
             "api": "PathTracer::generateImage (libpbr_host.so) per frame, every frame into a pinned host image, "
-                   "setRenderAhead(true): the next frame is traced while this one is copied" + (
+                   "setRenderAhead(%d): the next frames are traced while this one is copied" % AHEAD + (
                        "; N > 1: PathTracer::setRanks, every frame ends with the library's own collective, rank 0's host "
                        "receives every combined frame" if world > 1 else ""),
         }
-        r.set_render_ahead(False)
 
     # ---- strong scaling of ONE image (N > 1): rows of every frame sharded in interleaved stripes ----
     strong = None
@@ -457,6 +484,7 @@ def run_ours(args):
                 "traversal": WALK_NAMES[walk] + ("; chosen automatically: no debug image is requested" if args.traversal < 0 else "; forced"),
                 "wide_bvh": {"nodes": tinfo["wide_nodes"], "depth": tinfo["wide_depth"], "staged_in_shared_memory": tinfo["wide_top"],
                              "build_ms": round(tinfo["wide_build_ms"], 1)} if walk == 1 else None,
+                "frames_in_flight": FRAMES_IN_FLIGHT,
                 "pipeline": {0: "wavefront", 1: "megakernel", -1: "wavefront (batched frames)"}[pipeline] +
                             " (chosen by measurement on the first frames)",
                 "l2_policy": "working set > L2: scene %.0f MB (wide nodes + triangles%s), path state %.0f MB, images %.0f MB" % (

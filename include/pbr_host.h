@@ -76,8 +76,9 @@ int pbrh_renderer_set_seed_schedule(pbrh_renderer* r, uint32_t stride, uint32_t 
 /* simulated clock: frame with global index g gets the seed the reference derives from its wall clock at
  * t = ms * (g + 1) milliseconds, (ms * (g + 1)) * 0.001f (PathTracer.cpp:78-82); 0 = off */
 int pbrh_renderer_set_frame_time_ms(pbrh_renderer* r, uint32_t ms);
-/* generate_image starts tracing the next frame before it waits for the copy of this one (PathTracer::setRenderAhead) */
-int pbrh_renderer_set_render_ahead(pbrh_renderer* r, int32_t enabled);
+/* generate_image starts tracing the next `depth` (0..3) frames before it waits for the copy of this one
+ * (PathTracer::setRenderAhead); 0 = off */
+int pbrh_renderer_set_render_ahead(pbrh_renderer* r, int32_t depth);
 int pbrh_renderer_set_tile(pbrh_renderer* r, int32_t y0, int32_t y1);
 /* interleaved stripes of rows for load balance (pbr_set_tile_stripes); stripe_rows <= 0 = off */
 int pbrh_renderer_set_tile_stripes(pbrh_renderer* r, int32_t stripe_rows, int32_t world, int32_t rank);

@@ -37,6 +37,9 @@ struct Mem {
 	uint64_t epoch = 0;               /* bumped whenever the contents may have changed (create, update, free) */
 	cudaEvent_t evCombined = nullptr; /* pbr_frame_combine still reads (or all-gathers into) this image until then */
 	bool combinePending = false;
+	cudaEvent_t evWritten = nullptr;  /* recorded on the context's stream behind the last launch / copy that wrote this image:
+	                                     an asynchronous read-back waits for THIS, not for whatever has been queued since */
+	bool writtenValid = false;
 };
 
 struct KernelArgs {
@@ -144,7 +147,9 @@ struct pbr_ctx {
 	enum { MAX_IN_FLIGHT = 4 };
 	WaveSet sets[MAX_IN_FLIGHT];
 	int framesInFlight = 4;                    /* tuning "frames_in_flight": 1 -> 2 -> 3 -> 4 = 1356 -> 1548 -> 1599 -> 1619 Mrays/s on C2 */
-	cudaEvent_t evBatchStart = nullptr;
+	cudaEvent_t evPrepared = nullptr;
+	uint64_t preparedVersion = ~0ull, preparedWide = ~0ull;
+	uint64_t overlapCounter = 0;               /* frames launched through launchOverlapped: picks the wave set */
 	int batchCombineMode = -1;                 /* pbr_set_batch_combine */
 	pbr_mem batchCombineOut[2] = {0, 0};
 	int batchCombineParity = 0;
@@ -296,6 +301,9 @@ int ensureScene(pbr_ctx* ctx, pbr_mem hBvh, pbr_mem hFacesV, pbr_mem hVertices, 
 		return PBR_OK;
 	}
 
+	/* frames still being traced on streams of their own read the arrays that are about to be rebuilt */
+	for (pbr_ctx::WaveSet& T : ctx->sets) if (T.stream) CK(cudaStreamSynchronize(T.stream));
+
 	const int numSrcNodes = (int) (bvh->bytes / sizeof(pbr_bvh_node));
 	if (numNodes > numSrcNodes) return fail(ctx, PBR_ERR_INVALID, "BVH_NUM_NODES exceeds the size of the bvh buffer");
 	if (numNodes > (1 << 24)) return fail(ctx, PBR_ERR_INVALID, "BVH_NUM_NODES exceeds 2^24: float-encoded indices are no longer exact");
@@ -355,6 +363,7 @@ int ensureScene(pbr_ctx* ctx, pbr_mem hBvh, pbr_mem hFacesV, pbr_mem hVertices, 
  * stays false and every launch keeps the reference-order walk; pbr_traversal_info tells why. */
 int ensureWide(pbr_ctx* ctx) {
 	if (ctx->wideBuilt && ctx->wideVersion == ctx->geometryVersion && ctx->wideBudgetBuilt == ctx->wideTopBudget) return PBR_OK;
+	for (pbr_ctx::WaveSet& T : ctx->sets) if (T.stream) CK(cudaStreamSynchronize(T.stream));
 	ctx->wideBuilt = true;
 	ctx->wideVersion = ctx->geometryVersion;
 	ctx->wideBudgetBuilt = ctx->wideTopBudget;
@@ -717,6 +726,14 @@ __global__ void unpackStripesKernel(float4* __restrict__ image, const float4* __
 	}
 }
 
+int markWritten(pbr_ctx* ctx, Mem* m) {
+	if (!m) return PBR_OK;
+	if (!m->evWritten) CK(cudaEventCreateWithFlags(&m->evWritten, cudaEventDisableTiming));
+	CK(cudaEventRecord(m->evWritten, ctx->stream));
+	m->writtenValid = true;
+	return PBR_OK;
+}
+
 /* A launch that overwrites an image waits for the combine that still reads it (frame k + 2 and the combine of frame k
  * share a buffer of PathTracer's ping-pong pair); with depth of field a frame also READS other pixels of imageIn, which
  * a row gather is still filling. */
@@ -802,7 +819,7 @@ int pbr_destroy(pbr_ctx* ctx) {
 	for (void* p : ctx->pinned) cudaFreeHost(p);
 	cudaFree(ctx->nodes); cudaFree(ctx->tris); cudaFree(ctx->wide); cudaFree(ctx->faceLeaf);
 	for (pbr_ctx::WaveSet& T : ctx->sets) freeWaveSet(T);
-	if (ctx->evBatchStart) cudaEventDestroy(ctx->evBatchStart);
+	if (ctx->evPrepared) cudaEventDestroy(ctx->evPrepared);
 	cudaFree(ctx->stats); cudaFree(ctx->cursor64);
 	cudaEventDestroy(ctx->evStart); cudaEventDestroy(ctx->evStop);
 	for (const pbr_ctx::Timed& t : ctx->timedInFlight) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
@@ -812,7 +829,7 @@ int pbr_destroy(pbr_ctx* ctx) {
 	if (ctx->commStream) cudaStreamDestroy(ctx->commStream);
 	if (ctx->evRendered) cudaEventDestroy(ctx->evRendered);
 	cudaFree(ctx->commSend); cudaFree(ctx->commRecv);
-	for (Mem& m : ctx->mems) if (m.evCombined) cudaEventDestroy(m.evCombined);
+	for (Mem& m : ctx->mems) { if (m.evCombined) cudaEventDestroy(m.evCombined); if (m.evWritten) cudaEventDestroy(m.evWritten); }
 	if (ctx->copyStream) { cudaStreamSynchronize(ctx->copyStream); cudaStreamDestroy(ctx->copyStream); }
 	if (ctx->evCopy) cudaEventDestroy(ctx->evCopy);
 	for (int i = 0; i < 8; i++) if (ctx->evAuto[i]) cudaEventDestroy(ctx->evAuto[i]);
@@ -908,6 +925,7 @@ int pbr_image_write(pbr_ctx* ctx, pbr_mem image, size_t width, size_t height, co
 	CK(cudaSetDevice(ctx->device));
 	CK(cudaMemcpyAsync(m->dptr, host, m->bytes, cudaMemcpyHostToDevice, ctx->stream));
 	CK(cudaStreamSynchronize(ctx->stream));
+	m->writtenValid = false;
 	return PBR_OK;
 }
 
@@ -935,8 +953,11 @@ int pbr_image_read_begin(pbr_ctx* ctx, pbr_mem image, size_t width, size_t heigh
 		CK(cudaStreamCreateWithFlags(&ctx->copyStream, cudaStreamNonBlocking));
 		CK(cudaEventCreateWithFlags(&ctx->evCopy, cudaEventDisableTiming));
 	}
-	CK(cudaEventRecord(ctx->evCopy, ctx->stream));
-	CK(cudaStreamWaitEvent(ctx->copyStream, ctx->evCopy, 0));
+	if (m->writtenValid) CK(cudaStreamWaitEvent(ctx->copyStream, m->evWritten, 0));
+	else if (!m->combinePending) {
+		CK(cudaEventRecord(ctx->evCopy, ctx->stream));
+		CK(cudaStreamWaitEvent(ctx->copyStream, ctx->evCopy, 0));
+	}
 	if (m->combinePending) CK(cudaStreamWaitEvent(ctx->copyStream, m->evCombined, 0));
 	CK(cudaMemcpyAsync(host, m->dptr, m->bytes, cudaMemcpyDeviceToHost, ctx->copyStream));
 	ctx->copyInFlight = true;
@@ -959,6 +980,7 @@ int pbr_image_copy(pbr_ctx* ctx, pbr_mem dst, pbr_mem src) {
 	if (!d || !s || d->bytes != s->bytes) return fail(ctx, PBR_ERR_INVALID, "pbr_image_copy: bad images");
 	CK(cudaSetDevice(ctx->device));
 	CK(cudaMemcpyAsync(d->dptr, s->dptr, s->bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+	d->writtenValid = false;
 	return PBR_OK;
 }
 
@@ -1085,6 +1107,13 @@ static int prepareLaunch(pbr_ctx* ctx) {
 	rc = chooseTraversal(ctx, ctx->debugImage || phong, &useWide);
 	if (rc) return rc;
 	ctx->launchUseWide = useWide;
+	/* frames traced on streams of their own start behind whatever the preparation has put on the context's stream */
+	if (!ctx->evPrepared) CK(cudaEventCreateWithFlags(&ctx->evPrepared, cudaEventDisableTiming));
+	if (ctx->preparedVersion != ctx->geometryVersion || ctx->preparedWide != (ctx->wideBuilt ? ctx->wideVersion : ~0ull)) {
+		CK(cudaEventRecord(ctx->evPrepared, ctx->stream));
+		ctx->preparedVersion = ctx->geometryVersion;
+		ctx->preparedWide = ctx->wideBuilt ? ctx->wideVersion : ~0ull;
+	}
 	return PBR_OK;
 }
 
@@ -1201,6 +1230,71 @@ static int launchFrames(pbr_ctx* ctx, int n, const float* seeds, const float* we
 	return rc;
 }
 
+/* Several frames in flight: a frame's rays do not depend on the frame before it -- only the final mix of a pixel does
+ * (setColors reads the previous image, pt_rgb.cl:15).  So consecutive frames are traced on streams of their own, each
+ * into its own wave state, finished pixels leave their radiance in a per-frame buffer, and mixFrameKernel folds the
+ * frames into imageOut in order on the context's stream: the long tail of one frame's traverse launches is filled with
+ * the next frame's work.  Same operands, same operations, same bits.  Not with the megakernel (nothing to overlap),
+ * the debug image (written by the shade kernels) or depth of field (a frame reads the previous image when it starts). */
+static bool overlapEligible(pbr_ctx* ctx) {
+	const KernelArgs& a = ctx->args;
+	if (ctx->framesInFlight < 2 || ctx->debugImage) return false;
+	if (a.cam.focusPoint.x >= 0 && a.cam.focusPoint.y >= 0) return false;
+	if (ctx->pipelineAuto) return ctx->autoState >= 6 ? ctx->autoChoice == 0 : false;    /* (while the two pipelines are being timed: no) */
+	return ctx->pipeline == 0;
+}
+
+static int launchOverlapped(pbr_ctx* ctx, const float* seed, const float* weight, pbr_mem hIn, pbr_mem hOut) {
+	Mem* outM = getMem(ctx, hOut);
+	if (!outM) return fail(ctx, PBR_ERR_INVALID, "pathTracing: imageOut is not live");
+	const size_t outF4 = outM->bytes / 16;
+	int rc = prepareLaunch(ctx);                   /* (scene repack, wide BVH: on the context's stream, before the fork) */
+	if (rc) return rc;
+	pbr_ctx::WaveSet& T = ctx->sets[ctx->overlapCounter % (uint64_t) ctx->framesInFlight];
+	ctx->overlapCounter++;
+	if (!T.stream) {
+		CK(cudaStreamCreateWithFlags(&T.stream, cudaStreamNonBlocking));
+		CK(cudaEventCreateWithFlags(&T.evTraced, cudaEventDisableTiming));
+		CK(cudaEventCreateWithFlags(&T.evConsumed, cudaEventDisableTiming));
+	}
+	if (outF4 > T.frameOutCap) {
+		if (T.consumedPending) { CK(cudaEventSynchronize(T.evConsumed)); T.consumedPending = false; }
+		cudaFree(T.frameOut);
+		T.frameOut = nullptr;
+		T.frameOutCap = 0;
+		CK(cudaMalloc(&T.frameOut, outF4 * 16));
+		T.frameOutCap = outF4;
+	}
+	/* this set's stream: behind the scene preparation, and behind the mix that last read its buffer */
+	CK(cudaStreamWaitEvent(T.stream, ctx->evPrepared, 0));
+	if (T.consumedPending) { CK(cudaStreamWaitEvent(T.stream, T.evConsumed, 0)); T.consumedPending = false; }
+	const int savedPipeline = ctx->pipeline;
+	const bool savedAuto = ctx->pipelineAuto;
+	ctx->pipeline = 0;
+	ctx->pipelineAuto = false;
+	ctx->launchSet = (int) (&T - ctx->sets);
+	ctx->launchStream = T.stream;
+	ctx->launchFrameOut = T.frameOut;
+	rc = launchFrames(ctx, 1, seed, weight, hIn, hOut);
+	ctx->launchSet = 0;
+	ctx->launchStream = nullptr;
+	ctx->launchFrameOut = nullptr;
+	ctx->pipeline = savedPipeline;
+	ctx->pipelineAuto = savedAuto;
+	if (rc) return rc;
+	CK(cudaEventRecord(T.evTraced, T.stream));
+	CK(cudaStreamWaitEvent(ctx->stream, T.evTraced, 0));
+	if (outM->combinePending) { CK(cudaStreamWaitEvent(ctx->stream, outM->evCombined, 0)); outM->combinePending = false; }
+	{
+		LaunchScope ls(ctx, K_SHADE);
+		mixFrameKernel<<<ctx->smCount * 8, 256, 0, ctx->stream>>>(ctx->lastFrameParams, T.frameOut, ctx->lastNumPaths);
+	}
+	CK(cudaGetLastError());
+	CK(cudaEventRecord(T.evConsumed, ctx->stream));
+	T.consumedPending = true;
+	return PBR_OK;
+}
+
 static int checkLaunchable(pbr_ctx* ctx, pbr_kernel k, uint32_t needed) {
 	if (!ctx || k != 1) return PBR_ERR_INVALID;
 	if (!ctx->programLoaded) return fail(ctx, PBR_ERR_NOT_READY, "execute before loadProgram");
@@ -1217,7 +1311,10 @@ int pbr_kernel_launch(pbr_ctx* ctx, pbr_kernel k) {
 	if (rc) return rc;
 	if (a.cam.focusPoint.x >= 0 && a.cam.focusPoint.y >= 0) { rc = waitForCombine(ctx, getMem(ctx, a.mem[11])); if (rc) return rc; }
 	CK(cudaEventRecord(ctx->evStart, ctx->stream));
-	rc = launchFrames(ctx, 1, &a.seed, &a.pixelWeight, a.mem[11], a.mem[12]);
+	if (overlapEligible(ctx)) rc = launchOverlapped(ctx, &a.seed, &a.pixelWeight, a.mem[11], a.mem[12]);
+	else rc = launchFrames(ctx, 1, &a.seed, &a.pixelWeight, a.mem[11], a.mem[12]);
+	if (rc) return rc;
+	rc = markWritten(ctx, getMem(ctx, a.mem[12]));
 	if (rc) return rc;
 	CK(cudaEventRecord(ctx->evStop, ctx->stream));
 	ctx->timed = true;
@@ -1239,68 +1336,19 @@ int pbr_kernel_launch_batch(pbr_ctx* ctx, pbr_kernel k, int32_t n_frames, const 
 	const bool depthOfField = a.cam.focusPoint.x >= 0 && a.cam.focusPoint.y >= 0;
 	Mem* outM = getMem(ctx, hOut);
 	if (!outM) return fail(ctx, PBR_ERR_INVALID, "pathTracing: imageOut is not live");
-	const size_t outF4 = outM->bytes / 16;
 	const bool combine = ctx->batchCombineMode >= 0 && ctx->comm != nullptr;
-	/* Several frames in flight: a frame's rays do not depend on the frame before it -- only the final mix of a pixel does
-	 * (setColors reads the previous image, pt_rgb.cl:15).  So consecutive frames are traced on streams of their own, each
-	 * into its own wave state, finished pixels leave their radiance in a per-frame buffer, and mixFrameKernel folds the
-	 * frames into imageOut in order on the context's stream: the long tail of one frame's traverse launches is filled with
-	 * the next frame's work.  Same operands, same operations, same bits.  Not with the megakernel (nothing to overlap),
-	 * the debug image (written by the shade kernels) or depth of field (a frame reads the previous image when it starts). */
-	const int inFlight = (ctx->framesInFlight < n_frames ? ctx->framesInFlight : n_frames);
-	const bool overlap = !depthOfField && inFlight > 1 && !ctx->debugImage && (ctx->pipelineAuto || ctx->pipeline == 0);
-	if (!depthOfField && overlap) {
-		rc = prepareLaunch(ctx);                   /* (scene repack, wide BVH: on the context's stream, before the fork) */
-		if (rc) return rc;
-		if (!ctx->evBatchStart) CK(cudaEventCreateWithFlags(&ctx->evBatchStart, cudaEventDisableTiming));
-		CK(cudaEventRecord(ctx->evBatchStart, ctx->stream));
-		const int savedPipeline = ctx->pipeline;
-		const bool savedAuto = ctx->pipelineAuto;
-		ctx->pipeline = 0;
-		ctx->pipelineAuto = false;
-		for (int f = 0; f < n_frames && rc == PBR_OK; f++) {
-			pbr_ctx::WaveSet& T = ctx->sets[f % inFlight];
-			if (!T.stream) {
-				CK(cudaStreamCreateWithFlags(&T.stream, cudaStreamNonBlocking));
-				CK(cudaEventCreateWithFlags(&T.evTraced, cudaEventDisableTiming));
-				CK(cudaEventCreateWithFlags(&T.evConsumed, cudaEventDisableTiming));
-			}
-			if (outF4 > T.frameOutCap) {
-				cudaFree(T.frameOut);
-				T.frameOut = nullptr;
-				T.frameOutCap = 0;
-				CK(cudaMalloc(&T.frameOut, outF4 * 16));
-				T.frameOutCap = outF4;
-			}
-			/* this set's stream: behind everything before the batch, and behind the mix that last read its buffer */
-			if (f < inFlight) CK(cudaStreamWaitEvent(T.stream, ctx->evBatchStart, 0));
-			if (T.consumedPending) { CK(cudaStreamWaitEvent(T.stream, T.evConsumed, 0)); T.consumedPending = false; }
-			ctx->launchSet = f % inFlight;
-			ctx->launchStream = T.stream;
-			ctx->launchFrameOut = T.frameOut;
-			rc = launchFrames(ctx, 1, seeds + f, pixel_weights + f, f == 0 ? hIn : hOut, hOut);
-			ctx->launchSet = 0;
-			ctx->launchStream = nullptr;
-			ctx->launchFrameOut = nullptr;
-			if (rc) break;
-			CK(cudaEventRecord(T.evTraced, T.stream));
-			CK(cudaStreamWaitEvent(ctx->stream, T.evTraced, 0));
-			if (outM->combinePending) { CK(cudaStreamWaitEvent(ctx->stream, outM->evCombined, 0)); outM->combinePending = false; }
-			{
-				LaunchScope ls(ctx, K_SHADE);
-				mixFrameKernel<<<ctx->smCount * 8, 256, 0, ctx->stream>>>(ctx->lastFrameParams, T.frameOut, ctx->lastNumPaths);
-			}
-			CK(cudaGetLastError());
-			CK(cudaEventRecord(T.evConsumed, ctx->stream));
-			T.consumedPending = true;
+	/* a batch is a request for throughput: while the measured pipeline choice is still open it takes the wavefront */
+	const bool overlap = !depthOfField && ctx->framesInFlight > 1 && !ctx->debugImage &&
+		(ctx->pipelineAuto ? !(ctx->autoState >= 6 && ctx->autoChoice == 1) : ctx->pipeline == 0);
+	if (overlap) {
+		for (int f = 0; f < n_frames; f++) {
+			rc = launchOverlapped(ctx, seeds + f, pixel_weights + f, f == 0 ? hIn : hOut, hOut);
+			if (rc) return rc;
 			if (combine) {
 				rc = pbr_frame_combine(ctx, hOut, ctx->batchCombineMode, ctx->batchCombineOut[(ctx->batchCombineParity + f) & 1]);
-				outM = getMem(ctx, hOut);
+				if (rc) return rc;
 			}
 		}
-		ctx->pipeline = savedPipeline;
-		ctx->pipelineAuto = savedAuto;
-		if (rc) return rc;
 	}
 	else if (!depthOfField) {
 		/* pixels are independent of each other, so everything after frame 0 can run in place in imageOut, frame after
@@ -1346,6 +1394,9 @@ int pbr_kernel_launch_batch(pbr_ctx* ctx, pbr_kernel k, int32_t n_frames, const 
 			prev = dst;
 		}
 	}
+	rc = markWritten(ctx, getMem(ctx, hOut));
+	if (rc) return rc;
+	if (Mem* scratch = getMem(ctx, ctx->scratchImage)) scratch->writtenValid = false;
 	CK(cudaEventRecord(ctx->evStop, ctx->stream));
 	ctx->timed = true;
 	return PBR_OK;

@@ -297,9 +297,10 @@ class Renderer:
         """Simulated clock: frame k gets the seed of the reference's wall clock at (k + 1) * ms milliseconds."""
         _ck(self.lib.pbrh_renderer_set_frame_time_ms(self.h, int(ms)), "setFrameTimeMs")
 
-    def set_render_ahead(self, enabled=True):
-        """generate_image() traces the next frame while this one is copied to the host (PathTracer::setRenderAhead)."""
-        _ck(self.lib.pbrh_renderer_set_render_ahead(self.h, int(enabled)), "setRenderAhead")
+    def set_render_ahead(self, depth=1):
+        """generate_image() traces the next `depth` (0..3; True = 1) frames while this one is copied to the host
+        (PathTracer::setRenderAhead)."""
+        _ck(self.lib.pbrh_renderer_set_render_ahead(self.h, int(depth)), "setRenderAhead")
 
     def set_seed_schedule(self, stride, offset):
         _ck(self.lib.pbrh_renderer_set_seed_schedule(self.h, stride, offset), "setSeedSchedule")

@@ -53,9 +53,7 @@ PathTracer::PathTracer( GLWidget* parent ) {
 	mSeedStride = 1;
 	mSeedOffset = 0;
 	mFrameTimeMs = 0;
-	mRenderAhead = false;
-	mAheadLaunched = false;
-	mSampleCountBeforeAhead = 0;
+	mRenderAhead = 0;
 	mHaveOutput = false;
 	mRank = 0;
 	mWorld = 1;
@@ -99,14 +97,26 @@ void PathTracer::clPathTracing( cl_float timeSinceStart ) {
 void PathTracer::launchFrame() {
 	this->updateEyeBuffer();
 	if( mHaveOutput ) {
-		std::swap( mBufTextureIn, mBufTextureOut );
-		mCL->setKernelArg( mKernelPathTracing, 11, sizeof( cl_mem ), &mBufTextureIn );
-		mCL->setKernelArg( mKernelPathTracing, 12, sizeof( cl_mem ), &mBufTextureOut );
+		this->advanceImages();
 	}
 	this->clPathTracing( this->nextSeed() );
 	mSampleCount++;
 	mHaveOutput = true;
 	this->combineFrame();
+}
+
+
+/**
+ * The previous output becomes the next input; the next output is the image behind it in the ring.  Two images (a swap)
+ * unless frames are traced ahead: a frame that has not been delivered yet keeps its image until it has been copied out.
+ */
+void PathTracer::advanceImages() {
+	size_t at = 0;
+	for( size_t i = 0; i < mImages.size(); i++ ) { if( mImages[i] == mBufTextureOut ) { at = i; } }
+	mBufTextureIn = mBufTextureOut;
+	mBufTextureOut = mImages[( at + 1 ) % mImages.size()];
+	mCL->setKernelArg( mKernelPathTracing, 11, sizeof( cl_mem ), &mBufTextureIn );
+	mCL->setKernelArg( mKernelPathTracing, 12, sizeof( cl_mem ), &mBufTextureOut );
 }
 
 
@@ -215,48 +225,72 @@ void PathTracer::generateImageInto( cl_float* target, cl_float* targetDebug ) {
 	if( targetDebug != NULL ) {
 		this->dropFrameAhead();          /* a frame traced ahead has no debug image */
 	}
-	if( !mAheadLaunched ) {
+	if( mAhead.empty() ) {
 		mCL->setDebugImage( targetDebug != NULL );
-		this->launchFrame();
+		this->launchAhead();
 	}
-	mAheadLaunched = false;
+	const AheadFrame f = mAhead.front();  /* the frame this call delivers */
 
-	if( mRenderAhead && targetDebug == NULL ) {
-		/* copy this frame out on the copy stream while the next one is traced: the next frame only reads
-		 * the image that is being copied (it is its imageIn) and writes the other one (with ranks: the copy waits for
-		 * this frame's collective, and the next frame's mean lands in the other display image) */
-		mCL->readImageOutputBegin( this->deliveredImage(), mWidth, mHeight, target );
-		mSampleCountBeforeAhead = mSampleCount;
+	if( mRenderAhead > 0 && targetDebug == NULL ) {
+		/* copy this frame out on the copy stream while the next ones are traced: they read the image that is being
+		 * copied (or one traced after it) and write images further down the ring (with ranks: the copy waits for this
+		 * frame's collective, and the next frame's mean lands in the other display image) */
+		mCL->readImageOutputBegin( f.delivered, mWidth, mHeight, target );
 		mCL->setDebugImage( false );
-		this->launchFrame();
-		mAheadLaunched = true;
+		while( mAhead.size() < 1 + (size_t) this->aheadDepth() ) { this->launchAhead(); }
 		mCL->readImageOutputEnd();
+		mAhead.pop_front();
 		return;
 	}
-	mCL->readImageOutput( this->deliveredImage(), mWidth, mHeight, target );
+	mAhead.pop_front();
+	mCL->readImageOutput( f.delivered, mWidth, mHeight, target );
 	if( targetDebug != NULL ) {
 		mCL->readImageOutput( mBufTextureDebug, mWidth, mHeight, targetDebug );
 	}
 }
 
 
-void PathTracer::setRenderAhead( bool enabled ) {
-	mRenderAhead = enabled;          /* a frame already traced ahead stays valid: the next call returns it */
+/** launchFrame() for a frame that is delivered later: remember what has to be undone if it is not wanted after all. */
+void PathTracer::launchAhead() {
+	AheadFrame f;
+	f.in = mBufTextureIn; f.out = mBufTextureOut; f.sampleCount = mSampleCount; f.combines = mCombines; f.haveOutput = mHaveOutput;
+	this->launchFrame();
+	f.delivered = this->deliveredImage();
+	mAhead.push_back( f );
+}
+
+
+/** How many frames are traced beyond the one being delivered: setRenderAhead's, one with ranks (two display images). */
+int PathTracer::aheadDepth() const {
+	return ( mWorld > 1 && mSharding != SHARD_NONE ) ? std::min( mRenderAhead, 1 ) : mRenderAhead;
+}
+
+
+void PathTracer::setRenderAhead( int depth ) {
+	/* frames already traced ahead stay valid: the next calls return them */
+	mRenderAhead = std::max( 0, std::min( depth, 3 ) );
+	while( mCL != NULL && mImages.size() < 2 + (size_t) mRenderAhead ) {
+		mImages.push_back( mCL->createImage2DWriteOnly( mWidth, mHeight ) );
+	}
 }
 
 
 /**
- * The frame traced ahead is not wanted after all: undo launchFrame's bookkeeping, so that the image returned
- * last is the current output again.  (The device work is simply wasted; stream order keeps it harmless.)
+ * Frames traced ahead are not wanted after all -- all of them, or all but the first `keep`: undo launchFrame's
+ * bookkeeping, so that the last frame kept (or delivered) is the current output again.  (The device work is simply wasted;
+ * stream order keeps it harmless.)
  */
-void PathTracer::dropFrameAhead() {
-	if( !mAheadLaunched ) { return; }
-	mAheadLaunched = false;
-	std::swap( mBufTextureIn, mBufTextureOut );
+void PathTracer::dropFrameAhead( size_t keep ) {
+	if( mAhead.size() <= keep ) { mAhead.resize( std::min( keep, mAhead.size() ) ); return; }
+	const AheadFrame f = mAhead[keep];      /* the state before the first frame that goes */
+	mAhead.resize( keep );
+	mBufTextureIn = f.in;
+	mBufTextureOut = f.out;
 	mCL->setKernelArg( mKernelPathTracing, 11, sizeof( cl_mem ), &mBufTextureIn );
 	mCL->setKernelArg( mKernelPathTracing, 12, sizeof( cl_mem ), &mBufTextureOut );
-	mSampleCount = mSampleCountBeforeAhead;
-	if( mWorld > 1 && mSharding != SHARD_NONE ) { mCombines--; }           /* its mean over ranks is not wanted either */
+	mSampleCount = f.sampleCount;
+	mCombines = f.combines;
+	mHaveOutput = f.haveOutput;
 }
 
 
@@ -266,10 +300,11 @@ void PathTracer::dropFrameAhead() {
  * deterministic schedule, instead of by the time the frames happen to take).
  */
 void PathTracer::renderFrames( cl_uint frames ) {
-	if( mAheadLaunched && frames > 0 ) {
-		mAheadLaunched = false;          /* the frame traced ahead is the first of these */
-		frames--;
-	}
+	/* frames traced ahead are the first of these; more of them than asked for are dropped */
+	const size_t keep = std::min( (size_t) frames, mAhead.size() );
+	this->dropFrameAhead( keep );
+	mAhead.clear();
+	frames -= (cl_uint) keep;
 	if( frames == 0 ) { return; }
 	mCL->setDebugImage( false );
 	/* with ranks, every frame of the batch is completed across the ranks by the library (progressive display) */
@@ -279,9 +314,7 @@ void PathTracer::renderFrames( cl_uint frames ) {
 	if( combine ) { mCombines += frames; }
 	this->updateEyeBuffer();
 	if( mHaveOutput ) {
-		std::swap( mBufTextureIn, mBufTextureOut );
-		mCL->setKernelArg( mKernelPathTracing, 11, sizeof( cl_mem ), &mBufTextureIn );
-		mCL->setKernelArg( mKernelPathTracing, 12, sizeof( cl_mem ), &mBufTextureOut );
+		this->advanceImages();
 	}
 	vector<cl_float> seeds( frames ), weights( frames );
 	const cl_float now = this->getTimeSinceStart();
@@ -439,7 +472,10 @@ void PathTracer::initOpenCLBuffers(
 	this->initKernelArgs();
 	mSampleCount = 0;
 	mHaveOutput = false;
-	mAheadLaunched = false;
+	mAhead.clear();
+	mImages.clear();
+	mImages.push_back( mBufTextureIn );
+	mImages.push_back( mBufTextureOut );
 }
 
 

@@ -22,6 +22,7 @@
 #define PATH_TRACER_H
 
 #include <chrono>
+#include <deque>
 #include <string>
 #include <vector>
 
@@ -103,12 +104,13 @@ class PathTracer {
 		int getWorld() const { return mWorld; }
 		/** -1 automatic (default), 0 the reference's visiting order, 1 the ordered walk (pbr_set_traversal). */
 		void setTraversal( int mode ) { mCL->setTraversal( mode ); }
-		cl_uint getSampleCount() const { return mAheadLaunched ? mSampleCountBeforeAhead : mSampleCount; }
-		/** Render ahead: generateImage() starts tracing the NEXT frame before it waits for the copy of this one,
-		 *  so the read-back is hidden behind the next frame.  Anything that changes what the next frame should
-		 *  look like (camera, focus, sample count, tile, seeds) discards the frame traced ahead.  Off by default:
-		 *  then a frame is only ever traced inside the call that returns it, as upstream. */
-		void setRenderAhead( bool enabled );
+		cl_uint getSampleCount() const { return mSampleCount - (cl_uint) mAhead.size(); }
+		/** Render ahead: generateImage() starts tracing the next `depth` (0..3) frames before it waits for the copy of this
+		 *  one, so the read-back -- and the tail of every frame's launches -- is hidden behind the following frames
+		 *  (each frame traced ahead keeps an image of its own until it has been delivered).  Anything that changes what
+		 *  the next frame should look like (camera, focus, sample count, tile, seeds) discards the frames traced ahead.
+		 *  0 by default: then a frame is only ever traced inside the call that returns it, as upstream. */
+		void setRenderAhead( int depth );
 		cl_uint getWidth() const { return mWidth; }
 		cl_uint getHeight() const { return mHeight; }
 		CL* getCL() { return mCL; }
@@ -158,9 +160,18 @@ class PathTracer {
 		bool mDeterministicSeeds;
 		cl_uint mSeedStride, mSeedOffset;
 		cl_uint mFrameTimeMs;
-		bool mRenderAhead, mAheadLaunched;
-		cl_uint mSampleCountBeforeAhead;
-		void dropFrameAhead();
+		int mRenderAhead;
+		struct AheadFrame {           // a frame launched but not delivered yet, and the state before it was launched
+			cl_mem in, out, delivered;
+			cl_uint sampleCount, combines;
+			bool haveOutput;
+		};
+		std::deque<AheadFrame> mAhead;
+		std::vector<cl_mem> mImages;  // the accumulation images: In / Out walk around this ring
+		void advanceImages();
+		void launchAhead();
+		int aheadDepth() const;
+		void dropFrameAhead( size_t keep = 0 );
 		bool mHaveOutput;             // imageOut holds a frame that the next launch must read as imageIn
 		int mRank, mWorld, mSharding;
 		cl_mem mBufTextureDisplay[2]; // SHARD_SPP: the mean over ranks of frame k lands in [k & 1]

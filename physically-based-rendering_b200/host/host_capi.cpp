@@ -385,8 +385,8 @@ int pbrh_renderer_set_traversal( pbrh_renderer* r, int32_t mode ) {
 	return 0;
 }
 
-int pbrh_renderer_set_render_ahead( pbrh_renderer* r, int32_t enabled ) {
-	r->widget->getPathTracer()->setRenderAhead( enabled != 0 );
+int pbrh_renderer_set_render_ahead( pbrh_renderer* r, int32_t depth ) {
+	r->widget->getPathTracer()->setRenderAhead( depth );
 	return 0;
 }
 

@@ -240,7 +240,7 @@ def test_product_equals_reference_renderer(cfg, name):
 
 
 def test_render_ahead_returns_the_same_frames(cfg):
-    """PathTracer::setRenderAhead: the next frame is traced while this one is copied out.  Same frames, also
+    """PathTracer::setRenderAhead: the next 1..3 frames are traced while this one is copied out.  Same frames, also
     across everything that invalidates the frame traced ahead (camera, focus, reset, renderFrames, readImage)."""
     from pbr_b200 import host
     cfg.update({"window.width": 120, "window.height": 72, "render.max_depth": 4})
@@ -271,7 +271,9 @@ def test_render_ahead_returns_the_same_frames(cfg):
         r.close()
         return out
 
-    plain, ahead = session(False), session(True)
-    assert len(plain) == len(ahead)
-    for i, (a, b) in enumerate(zip(plain, ahead)):
-        assert Hh.images_equal(a, b), "image %d differs with render-ahead" % i
+    plain = session(0)
+    for depth in (1, 2, 3):
+        ahead = session(depth)
+        assert len(plain) == len(ahead)
+        for i, (a, b) in enumerate(zip(plain, ahead)):
+            assert Hh.images_equal(a, b), "image %d differs with render-ahead %d" % (i, depth)

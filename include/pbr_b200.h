@@ -154,11 +154,12 @@ int pbr_kernel_launch_batch(pbr_ctx* ctx, pbr_kernel k, int32_t n_frames, const 
  * "traverse_blocks" / "wide_blocks" (cap on resident blocks per SM of the reference-order / ordered traversal kernels,
  * 0 = all that fit), "wide_top" (how many nodes of the top of the 4-wide BVH the ordered walk stages in shared memory;
  * the tree is renumbered at the next launch), "shadow_stage" (1: shadow rays are a wavefront stage of their own, walked
- * by the traversal engine; 0: inside the shade kernel), "frames_in_flight" (1..4, default 4: how many consecutive frames of a
+ * by the traversal engine; 0: inside the shade kernel), "frames_in_flight" (1..8, default 4: how many consecutive frames of a
  * pbr_kernel_launch_batch are traced concurrently, each on a stream and in a wave state of its own; finished pixels leave
  * their frame's radiance in a per-frame buffer and are mixed into imageOut in frame order -- same bits; 1 = one frame
  * after the other).
- * The environment variables PBR_NODE_PHASE_MIN, PBR_REFILL_MIN, PBR_PIPELINE, PBR_TRAVERSAL set the initial values.
+ * The environment variables PBR_NODE_PHASE_MIN, PBR_REFILL_MIN, PBR_PIPELINE, PBR_TRAVERSAL, PBR_FRAMES_IN_FLIGHT set the
+ * initial values.
  * Stands where opencl.localgroupsize stands in the reference's config.json. */
 int pbr_set_tuning(pbr_ctx* ctx, const char* key, int32_t value);
 /* Skip the imageDebug write.  The debug image is the only place where the reference's visit counters

@@ -144,7 +144,7 @@ struct pbr_ctx {
 		cudaEvent_t evTraced = nullptr, evConsumed = nullptr;
 		bool consumedPending = false;
 	};
-	enum { MAX_IN_FLIGHT = 4 };
+	enum { MAX_IN_FLIGHT = 8 };
 	WaveSet sets[MAX_IN_FLIGHT];
 	int framesInFlight = 4;                    /* tuning "frames_in_flight": 1 -> 2 -> 3 -> 4 = 1356 -> 1548 -> 1599 -> 1619 Mrays/s on C2 */
 	cudaEvent_t evPrepared = nullptr;
@@ -805,6 +805,7 @@ int pbr_create(int device, pbr_ctx** out) {
 	}
 	if (const char* e = getenv("PBR_PIPELINE")) { const int v = atoi(e); if (v >= 0 && v <= 1) { ctx->pipeline = v; ctx->pipelineAuto = false; } }
 	if (const char* e = getenv("PBR_TRAVERSAL")) { const int v = atoi(e); if (v >= -1 && v <= 1) ctx->traversal = v; }
+	if (const char* e = getenv("PBR_FRAMES_IN_FLIGHT")) { const int v = atoi(e); if (v >= 1 && v <= pbr_ctx::MAX_IN_FLIGHT) ctx->framesInFlight = v; }
 	memset(&ctx->defines, 0, sizeof(ctx->defines));
 	memset(&ctx->args.cam, 0, sizeof(ctx->args.cam));
 	*out = ctx;
@@ -1546,7 +1547,10 @@ int pbr_comm_init(pbr_ctx* ctx, const void* id128, int32_t rank, int32_t world) 
 	NK(N.CommInitRank(&ctx->comm, world, id, rank));
 	ctx->commRank = rank;
 	ctx->commWorld = world;
-	CK(cudaStreamCreateWithFlags(&ctx->commStream, cudaStreamNonBlocking));
+	/* highest priority: the collective's few blocks go first whenever the persistent traversal kernels free a slot */
+	int prioLow = 0, prioHigh = 0;
+	CK(cudaDeviceGetStreamPriorityRange(&prioLow, &prioHigh));
+	CK(cudaStreamCreateWithPriority(&ctx->commStream, cudaStreamNonBlocking, prioHigh));
 	CK(cudaEventCreateWithFlags(&ctx->evRendered, cudaEventDisableTiming));
 	return PBR_OK;
 }

@@ -1,6 +1,6 @@
 set -x
 mkdir -p gpurun_out
-T=r02h
+T=r02m
 N=${1:-8}
 M=tests/golden/models/
 H=physically-based-rendering_b200/host/pbr_headless

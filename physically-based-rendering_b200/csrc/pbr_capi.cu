@@ -146,6 +146,9 @@ struct pbr_ctx {
 	};
 	enum { MAX_IN_FLIGHT = 8 };
 	WaveSet sets[MAX_IN_FLIGHT];
+	WaveSet serialSet;                         /* frames launched on the context's stream (debug image, depth of field, megakernel
+	                                              timing rounds): a state of their own, so that they never share one with a frame
+	                                              that is still being traced on a stream of its own */
 	int framesInFlight = 4;                    /* tuning "frames_in_flight": 1 -> 2 -> 3 -> 4 = 1356 -> 1548 -> 1599 -> 1619 Mrays/s on C2 */
 	cudaEvent_t evPrepared = nullptr;
 	uint64_t preparedVersion = ~0ull, preparedWide = ~0ull;
@@ -158,7 +161,7 @@ struct pbr_ctx {
 	FrameParams lastFrameParams;               /* of the frame launched last (the deferred mix needs them) */
 	int lastNumPaths = 0;
 	bool launchUseWide = false;
-	int launchSet = 0;                         /* which wave set / stream the frame being launched uses (launchFrames) */
+	int launchSet = -1;                        /* which wave set / stream the frame being launched uses (-1: serialSet) */
 	cudaStream_t launchStream = nullptr;
 	float4* launchFrameOut = nullptr;          /* != NULL: the frame's radiance goes here, mixing is deferred */
 	int traverseBlocks = 0;                    /* tuning: cap on resident traverse blocks per SM (0 = all that fit) */
@@ -636,7 +639,7 @@ int runFrame(pbr_ctx* ctx, const FrameParams& P, int nPaths) {
 		CK(cudaGetLastError());
 		return PBR_OK;
 	}
-	pbr_ctx::WaveSet& T = ctx->sets[ctx->launchSet];
+	pbr_ctx::WaveSet& T = ctx->launchSet < 0 ? ctx->serialSet : ctx->sets[ctx->launchSet];
 	int rc = ensureWave(ctx, T, (size_t) nPaths);
 	if (rc) return rc;
 	return runWavefront<BRDF, SHADOW, PHONG>(ctx, P, T, ctx->launchStream ? ctx->launchStream : ctx->stream, nPaths);
@@ -820,6 +823,7 @@ int pbr_destroy(pbr_ctx* ctx) {
 	for (void* p : ctx->pinned) cudaFreeHost(p);
 	cudaFree(ctx->nodes); cudaFree(ctx->tris); cudaFree(ctx->wide); cudaFree(ctx->faceLeaf);
 	for (pbr_ctx::WaveSet& T : ctx->sets) freeWaveSet(T);
+	freeWaveSet(ctx->serialSet);
 	if (ctx->evPrepared) cudaEventDestroy(ctx->evPrepared);
 	cudaFree(ctx->stats); cudaFree(ctx->cursor64);
 	cudaEventDestroy(ctx->evStart); cudaEventDestroy(ctx->evStop);
@@ -1277,7 +1281,7 @@ static int launchOverlapped(pbr_ctx* ctx, const float* seed, const float* weight
 	ctx->launchStream = T.stream;
 	ctx->launchFrameOut = T.frameOut;
 	rc = launchFrames(ctx, 1, seed, weight, hIn, hOut);
-	ctx->launchSet = 0;
+	ctx->launchSet = -1;
 	ctx->launchStream = nullptr;
 	ctx->launchFrameOut = nullptr;
 	ctx->pipeline = savedPipeline;
@@ -1338,25 +1342,17 @@ int pbr_kernel_launch_batch(pbr_ctx* ctx, pbr_kernel k, int32_t n_frames, const 
 	Mem* outM = getMem(ctx, hOut);
 	if (!outM) return fail(ctx, PBR_ERR_INVALID, "pathTracing: imageOut is not live");
 	const bool combine = ctx->batchCombineMode >= 0 && ctx->comm != nullptr;
-	/* a batch is a request for throughput: while the measured pipeline choice is still open it takes the wavefront */
-	const bool overlap = !depthOfField && ctx->framesInFlight > 1 && !ctx->debugImage &&
-		(ctx->pipelineAuto ? !(ctx->autoState >= 6 && ctx->autoChoice == 1) : ctx->pipeline == 0);
-	if (overlap) {
+	if (!depthOfField) {
+		/* pixels are independent of each other, so everything after frame 0 accumulates in place in imageOut.  While the
+		 * measured pipeline choice is still open the first frames of the batch are its timing rounds; after that the
+		 * frames overlap (launchOverlapped) unless the megakernel won, the debug image is on, or frames_in_flight is 1 */
 		for (int f = 0; f < n_frames; f++) {
-			rc = launchOverlapped(ctx, seeds + f, pixel_weights + f, f == 0 ? hIn : hOut, hOut);
-			if (rc) return rc;
-			if (combine) {
-				rc = pbr_frame_combine(ctx, hOut, ctx->batchCombineMode, ctx->batchCombineOut[(ctx->batchCombineParity + f) & 1]);
-				if (rc) return rc;
+			const pbr_mem in = f == 0 ? hIn : hOut;
+			if (overlapEligible(ctx)) rc = launchOverlapped(ctx, seeds + f, pixel_weights + f, in, hOut);
+			else {
+				if (f > 0 && outM->combinePending) { CK(cudaStreamWaitEvent(ctx->stream, outM->evCombined, 0)); outM->combinePending = false; }
+				rc = launchFrames(ctx, 1, seeds + f, pixel_weights + f, in, hOut);
 			}
-		}
-	}
-	else if (!depthOfField) {
-		/* pixels are independent of each other, so everything after frame 0 can run in place in imageOut, frame after
-		 * frame (the rays of one bounce of one frame stay together, which the caches like) */
-		for (int f = 0; f < n_frames; f++) {
-			if (f > 0 && outM->combinePending) { CK(cudaStreamWaitEvent(ctx->stream, outM->evCombined, 0)); outM->combinePending = false; }
-			rc = launchFrames(ctx, 1, seeds + f, pixel_weights + f, f == 0 ? hIn : hOut, hOut);
 			if (rc) return rc;
 			if (combine) {
 				rc = pbr_frame_combine(ctx, hOut, ctx->batchCombineMode, ctx->batchCombineOut[(ctx->batchCombineParity + f) & 1]);

@@ -7,6 +7,7 @@
 #include <stdexcept>
 #include <stdio.h>
 #include <string.h>
+#include <functional>
 #include <string>
 #include <vector>
 
@@ -537,30 +538,47 @@ int pbrh_renderer_handles( pbrh_renderer* r, void** pbr_ctx_out, uint64_t handle
 /* ---- image files ----------------------------------------------------------------------------- */
 
 /** Portable float map, RGB, little endian, bottom row first -- the kernel's row order. */
-int pbrh_write_pfm( const char* path, const float* rgba, int32_t width, int32_t height ) {
-	FILE* f = fopen( path, "wb" );
-	if( !f ) { return failMsg( string( "cannot write " ) + path ); }
-	fprintf( f, "PF\n%d %d\n-1.0\n", width, height );
-	vector<float> row( (size_t) width * 3 );
-	for( int32_t y = 0; y < height; y++ ) {
-		for( int32_t x = 0; x < width; x++ ) {
-			const float* p = rgba + ( (size_t) y * width + x ) * 4;
-			row[3 * x] = p[0]; row[3 * x + 1] = p[1]; row[3 * x + 2] = p[2];
-		}
-		fwrite( row.data(), sizeof( float ), row.size(), f );
+/* Files are written next to their final name and renamed into place once every byte has reached the file: a full disk
+ * or an I/O error leaves the previous file (the checkpoint a long render resumes from) untouched and is reported. */
+static int writeAtomically( const char* path, const std::function<bool( FILE* )>& body ) {
+	const string tmp = string( path ) + ".tmp";
+	FILE* f = fopen( tmp.c_str(), "wb" );
+	if( !f ) { return failMsg( string( "cannot write " ) + tmp ); }
+	bool ok = body( f );
+	ok = ( fflush( f ) == 0 ) && ok;
+	ok = ( fclose( f ) == 0 ) && ok;
+	if( !ok ) {
+		remove( tmp.c_str() );
+		return failMsg( string( "write error on " ) + tmp + " (disk full?)" );
 	}
-	fclose( f );
+	if( rename( tmp.c_str(), path ) != 0 ) {
+		remove( tmp.c_str() );
+		return failMsg( string( "cannot rename " ) + tmp + " to " + path );
+	}
 	return 0;
+}
+
+int pbrh_write_pfm( const char* path, const float* rgba, int32_t width, int32_t height ) {
+	return writeAtomically( path, [&]( FILE* f ) {
+		if( fprintf( f, "PF\n%d %d\n-1.0\n", width, height ) < 0 ) { return false; }
+		vector<float> row( (size_t) width * 3 );
+		for( int32_t y = 0; y < height; y++ ) {
+			for( int32_t x = 0; x < width; x++ ) {
+				const float* p = rgba + ( (size_t) y * width + x ) * 4;
+				row[3 * x] = p[0]; row[3 * x + 1] = p[1]; row[3 * x + 2] = p[2];
+			}
+			if( fwrite( row.data(), sizeof( float ), row.size(), f ) != row.size() ) { return false; }
+		}
+		return true;
+	} );
 }
 
 /** Accumulation checkpoint: "PBRACC1\n" width height sampleCount, then W*H*4 floats. */
 int pbrh_write_checkpoint( const char* path, const float* rgba, int32_t width, int32_t height, uint32_t sample_count ) {
-	FILE* f = fopen( path, "wb" );
-	if( !f ) { return failMsg( string( "cannot write " ) + path ); }
-	fprintf( f, "PBRACC1\n%d %d %u\n", width, height, sample_count );
-	fwrite( rgba, sizeof( float ), (size_t) width * height * 4, f );
-	fclose( f );
-	return 0;
+	return writeAtomically( path, [&]( FILE* f ) {
+		const size_t n = (size_t) width * height * 4;
+		return fprintf( f, "PBRACC1\n%d %d %u\n", width, height, sample_count ) >= 0 && fwrite( rgba, sizeof( float ), n, f ) == n;
+	} );
 }
 
 int pbrh_read_checkpoint( const char* path, float* rgba, int32_t width, int32_t height, uint32_t* sample_count ) {

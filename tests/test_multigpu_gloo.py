@@ -136,3 +136,39 @@ def test_sample_sharding_is_the_mean_of_the_ranks(tmp_path):
     p = _prepared()
     ref, _, _ = p.oracle_frames(2 * FRAMES, nthreads=2)
     assert Hh.mean_relative_error(shown[0], ref) < 0.5
+
+
+def test_c_abi_row_partition_is_the_python_one():
+    """pbr_tile_rows (what pbr_frame_combine(ROWS) and PathTracer::setRanks use) == multigpu.tile_rows."""
+    from pbr_b200 import capi, multigpu
+    for height in (1, 3, 4, 7, 100, 512, 1080, 2160):
+        for world in (1, 2, 3, 4, 5, 8):
+            rows = [capi.Device.tileRows(height, r, world) for r in range(world)]
+            assert rows == [multigpu.tile_rows(height, r, world) for r in range(world)]
+            assert rows[0][0] == 0 and rows[-1][1] == height
+            assert all(a[1] == b[0] for a, b in zip(rows, rows[1:]))
+    with pytest.raises(capi.PbrError):
+        capi.Device.tileRows(100, 3, 3)
+
+
+def test_nccl_is_loaded_on_demand_and_an_id_can_be_made_without_a_gpu():
+    """pbr_comm_unique_id dlopens libnccl.so.2: 128 bytes, different every time (no GPU, no communicator needed)."""
+    from pbr_b200 import capi, host
+    a, b = capi.Device.commUniqueId(), host.comm_unique_id()
+    assert len(a) == 128 and len(b) == 128 and a != b
+
+
+def test_checkpoint_files_are_written_atomically(tmp_path):
+    from pbr_b200 import host
+    img = np.arange(4 * 3 * 4, dtype=np.float32).reshape(3, 4, 4)
+    path = tmp_path / "acc.bin"
+    host.write_checkpoint(str(path), img, 7)
+    got, sc = host.read_checkpoint(str(path), 4, 3)
+    assert sc == 7 and np.array_equal(got, img) and not (tmp_path / "acc.bin.tmp").exists()
+    # a target that cannot be written reports an error and leaves the good file alone
+    with pytest.raises(host.HostError):
+        host.write_checkpoint(str(tmp_path / "no_such_dir" / "acc.bin"), img, 8)
+    got, sc = host.read_checkpoint(str(path), 4, 3)
+    assert sc == 7
+    host.write_pfm(str(tmp_path / "img.pfm"), img)
+    assert (tmp_path / "img.pfm").read_bytes().startswith(b"PF\n4 3\n-1.0\n")

@@ -37,6 +37,9 @@ struct Mem {
 	uint64_t epoch = 0;               /* bumped whenever the contents may have changed (create, update, free) */
 	cudaEvent_t evCombined = nullptr; /* pbr_frame_combine still reads (or all-gathers into) this image until then */
 	bool combinePending = false;
+	cudaEvent_t evOwnRowsFree = nullptr; /* ROWS combine with stripes: this rank's rows have been packed -- a frame that
+	                                        touches only its own rows may overwrite them while the gather is still running */
+	bool ownRowsPending = false;
 	cudaEvent_t evWritten = nullptr;  /* recorded on the context's stream behind the last launch / copy that wrote this image:
 	                                     an asynchronous read-back waits for THIS, not for whatever has been queued since */
 	bool writtenValid = false;
@@ -740,10 +743,18 @@ int markWritten(pbr_ctx* ctx, Mem* m) {
 /* A launch that overwrites an image waits for the combine that still reads it (frame k + 2 and the combine of frame k
  * share a buffer of PathTracer's ping-pong pair); with depth of field a frame also READS other pixels of imageIn, which
  * a row gather is still filling. */
-int waitForCombine(pbr_ctx* ctx, Mem* m) {
-	if (m && m->combinePending) {
+int waitForCombine(pbr_ctx* ctx, Mem* m, bool ownRowsOnly = false) {
+	if (!m) return PBR_OK;
+	if (ownRowsOnly && m->ownRowsPending) {
+		/* (the collective itself stays pending: whoever reads the whole image still waits for it) */
+		CK(cudaStreamWaitEvent(ctx->stream, m->evOwnRowsFree, 0));
+		m->ownRowsPending = false;
+		return PBR_OK;
+	}
+	if (m->combinePending) {
 		CK(cudaStreamWaitEvent(ctx->stream, m->evCombined, 0));
 		m->combinePending = false;
+		m->ownRowsPending = false;
 	}
 	return PBR_OK;
 }
@@ -834,7 +845,11 @@ int pbr_destroy(pbr_ctx* ctx) {
 	if (ctx->commStream) cudaStreamDestroy(ctx->commStream);
 	if (ctx->evRendered) cudaEventDestroy(ctx->evRendered);
 	cudaFree(ctx->commSend); cudaFree(ctx->commRecv);
-	for (Mem& m : ctx->mems) { if (m.evCombined) cudaEventDestroy(m.evCombined); if (m.evWritten) cudaEventDestroy(m.evWritten); }
+	for (Mem& m : ctx->mems) {
+		if (m.evCombined) cudaEventDestroy(m.evCombined);
+		if (m.evWritten) cudaEventDestroy(m.evWritten);
+		if (m.evOwnRowsFree) cudaEventDestroy(m.evOwnRowsFree);
+	}
 	if (ctx->copyStream) { cudaStreamSynchronize(ctx->copyStream); cudaStreamDestroy(ctx->copyStream); }
 	if (ctx->evCopy) cudaEventDestroy(ctx->evCopy);
 	for (int i = 0; i < 8; i++) if (ctx->evAuto[i]) cudaEventDestroy(ctx->evAuto[i]);
@@ -1289,7 +1304,8 @@ static int launchOverlapped(pbr_ctx* ctx, const float* seed, const float* weight
 	if (rc) return rc;
 	CK(cudaEventRecord(T.evTraced, T.stream));
 	CK(cudaStreamWaitEvent(ctx->stream, T.evTraced, 0));
-	if (outM->combinePending) { CK(cudaStreamWaitEvent(ctx->stream, outM->evCombined, 0)); outM->combinePending = false; }
+	rc = waitForCombine(ctx, outM, true);          /* the mix reads and writes this rank's rows only */
+	if (rc) return rc;
 	{
 		LaunchScope ls(ctx, K_SHADE);
 		mixFrameKernel<<<ctx->smCount * 8, 256, 0, ctx->stream>>>(ctx->lastFrameParams, T.frameOut, ctx->lastNumPaths);
@@ -1312,9 +1328,10 @@ int pbr_kernel_launch(pbr_ctx* ctx, pbr_kernel k) {
 	if (rc) return rc;
 	CK(cudaSetDevice(ctx->device));
 	KernelArgs& a = ctx->args;
-	rc = waitForCombine(ctx, getMem(ctx, a.mem[12]));
+	const bool dof = a.cam.focusPoint.x >= 0 && a.cam.focusPoint.y >= 0;
+	rc = waitForCombine(ctx, getMem(ctx, a.mem[12]), !dof);
 	if (rc) return rc;
-	if (a.cam.focusPoint.x >= 0 && a.cam.focusPoint.y >= 0) { rc = waitForCombine(ctx, getMem(ctx, a.mem[11])); if (rc) return rc; }
+	if (dof) { rc = waitForCombine(ctx, getMem(ctx, a.mem[11])); if (rc) return rc; }
 	CK(cudaEventRecord(ctx->evStart, ctx->stream));
 	if (overlapEligible(ctx)) rc = launchOverlapped(ctx, &a.seed, &a.pixelWeight, a.mem[11], a.mem[12]);
 	else rc = launchFrames(ctx, 1, &a.seed, &a.pixelWeight, a.mem[11], a.mem[12]);
@@ -1333,12 +1350,12 @@ int pbr_kernel_launch_batch(pbr_ctx* ctx, pbr_kernel k, int32_t n_frames, const 
 	CK(cudaSetDevice(ctx->device));
 	KernelArgs& a = ctx->args;
 	const pbr_mem hIn = a.mem[11], hOut = a.mem[12];
-	rc = waitForCombine(ctx, getMem(ctx, hOut));
+	const bool depthOfField = a.cam.focusPoint.x >= 0 && a.cam.focusPoint.y >= 0;
+	rc = waitForCombine(ctx, getMem(ctx, hOut), !depthOfField);
 	if (rc) return rc;
-	rc = waitForCombine(ctx, getMem(ctx, hIn));
+	rc = waitForCombine(ctx, getMem(ctx, hIn), !depthOfField);
 	if (rc) return rc;
 	CK(cudaEventRecord(ctx->evStart, ctx->stream));
-	const bool depthOfField = a.cam.focusPoint.x >= 0 && a.cam.focusPoint.y >= 0;
 	Mem* outM = getMem(ctx, hOut);
 	if (!outM) return fail(ctx, PBR_ERR_INVALID, "pathTracing: imageOut is not live");
 	const bool combine = ctx->batchCombineMode >= 0 && ctx->comm != nullptr;
@@ -1350,7 +1367,7 @@ int pbr_kernel_launch_batch(pbr_ctx* ctx, pbr_kernel k, int32_t n_frames, const 
 			const pbr_mem in = f == 0 ? hIn : hOut;
 			if (overlapEligible(ctx)) rc = launchOverlapped(ctx, seeds + f, pixel_weights + f, in, hOut);
 			else {
-				if (f > 0 && outM->combinePending) { CK(cudaStreamWaitEvent(ctx->stream, outM->evCombined, 0)); outM->combinePending = false; }
+				if (f > 0) { rc = waitForCombine(ctx, outM, true); if (rc) return rc; }
 				rc = launchFrames(ctx, 1, seeds + f, pixel_weights + f, in, hOut);
 			}
 			if (rc) return rc;
@@ -1571,7 +1588,7 @@ int pbr_comm_destroy(pbr_ctx* ctx) {
 	ctx->comm = nullptr;
 	ctx->commWorld = 1;
 	ctx->commRank = 0;
-	for (Mem& m : ctx->mems) m.combinePending = false;
+	for (Mem& m : ctx->mems) { m.combinePending = false; m.ownRowsPending = false; }
 	return PBR_OK;
 }
 
@@ -1618,6 +1635,9 @@ int pbr_frame_combine(pbr_ctx* ctx, pbr_mem image, int32_t mode, pbr_mem out) {
 			if (per * world > ctx->commRecvCap) { cudaFree(ctx->commRecv); ctx->commRecv = nullptr; CK(cudaMalloc(&ctx->commRecv, per * world * 16)); ctx->commRecvCap = per * world; }
 			ctx->prof.launches += 2; ctx->prof.other_launches += 2;
 			packStripesKernel<<<ctx->smCount * 4, 256, 0, ctx->commStream>>>((const float4*) img->dptr, ctx->commSend, rowF4, localRows, ctx->stripeRows, world, rank);
+			if (!img->evOwnRowsFree) CK(cudaEventCreateWithFlags(&img->evOwnRowsFree, cudaEventDisableTiming));
+			CK(cudaEventRecord(img->evOwnRowsFree, ctx->commStream));
+			img->ownRowsPending = true;
 			NK(N.AllGather(ctx->commSend, ctx->commRecv, per * 4, ncclFloat, ctx->comm, ctx->commStream));
 			unpackStripesKernel<<<ctx->smCount * 4, 256, 0, ctx->commStream>>>((float4*) img->dptr, ctx->commRecv, rowF4, localRows, ctx->stripeRows, world, rank);
 			CK(cudaGetLastError());
@@ -1678,6 +1698,7 @@ int pbr_comm_fence(pbr_ctx* ctx) {
 		if (m.alive && m.combinePending) {
 			CK(cudaStreamWaitEvent(ctx->stream, m.evCombined, 0));
 			m.combinePending = false;
+			m.ownRowsPending = false;
 		}
 	}
 	return PBR_OK;

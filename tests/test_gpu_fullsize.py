@@ -65,6 +65,19 @@ def test_fullsize_pipelines_agree(device, c2dev):
         assert Hh.images_equal(frames[pipeline][0], ref[0]), "pipeline %d: frame" % pipeline
         assert Hh.images_equal(frames[pipeline][1], ref[1]), "pipeline %d: debug image" % pipeline
         assert np.array_equal(frames[pipeline][2], ref[2]), "pipeline %d: counters" % pipeline
+    # the ordered walk (no debug image), one frame after the other and four in flight: the same 1080p frame
+    device.setDebugImage(False)
+    try:
+        for in_flight in (1, 4):
+            device.setTuning("frames_in_flight", in_flight)
+            device.traversalInfo(reset=True)
+            img, _ = c2dev.frames_batch(2)
+            info = device.traversalInfo()
+            assert info["last_used"] == 1 and info["ordered_rays"] == int(ref[2][0]) and info["rewalked_rays"] == 0
+            assert Hh.images_equal(img, ref[0]), "ordered walk, %d frame(s) in flight" % in_flight
+    finally:
+        device.setTuning("frames_in_flight", 4)
+        device.setDebugImage(True)
 
 
 def test_fullsize_row_blocks_and_batches(device, c2, c2dev):

@@ -490,3 +490,78 @@ def test_frames_in_flight_same_bits(device, suzanne, brdf, shadow, samples, trav
         device.setTuning("frames_in_flight", 4)
         device.setTraversal(-1)
         device.setDebugImage(True)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# Node arrays the reference's host never writes but its kernel gives a meaning to, and the
+# bookkeeping around scene buffers.
+
+def test_foreign_node_words_follow_the_reference_kernel(device, suzanne):
+    """bbMin.w == -2 (traverseShadows' "skip the next left child", pt_bvh.cl:157-159) and bbMin.w strictly between -1
+    and 0 (neither inner nor leaf for the reference: the walk steps over the node) behave as in the reference kernel."""
+    p = Hh.Prepared(suzanne, 64, 48, max_depth=3, shadow_rays=1, brdf=0)
+    inner = np.where(p.nodes[1:, 3] <= -1.0)[0] + 1
+    leaf = np.where(p.nodes[1:, 3] >= 0.0)[0] + 1
+    p.nodes = p.nodes.copy()
+    p.nodes[inner[5::7], 3] = -2.0
+    p.nodes[leaf[3::11], 3] = -0.5
+    ds = Hh.DeviceScene(device, p)
+    rays = np.concatenate([Hh.primary_rays(p, 96, 64), Hh.random_rays(20000, 12, -2.0, 2.0)])
+    want, _ = p.oracle_trace(rays)
+    got = ds.trace(rays)
+    for f in ("hitFace", "leaf", "visits"):
+        assert np.array_equal(got[f], want[f]), f
+    sh = Hh.shadow_rays_from_hits(rays, want, (0.1, 1.3, 1.2))
+    want_s, _ = p.oracle_trace(sh, any_hit=True)
+    got_s = ds.trace(sh, any_hit=True)
+    assert np.array_equal(got_s["hitFace"], want_s["hitFace"]) and np.array_equal(got_s["visits"], want_s["visits"])
+    assert np.array_equal(got_s["t"].view(np.uint32), want_s["t"].view(np.uint32))
+    img, dbg = ds.frames(2)
+    wimg, wdbg, _ = p.oracle_frames(2)
+    assert Hh.images_equal(img, wimg) and Hh.images_equal(dbg, wdbg)
+    # such an array is not one the ordered walk takes: the automatic choice stays with the reference order
+    device.setDebugImage(False)
+    try:
+        img2, _ = ds.frames(2)
+        info = device.traversalInfo()
+    finally:
+        device.setDebugImage(True)
+    assert info["last_used"] == 0 and "skip flag" in info["why_not"]
+    assert Hh.images_equal(img2, wimg)
+
+
+def test_max_depth_zero_is_rejected(device, suzanne):
+    import pbr_b200
+    p = Hh.Prepared(suzanne, 32, 32, max_depth=3)
+    p.defines = p.defines.copy()
+    p.defines["max_depth"] = 0
+    with pytest.raises(pbr_b200.capi.PbrError):
+        Hh.DeviceScene(device, p)
+
+
+def test_updating_the_lights_does_not_rebuild_the_scene(device, oracle):
+    """Per-buffer epochs: only what was built from the buffer that changed is rebuilt."""
+    scene = oracle.load_obj(Hh.model_path("suzanne.obj"), 1)
+    p = Hh.Prepared(scene, 64, 48, max_depth=3, shadow_rays=1)
+    ds = Hh.DeviceScene(device, p)
+    device.setPipeline(0)
+    try:
+        ds.frames(1)
+        device.profileRead(reset=True)
+        ds.frames(1)
+        steady = device.profileRead(reset=True)["other_launches"]
+        lights = p.lights.copy()
+        lights[0, 0] += 0.25                                        # move the light
+        device.updateBuffer(ds.bufLights, lights)
+        got, _ = ds.frames(1)
+        after = device.profileRead(reset=True)["other_launches"]
+        assert after == steady, "a lights-only update re-ran the scene repack"
+        p.lights = lights
+        want, _, _ = p.oracle_frames(1)
+        assert Hh.images_equal(got, want)
+        nodes = p.nodes.copy()
+        device.updateBuffer(ds.bufBVH, nodes)                       # the same bytes, but the library cannot know: rebuilt
+        ds.frames(1)
+        assert device.profileRead(reset=True)["other_launches"] > steady
+    finally:
+        device.setPipeline(-1)

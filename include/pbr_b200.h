@@ -219,9 +219,10 @@ int pbr_comm_info(pbr_ctx* ctx, int32_t* rank, int32_t* world, int32_t* nccl_ver
 int pbr_comm_destroy(pbr_ctx* ctx);
 int pbr_frame_combine(pbr_ctx* ctx, pbr_mem image, int32_t mode, pbr_mem out);
 /* The same inside pbr_kernel_launch_batch: after every frame f of a batch, pbr_frame_combine(imageOut, mode,
- * f + first_parity even ? out0 : out1).  mode -1 switches it off.  (With several frames in flight the batch keeps tracing
- * the next frames while a frame is mixed and combined.) */
-int pbr_set_batch_combine(pbr_ctx* ctx, int32_t mode, pbr_mem out0, pbr_mem out1, int32_t first_parity);
+ * outs[(first + f) % n_outs]) -- a ring of up to 8 display images for PBR_COMBINE_SPP, none needed for PBR_COMBINE_ROWS.
+ * mode -1 switches it off.  (With several frames in flight the batch keeps tracing the next frames while a frame is mixed
+ * and combined.) */
+int pbr_set_batch_combine(pbr_ctx* ctx, int32_t mode, const pbr_mem* outs, int32_t n_outs, int32_t first);
 /* Make the render stream wait (on the device) for every combine enqueued so far. */
 int pbr_comm_fence(pbr_ctx* ctx);
 /* Rows [y0, y1) of rank `rank` of `world`: contiguous blocks of multiples of 4 rows covering [0, height). */

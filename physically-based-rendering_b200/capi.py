@@ -106,7 +106,7 @@ def load_library():
         "pbr_comm_info": [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)],
         "pbr_comm_destroy": [vp],
         "pbr_frame_combine": [vp, u64, i32, u64],
-        "pbr_set_batch_combine": [vp, i32, u64, u64, i32],
+        "pbr_set_batch_combine": [vp, i32, vp, i32, i32],
         "pbr_comm_fence": [vp],
         "pbr_tile_rows": [i32, i32, i32, C.POINTER(i32), C.POINTER(i32)],
         "pbr_trace": [vp, u64, u64, u64, u64, i32, vp, i64, i32, vp],
@@ -319,8 +319,9 @@ class Device:
         """mode: 0 samples (out = mean over ranks of image), 1 rows (the other ranks' rows gathered into image)."""
         self._ck(self.lib.pbr_frame_combine(self.ctx, image, mode, out), "pbr_frame_combine")
 
-    def setBatchCombine(self, mode, out0=0, out1=0, first_parity=0):
-        self._ck(self.lib.pbr_set_batch_combine(self.ctx, mode, out0, out1, first_parity), "pbr_set_batch_combine")
+    def setBatchCombine(self, mode, outs=(), first=0):
+        a = np.asarray(list(outs), np.uint64)
+        self._ck(self.lib.pbr_set_batch_combine(self.ctx, mode, _p(a) if len(a) else None, len(a), first), "pbr_set_batch_combine")
 
     def commFence(self):
         self._ck(self.lib.pbr_comm_fence(self.ctx), "pbr_comm_fence")

@@ -157,8 +157,8 @@ struct pbr_ctx {
 	uint64_t preparedVersion = ~0ull, preparedWide = ~0ull;
 	uint64_t overlapCounter = 0;               /* frames launched through launchOverlapped: picks the wave set */
 	int batchCombineMode = -1;                 /* pbr_set_batch_combine */
-	pbr_mem batchCombineOut[2] = {0, 0};
-	int batchCombineParity = 0;
+	pbr_mem batchCombineOut[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+	int batchCombineOuts = 0, batchCombineFirst = 0;
 	int shadowStage = 1;                       /* tuning "shadow_stage": 0 = walk shadow rays inside the shade kernel */
 
 	FrameParams lastFrameParams;               /* of the frame launched last (the deferred mix needs them) */
@@ -182,6 +182,7 @@ struct pbr_ctx {
 
 	/* multi-GPU (pbr_comm_init): one process per GPU, one NCCL collective per frame on a stream of its own */
 	ncclComm_t comm = nullptr;
+	ncclComm_t commReduce = nullptr;           /* the all-reduce's communicator: split off `comm` with a cap on its blocks */
 	int commRank = 0, commWorld = 1;
 	cudaStream_t commStream = nullptr;
 	cudaEvent_t evRendered = nullptr;
@@ -648,12 +649,17 @@ int runFrame(pbr_ctx* ctx, const FrameParams& P, int nPaths) {
 	return runWavefront<BRDF, SHADOW, PHONG>(ctx, P, T, ctx->launchStream ? ctx->launchStream : ctx->stream, nPaths);
 }
 
+#ifndef PBR_DEFAULT_NCCL_MAX_CTAS
+#define PBR_DEFAULT_NCCL_MAX_CTAS 4   /* measured: NCCL's own choice 3 080, 2 / 4 / 8 blocks 3 186 / 3 186 / 3 169 Mrays/s on 2 GPUs */
+#endif
+
 /* ---- NCCL, loaded on demand ---------------------------------------------------------------------------- */
 
 struct NcclApi {
 	void* handle = nullptr;
 	decltype(&ncclGetUniqueId) GetUniqueId = nullptr;
 	decltype(&ncclCommInitRank) CommInitRank = nullptr;
+	decltype(&ncclCommSplit) CommSplit = nullptr;                       /* optional */
 	decltype(&ncclCommDestroy) CommDestroy = nullptr;
 	decltype(&ncclAllReduce) AllReduce = nullptr;
 	decltype(&ncclAllGather) AllGather = nullptr;
@@ -678,6 +684,7 @@ NcclApi& nccl() {
 	auto sym = [&](const char* n) { void* p = dlsym(api.handle, n); if (!p) { ok = false; api.error = std::string("libnccl lacks ") + n; } return p; };
 	api.GetUniqueId = (decltype(api.GetUniqueId)) sym("ncclGetUniqueId");
 	api.CommInitRank = (decltype(api.CommInitRank)) sym("ncclCommInitRank");
+	api.CommSplit = (decltype(api.CommSplit)) dlsym(api.handle, "ncclCommSplit");
 	api.CommDestroy = (decltype(api.CommDestroy)) sym("ncclCommDestroy");
 	api.AllReduce = (decltype(api.AllReduce)) sym("ncclAllReduce");
 	api.AllGather = (decltype(api.AllGather)) sym("ncclAllGather");
@@ -841,6 +848,7 @@ int pbr_destroy(pbr_ctx* ctx) {
 	for (const pbr_ctx::Timed& t : ctx->timedInFlight) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
 	for (cudaEvent_t e : ctx->eventPool) cudaEventDestroy(e);
 	if (ctx->commStream) cudaStreamSynchronize(ctx->commStream);
+	if (ctx->commReduce && ctx->commReduce != ctx->comm && nccl().CommDestroy) nccl().CommDestroy(ctx->commReduce);
 	if (ctx->comm && nccl().CommDestroy) nccl().CommDestroy(ctx->comm);
 	if (ctx->commStream) cudaStreamDestroy(ctx->commStream);
 	if (ctx->evRendered) cudaEventDestroy(ctx->evRendered);
@@ -1372,7 +1380,7 @@ int pbr_kernel_launch_batch(pbr_ctx* ctx, pbr_kernel k, int32_t n_frames, const 
 			}
 			if (rc) return rc;
 			if (combine) {
-				rc = pbr_frame_combine(ctx, hOut, ctx->batchCombineMode, ctx->batchCombineOut[(ctx->batchCombineParity + f) & 1]);
+				rc = pbr_frame_combine(ctx, hOut, ctx->batchCombineMode, (ctx->batchCombineOuts > 0 ? ctx->batchCombineOut[(ctx->batchCombineFirst + f) % ctx->batchCombineOuts] : 0));
 				if (rc) return rc;
 				outM = getMem(ctx, hOut);
 			}
@@ -1400,7 +1408,7 @@ int pbr_kernel_launch_batch(pbr_ctx* ctx, pbr_kernel k, int32_t n_frames, const 
 			if (rc) return rc;
 			if (combine) {
 				CK(cudaStreamSynchronize(ctx->stream));          /* (depth of field reads what the gather writes: no overlap here) */
-				rc = pbr_frame_combine(ctx, dst, ctx->batchCombineMode, ctx->batchCombineOut[(ctx->batchCombineParity + f) & 1]);
+				rc = pbr_frame_combine(ctx, dst, ctx->batchCombineMode, (ctx->batchCombineOuts > 0 ? ctx->batchCombineOut[(ctx->batchCombineFirst + f) % ctx->batchCombineOuts] : 0));
 				if (rc) return rc;
 				rc = pbr_comm_fence(ctx);
 				if (rc) return rc;
@@ -1558,6 +1566,21 @@ int pbr_comm_init(pbr_ctx* ctx, const void* id128, int32_t rank, int32_t world) 
 	ncclUniqueId id;
 	memcpy(&id, id128, sizeof(id));
 	NK(N.CommInitRank(&ctx->comm, world, id, rank));
+	/* The per-frame all-reduce (33 MB at 1080p) shares the SMs with persistent traversal kernels and has a whole frame
+	 * to finish in: on a communicator of its own it is held to a few blocks (PBR_NCCL_MAX_CTAS; 0 = NCCL's own choice:
+	 * 3 080 instead of 3 186 Mrays/s on 2 GPUs, 12 355 instead of 12 676 on 8).  The row gather (132 MB at 4K, on the
+	 * critical path of ONE image) keeps NCCL's choice: held to 4 blocks it costs a quarter of the strong scaling. */
+	int maxCtas = PBR_DEFAULT_NCCL_MAX_CTAS;
+	if (const char* e = getenv("PBR_NCCL_MAX_CTAS")) maxCtas = atoi(e);
+	ctx->commReduce = ctx->comm;
+	if (maxCtas > 0 && N.CommSplit) {
+		ncclConfig_t config = NCCL_CONFIG_INITIALIZER;
+		config.minCTAs = 1;
+		config.maxCTAs = maxCtas;
+		ncclComm_t split = nullptr;
+		NK(N.CommSplit(ctx->comm, 0, rank, &split, &config));
+		if (split) ctx->commReduce = split;
+	}
 	ctx->commRank = rank;
 	ctx->commWorld = world;
 	/* default (lowest) priority, measured: at the highest priority the collective's kernel takes its blocks early and then
@@ -1584,6 +1607,8 @@ int pbr_comm_destroy(pbr_ctx* ctx) {
 	if (!ctx->comm) return PBR_OK;
 	CK(cudaSetDevice(ctx->device));
 	CK(cudaStreamSynchronize(ctx->commStream));
+	if (ctx->commReduce && ctx->commReduce != ctx->comm) NK(nccl().CommDestroy(ctx->commReduce));
+	ctx->commReduce = nullptr;
 	NK(nccl().CommDestroy(ctx->comm));
 	ctx->comm = nullptr;
 	ctx->commWorld = 1;
@@ -1619,7 +1644,7 @@ int pbr_frame_combine(pbr_ctx* ctx, pbr_mem image, int32_t mode, pbr_mem out) {
 		CK(cudaEventRecord(img->evCombined, ctx->commStream));
 		img->combinePending = true;
 		pending = nullptr;
-		NK(N.AllReduce(dst->dptr, dst->dptr, nF4 * 4, ncclFloat, ncclSum, ctx->comm, ctx->commStream));
+		NK(N.AllReduce(dst->dptr, dst->dptr, nF4 * 4, ncclFloat, ncclSum, ctx->commReduce, ctx->commStream));
 		if (!dst->evCombined) CK(cudaEventCreateWithFlags(&dst->evCombined, cudaEventDisableTiming));
 		CK(cudaEventRecord(dst->evCombined, ctx->commStream));
 		dst->combinePending = true;
@@ -1680,12 +1705,13 @@ int pbr_frame_combine(pbr_ctx* ctx, pbr_mem image, int32_t mode, pbr_mem out) {
 	return PBR_OK;
 }
 
-int pbr_set_batch_combine(pbr_ctx* ctx, int32_t mode, pbr_mem out0, pbr_mem out1, int32_t first_parity) {
-	if (!ctx || mode < -1 || mode > PBR_COMBINE_ROWS) return PBR_ERR_INVALID;
+int pbr_set_batch_combine(pbr_ctx* ctx, int32_t mode, const pbr_mem* outs, int32_t n_outs, int32_t first) {
+	if (!ctx || mode < -1 || mode > PBR_COMBINE_ROWS || n_outs < 0 || n_outs > 8 || (n_outs > 0 && !outs)) return PBR_ERR_INVALID;
+	if (mode == PBR_COMBINE_SPP && n_outs < 1) return fail(ctx, PBR_ERR_INVALID, "pbr_set_batch_combine(SPP) needs at least one display image");
 	ctx->batchCombineMode = mode;
-	ctx->batchCombineOut[0] = out0;
-	ctx->batchCombineOut[1] = out1;
-	ctx->batchCombineParity = first_parity & 1;
+	ctx->batchCombineOuts = n_outs;
+	for (int i = 0; i < n_outs; i++) ctx->batchCombineOut[i] = outs[i];
+	ctx->batchCombineFirst = n_outs > 0 ? ((first % n_outs) + n_outs) % n_outs : 0;
 	return PBR_OK;
 }
 

@@ -282,8 +282,8 @@ void CL::frameCombine( cl_mem image, int mode, cl_mem out ) {
 }
 
 
-void CL::setBatchCombine( int mode, cl_mem out0, cl_mem out1, int firstParity ) {
-	this->checkError( pbr_set_batch_combine( mContext, mode, out0, out1, firstParity ), "pbr_set_batch_combine" );
+void CL::setBatchCombine( int mode, const cl_mem* outs, int numOuts, int first ) {
+	this->checkError( pbr_set_batch_combine( mContext, mode, outs, numOuts, first ), "pbr_set_batch_combine" );
 }
 
 

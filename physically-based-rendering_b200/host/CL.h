@@ -71,7 +71,7 @@ class CL {
 		static bool commUniqueId( void* id128 );
 		bool commInit( const void* id128, int rank, int world );
 		void frameCombine( cl_mem image, int mode, cl_mem out );
-		void setBatchCombine( int mode, cl_mem out0, cl_mem out1, int firstParity );
+		void setBatchCombine( int mode, const cl_mem* outs, int numOuts, int first );
 		void commFence();
 		/* which walk finds the hits (pbr_set_traversal): -1 automatic, 0 reference order, 1 ordered */
 		void setTraversal( int mode );

@@ -58,7 +58,7 @@ PathTracer::PathTracer( GLWidget* parent ) {
 	mRank = 0;
 	mWorld = 1;
 	mSharding = SHARD_SPP;
-	mBufTextureDisplay[0] = mBufTextureDisplay[1] = 0;
+	for( int i = 0; i < NUM_DISPLAYS; i++ ) { mBufTextureDisplay[i] = 0; }
 	mCombines = 0;
 	mTimeSinceStart = std::chrono::steady_clock::now();
 
@@ -127,7 +127,7 @@ void PathTracer::advanceImages() {
 void PathTracer::combineFrame() {
 	if( mWorld <= 1 || mSharding == SHARD_NONE ) { return; }
 	if( mSharding == SHARD_SPP ) {
-		mCL->frameCombine( mBufTextureOut, PBR_COMBINE_SPP, mBufTextureDisplay[mCombines & 1] );
+		mCL->frameCombine( mBufTextureOut, PBR_COMBINE_SPP, mBufTextureDisplay[mCombines % NUM_DISPLAYS] );
 	}
 	else {
 		mCL->frameCombine( mBufTextureOut, PBR_COMBINE_ROWS, 0 );
@@ -138,7 +138,7 @@ void PathTracer::combineFrame() {
 
 /** The image a caller receives: the accumulation buffer, or with SHARD_SPP the mean over ranks of the last frame. */
 cl_mem PathTracer::deliveredImage() const {
-	if( mWorld > 1 && mSharding == SHARD_SPP && mCombines > 0 ) { return mBufTextureDisplay[( mCombines - 1 ) & 1]; }
+	if( mWorld > 1 && mSharding == SHARD_SPP && mCombines > 0 ) { return mBufTextureDisplay[( mCombines - 1 ) % NUM_DISPLAYS]; }
 	return mBufTextureOut;
 }
 
@@ -156,8 +156,7 @@ bool PathTracer::setRanks( int rank, int world, const void* ncclId, int sharding
 	}
 	if( !mCL->commInit( ncclId, rank, world ) ) { return false; }
 	mRank = rank; mWorld = world;
-	mBufTextureDisplay[0] = mCL->createImage2DWriteOnly( mWidth, mHeight );
-	mBufTextureDisplay[1] = mCL->createImage2DWriteOnly( mWidth, mHeight );
+	for( int i = 0; i < NUM_DISPLAYS; i++ ) { mBufTextureDisplay[i] = mCL->createImage2DWriteOnly( mWidth, mHeight ); }
 	return this->setSharding( sharding );
 }
 
@@ -260,9 +259,10 @@ void PathTracer::launchAhead() {
 }
 
 
-/** How many frames are traced beyond the one being delivered: setRenderAhead's, one with ranks (two display images). */
+/** How many frames are traced beyond the one being delivered: setRenderAhead's (with ranks: each of them keeps one of
+ *  the NUM_DISPLAYS display images until it has been delivered). */
 int PathTracer::aheadDepth() const {
-	return ( mWorld > 1 && mSharding != SHARD_NONE ) ? std::min( mRenderAhead, 1 ) : mRenderAhead;
+	return ( mWorld > 1 && mSharding != SHARD_NONE ) ? std::min( mRenderAhead, (int) NUM_DISPLAYS - 1 ) : mRenderAhead;
 }
 
 
@@ -310,7 +310,7 @@ void PathTracer::renderFrames( cl_uint frames ) {
 	/* with ranks, every frame of the batch is completed across the ranks by the library (progressive display) */
 	const bool combine = mWorld > 1 && mSharding != SHARD_NONE;
 	mCL->setBatchCombine( combine ? ( mSharding == SHARD_SPP ? PBR_COMBINE_SPP : PBR_COMBINE_ROWS ) : -1,
-		mBufTextureDisplay[0], mBufTextureDisplay[1], (int) ( mCombines & 1 ) );
+		mBufTextureDisplay, NUM_DISPLAYS, (int) ( mCombines % NUM_DISPLAYS ) );
 	if( combine ) { mCombines += frames; }
 	this->updateEyeBuffer();
 	if( mHaveOutput ) {

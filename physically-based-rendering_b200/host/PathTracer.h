@@ -174,7 +174,8 @@ class PathTracer {
 		void dropFrameAhead( size_t keep = 0 );
 		bool mHaveOutput;             // imageOut holds a frame that the next launch must read as imageIn
 		int mRank, mWorld, mSharding;
-		cl_mem mBufTextureDisplay[2]; // SHARD_SPP: the mean over ranks of frame k lands in [k & 1]
+		enum { NUM_DISPLAYS = 4 };
+		cl_mem mBufTextureDisplay[NUM_DISPLAYS]; // SHARD_SPP: the mean over ranks of frame k lands in [k % NUM_DISPLAYS]
 		cl_uint mCombines;
 		void combineFrame();
 		cl_mem deliveredImage() const;

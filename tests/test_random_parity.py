@@ -85,3 +85,16 @@ def test_random_materials_device_vs_reference_kernel(device, seed, brdf):
     want, wdbg = _reference_frames(p)
     got, gdbg = Hh.DeviceScene(device, p).frames(2)
     assert Hh.images_equal(got, want) and Hh.images_equal(gdbg, wdbg)
+    # the same frames without the debug image: the ordered walk (where the scene allows it: no depth of field needed,
+    # it only changes how frames overlap), several frames in flight -- the same bits
+    ds = Hh.DeviceScene(device, p)
+    device.setDebugImage(False)
+    device.setPipeline(0)
+    try:
+        fast, _ = ds.frames_batch(2)
+        info = device.traversalInfo()
+    finally:
+        device.setPipeline(-1)
+        device.setDebugImage(True)
+    assert info["last_used"] == 1, info
+    assert Hh.images_equal(fast, want)

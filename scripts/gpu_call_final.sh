@@ -4,7 +4,7 @@ set -x
 mkdir -p gpurun_out
 T=${1:-r02_final}
 python -c "import sys; sys.path.insert(0,'.'); import pbr_b200; print(pbr_b200.capi.build_id())" > gpurun_out/${T}_build_id.txt
-( time timeout 1500 python -m pytest tests -m gpu -x -q --durations=5 ) > gpurun_out/${T}_gpu_tests.log 2>&1
+( time timeout 1500 python -m pytest tests -m gpu -q --durations=5 ) > gpurun_out/${T}_gpu_tests.log 2>&1
 tail -8 gpurun_out/${T}_gpu_tests.log
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2 | tee gpurun_out/${T}_smoke.log
 timeout 900 python bench.py > gpurun_out/${T}_bench_n1.json 2> gpurun_out/${T}_bench_n1.err

@@ -89,6 +89,20 @@ def workload(args):
     return w
 
 
+def count_identical_pixels(a, b):
+    """Pixels whose four channels are bit-identical (NaN == NaN)."""
+    a, b = np.ascontiguousarray(a, np.float32), np.ascontiguousarray(b, np.float32)
+    same = (a.view(np.uint32) == b.view(np.uint32)) | (np.isnan(a) & np.isnan(b))
+    return int(same.reshape(-1, a.shape[-1]).all(axis=1).sum())
+
+
+def mean_relative_error(a, b):
+    """mean(|a-b| / (max(a,b) + 1e-3)) over RGB of pixels finite on both sides."""
+    a, b = np.asarray(a, np.float64)[..., :3], np.asarray(b, np.float64)[..., :3]
+    ok = np.isfinite(a) & np.isfinite(b)
+    return float((np.abs(a - b)[ok] / (np.maximum(a, b)[ok] + 1e-3)).mean())
+
+
 def measured_peak():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     try:
@@ -456,16 +470,14 @@ def run_ours(args):
         cpu_baseline, cpu_frames, cpu_image = cpu_baseline_sample(w, r.flat(), scene)
         # parity at the bench configuration itself: the frames the CPU arm has just rendered with the reference
         # kernel (same seeds, same accumulation from a black image) against the same frames on the GPU, bit for bit
-        sys.path.insert(0, os.path.join(ROOT, "tests"))
-        import helpers as Hh
         verify = {"frames": cpu_frames, "pixels": W * H, "against": "the CPU arm's %s kernel, all four channels" % cpu_baseline["kind"]}
         for mode, name in ((args.traversal, "as_timed"), (0, "reference_order_walk")):
             r.set_traversal(mode)
             r.reset_sample_count()
             r.render_frames(cpu_frames)
             gpu_image = r.read_image()
-            verify[name] = {"bit_identical_pixels": Hh.count_identical_pixels(gpu_image, cpu_image),
-                            "mre": Hh.mean_relative_error(gpu_image, cpu_image),
+            verify[name] = {"bit_identical_pixels": count_identical_pixels(gpu_image, cpu_image),
+                            "mre": mean_relative_error(gpu_image, cpu_image),
                             "walk": WALK_NAMES[int(dev.traversalInfo()["last_used"])]}
         r.set_traversal(args.traversal)
 
@@ -505,8 +517,6 @@ def run_ours(args):
 def strong_scaling(torch, dist, world, rank, r, dev, W, H, spp, steps, max_over_ranks, sum_over_ranks, name, already_stripes):
     """ONE image rendered by all ranks together: every frame's rows sharded in interleaved stripes, completed with one
     all-gather per frame (bit-identical to one GPU) -- against the same frames rendered by rank 0 alone."""
-    sys.path.insert(0, os.path.join(ROOT, "tests"))
-    import helpers as Hh
     sharding = "stripes" if H % world == 0 else "rows"
     if not already_stripes:
         r.set_sharding(sharding)
@@ -536,7 +546,7 @@ def strong_scaling(torch, dist, world, rank, r, dev, W, H, spp, steps, max_over_
         whole = r.read_image()
         out.update({
             "one_gpu_ms_per_step": round(ms1 / steps, 3), "speedup": round(ms1 / ms, 3), "efficiency": round(ms1 / ms / world, 4),
-            "bit_identical_pixels": Hh.count_identical_pixels(shown, whole), "pixels": W * H,
+            "bit_identical_pixels": count_identical_pixels(shown, whole), "pixels": W * H,
         })
     dist.barrier()
     r.set_sharding(sharding)

@@ -149,3 +149,21 @@ def test_builder_refuses_what_the_ordered_walk_cannot_honour(oracle):
     two = leaf[prep.nodes[leaf, 7] != -1.0]
     refused(lambda n: n.__setitem__((two[0], 7), n[two[0], 3] + 2.0), "first + 1")
     refused(lambda n: n.__setitem__((leaf[7], 1), np.nan), "NaN")
+
+
+def test_model_many_objects_and_tied_centres(oracle):
+    """A grid in 64 objects (one tree per object under an object-level tree, centres tied everywhere) and the interior
+    scene (flat walls and floors, 34 objects): the collapse of per-object trees and of skip-ahead chains."""
+    import pbr_b200
+    grid = pbr_b200.scenes.displaced_grid(60, 58, patches=8)
+    prep = Hh.Prepared(grid, 64, 64, eye=(0.0, 1.2, 1.8), center=(0.0, 0.55, 1.0))
+    rays = rays_for(prep, 20000, 21, -1.0, 1.0, grid=(200, 120))
+    rays[-20000:, 1] = np.abs(rays[-20000:, 1]) * 0.5 + 0.3
+    st = check_scene(prep, rays)
+    assert st["wide_visits"] < st["strict_nodes"]
+    interior = pbr_b200.scenes.interior(detail=0.15)
+    prep = Hh.Prepared(interior, 64, 64, eye=(0.0, 1.4, 5.2), center=(0.0, 0.1, 1.0), bvh_kwargs=dict(skip_ahead_compare=0.2))
+    rays = rays_for(prep, 30000, 22, -3.5, 3.5, grid=(200, 120))
+    rays[-30000:, 1] = np.abs(rays[-30000:, 1]) * 0.8 + 0.05
+    st = check_scene(prep, rays)
+    assert st["insane_winners"] > 0            # flat floor / wall boxes: hits in front of their own leaf box do occur here

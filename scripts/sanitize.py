@@ -67,6 +67,14 @@ def main():
             ok = Hh.images_equal(got, want)
             bad += not ok
             print("%-18s %-16s %s" % (name, "batch", "same bits" if ok else "DIFFERENT"), flush=True)
+            # no debug image: frames in flight (four streams, deferred mix), single launches and a batch
+            dev.setDebugImage(False)
+            for label, run in (("in flight, single", lambda: ds.frames(2, host_roundtrip=False)), ("in flight, batch", lambda: ds.frames_batch(2))):
+                got, _ = run()
+                ok = Hh.images_equal(got, want)
+                bad += not ok
+                print("%-18s %-16s %s" % (name, label, "same bits" if ok else "DIFFERENT"), flush=True)
+            dev.setDebugImage(True)
             # rows [8, 24) only, then stripes of 4 rows for rank 1 of 2
             dev.setTile(8, 24)
             got, _ = ds.frames(2)

@@ -167,3 +167,30 @@ def test_model_many_objects_and_tied_centres(oracle):
     rays[-30000:, 1] = np.abs(rays[-30000:, 1]) * 0.8 + 0.05
     st = check_scene(prep, rays)
     assert st["insane_winners"] > 0            # flat floor / wall boxes: hits in front of their own leaf box do occur here
+
+
+def test_model_quantised_child_boxes_keep_the_result(oracle):
+    """Premise of the layout DESIGN.md §6 names as the next step (64-byte nodes: child boxes quantised conservatively,
+    the exact leaf box tested at the leaf): the hits stay those of the reference-order walk; only visits are added.
+    Flat, coplanar geometry included (hits within an ulp of their leaf box's tNear)."""
+    import pbr_b200
+    lib = model()
+    vp, ll, i32 = C.c_void_p, C.c_longlong, C.c_int
+    lib.wide_model_quant.argtypes = [vp, i32, vp, i32, vp, vp, ll, i32, i32, i32, vp]
+    lib.wide_model_quant.restype = i32
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    soup = Hh.Prepared(pbr_b200.scenes.soup(20000, seed=31), 64, 64, eye=(0.0, 0.0, 3.5))
+    flat = Hh.Prepared(flat_floor_scene(), 64, 64, eye=(0.3, 1.5, 3.0), center=(0.0, 0.2, 1.0))
+    for prep, rays in ((soup, rays_for(soup, 10000, 6, -1.0, 1.0)), (flat, rays_for(flat, 20000, 12, -1.9, 1.9))):
+        nodes = np.ascontiguousarray(prep.nodes, np.float32)
+        fv = np.ascontiguousarray(prep.facesV, np.uint32)
+        v4 = np.ascontiguousarray(prep.vertices4, np.float32)
+        rays = np.ascontiguousarray(rays, np.float32)
+        visits = []
+        for bits, pow2 in ((0, 0), (8, 0), (8, 1), (4, 1)):
+            st = np.zeros(6, np.int64)
+            assert lib.wide_model_quant(p(nodes), nodes.shape[0], p(fv), fv.shape[0], p(v4), p(rays), rays.shape[0], 21, bits, pow2, p(st)) == 0
+            assert st[5] == 0, (bits, pow2, st.tolist())
+            visits.append(int(st[0]))
+        assert visits[0] <= visits[1] <= visits[3]          # coarser boxes only add visits
+        assert visits[1] < visits[0] * 1.1                  # and 8 bits add few

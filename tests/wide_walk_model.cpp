@@ -192,6 +192,101 @@ Hit fastWalk(const Scene& S, const wbvh::Result& W, V3 o, V3 d, float rt0, int s
 	return {rt, face, leaf, nn, nt};
 }
 
+
+/* EXPERIMENT (scripts/quant_nodes_stats.py; DESIGN.md §6 "where the next factor is"): the ordered walk on child boxes
+ * quantised to `bits` bits per plane relative to the union of the node's children (64-byte nodes), conservative (lo
+ * rounded down, hi up; power-of-two grid steps when pow2).  The exact leaf box would move next to the leaf's faces: a
+ * leaf item first repeats the box test on the exact bits (its tNear feeds the triangle test, pt_intersect.cl:96), so
+ * the candidates -- and with them the result -- are those of the exact walk; only the visits change. */
+struct QuantStats { uint64_t inner = 0, leaves = 0, leavesRejected = 0, tris = 0, fallbacks = 0, mismatches = 0; };
+
+void quantBox(const wbvh::Node& N, int j, int bits, bool pow2, float* lo, float* hi) {
+	const float steps = (float) ((1 << bits) - 1);
+	for (int a = 0; a < 3; a++) {
+		float flo = INFINITY, fhi = -INFINITY;
+		for (int k = 0; k < 4; k++) {
+			if (N.c[k].ref == wbvh::REF_EMPTY) continue;
+			flo = fminf(flo, N.c[k].lo(a)); fhi = fmaxf(fhi, N.c[k].hi(a));
+		}
+		double step = ((double) fhi - (double) flo) / steps;
+		if (pow2 && step > 0.0) step = exp2(ceil(log2(step)));
+		if (!(step > 0.0)) { lo[a] = N.c[j].lo(a); hi[a] = N.c[j].hi(a); continue; }
+		double ql = floor(((double) N.c[j].lo(a) - flo) / step), qh = ceil(((double) N.c[j].hi(a) - flo) / step);
+		float l = (float) (flo + ql * step), h = (float) (flo + qh * step);
+		while (l > N.c[j].lo(a)) l = nextafterf(l, -INFINITY);
+		while (h < N.c[j].hi(a)) h = nextafterf(h, INFINITY);
+		lo[a] = l; hi[a] = h;
+	}
+}
+
+Hit quantWalk(const Scene& S, const wbvh::Result& W, V3 o, V3 d, float rt0, int bits, bool pow2, QuantStats& st) {
+	const V3 inv = {pm::rcp(d.x), pm::rcp(d.y), pm::rcp(d.z)};
+	float rt = rt0, bestTn = -INFINITY, t2 = rt0;
+	int face = 0, leaf = -1;
+	std::vector<std::pair<int, float>> stack;
+	int item = 0;
+	bool have = !W.nodes.empty();
+	float lim = pruneLimit(rt);
+	auto pop = [&]() {
+		have = false;
+		while (!stack.empty()) {
+			const std::pair<int, float> e = stack.back();
+			stack.pop_back();
+			if (e.second <= lim) { item = e.first; have = true; break; }
+		}
+	};
+	while (have) {
+		if (item >= 0) {
+			st.inner++;
+			const wbvh::Node& N = W.nodes[(size_t) item];
+			int refs[4], n = 0;
+			float tns[4];
+			for (int j = 0; j < 4; j++) {
+				if (N.c[j].ref == wbvh::REF_EMPTY) continue;
+				float lo[3], hi[3], tNear, tFar;
+				if (bits > 0) quantBox(N, j, bits, pow2, lo, hi);
+				else for (int a = 0; a < 3; a++) { lo[a] = N.c[j].lo(a); hi[a] = N.c[j].hi(a); }
+				const bool hit = intersectBox(o, inv, lo, hi, tNear, tFar) && tFar > EPS5;
+				if (!(hit && tNear <= lim && tNear < INFINITY)) continue;
+				int k = n++;
+				while (k > 0 && tns[k - 1] > tNear) { tns[k] = tns[k - 1]; refs[k] = refs[k - 1]; k--; }
+				tns[k] = tNear; refs[k] = N.c[j].ref;
+			}
+			for (int k = n - 1; k >= 1; k--) stack.push_back({refs[k], tns[k]});
+			if (n > 0) item = refs[0];
+			else pop();
+		}
+		else {
+			st.leaves++;
+			const int f0 = (int) ((uint32_t) item & wbvh::REF_FACE_MASK);
+			/* the exact leaf box, as the leaf record would carry it */
+			const float* lo = S.nodes + 8 * (size_t) W.faceLeaf[(size_t) f0];
+			float tNear, tFar;
+			const bool hit = intersectBox(o, inv, lo, lo + 4, tNear, tFar) && tFar > EPS5 && tNear <= lim && tNear < INFINITY;
+			if (!hit) { st.leavesRejected++; pop(); continue; }
+			float tl = faceT(S, f0, o, d, tNear, INFINITY);
+			int fl = f0;
+			st.tris++;
+			if ((uint32_t) item & wbvh::REF_TWO) {
+				const float t1 = faceT(S, f0 + 1, o, d, tNear, INFINITY);
+				st.tris++;
+				if (t1 < tl) { tl = t1; fl = f0 + 1; }
+			}
+			if (tl < INFINITY) {
+				if (tl < rt || (tl == rt && leaf >= 0 && fl < face)) {
+					t2 = fminf(t2, rt);
+					rt = tl; face = fl; leaf = W.faceLeaf[(size_t) fl]; bestTn = tNear;
+				}
+				else t2 = fminf(t2, tl);
+				lim = pruneLimit(rt);
+			}
+			pop();
+		}
+	}
+	if (rt < bestTn && t2 <= bestTn) { st.fallbacks++; return strictWalk(S, o, d, rt0); }
+	return {rt, face, leaf, 0, 0};
+}
+
 } /* namespace */
 
 extern "C" {
@@ -227,6 +322,26 @@ int wide_model_run(const float* nodes, int numNodes, const uint32_t* facesV, int
 	stats[5] = sn; stats[6] = stt; stats[7] = (long long) st.wideVisits; stats[8] = (long long) st.triTests;
 	stats[9] = (long long) st.fallbacks; stats[10] = (long long) st.overflow; stats[11] = (long long) st.insaneWinners;
 	stats[12] = st.maxStack; stats[13] = mism;
+	return 0;
+}
+
+/* stats: inner visits, leaf visits, leaf visits the exact box rejects, triangle tests, re-walks, mismatches against the
+ * reference-order walk.  bits = 0: the exact boxes (the walk as shipped, leaf box test repeated at the leaf). */
+int wide_model_quant(const float* nodes, int numNodes, const uint32_t* facesV, int numFaces, const float* vertices,
+                     const float* rays, long long n, int topBudget, int bits, int pow2, long long* stats) {
+	const wbvh::Result W = wbvh::build(nodes, numNodes, numFaces, topBudget);
+	if (!W.ok) return 1;
+	const Scene S = {nodes, numNodes, facesV, numFaces, vertices};
+	QuantStats st;
+	for (long long i = 0; i < n; i++) {
+		const float* r = rays + 8 * i;
+		const V3 o = {r[0], r[1], r[2]}, d = {r[4], r[5], r[6]};
+		const Hit a = strictWalk(S, o, d, r[7]);
+		const Hit b = quantWalk(S, W, o, d, r[7], bits, pow2 != 0, st);
+		if (memcmp(&a.t, &b.t, 4) != 0 || a.face != b.face || a.leaf != b.leaf) st.mismatches++;
+	}
+	stats[0] = (long long) st.inner; stats[1] = (long long) st.leaves; stats[2] = (long long) st.leavesRejected;
+	stats[3] = (long long) st.tris; stats[4] = (long long) st.fallbacks; stats[5] = (long long) st.mismatches;
 	return 0;
 }
 
